@@ -1,0 +1,176 @@
+/* changa_b200_api.h -- entry points of the B200 gravity library.
+ *
+ * PART 1 declares, with C++ linkage and the reference's exact signatures, the
+ * free functions ChaNGa's Charm++ host code calls (so TreePiece / DataManager
+ * / Compute / Ewald link against this library unchanged).  Each one names the
+ * reference declaration it replaces and its call sites.
+ *
+ * PART 2 is the same surface as a plain C ABI (`extern "C"`, cb200_ prefix,
+ * pointers and sizes only) for FFI users (ctypes, cgo, JNI ...), plus the
+ * pieces that have no reference analogue: device moment build, SFC bucket
+ * partitioner, library/runtime introspection.
+ *
+ * Error convention (reference: HostCUDA.cu:39-47): every function returns
+ * void; a CUDA failure prints "Fatal CUDA Error ..." to stderr and abort()s.
+ * Completion is signalled through hapiAddCallback(stream, cb) exactly where
+ * the reference does it; standalone builds route that to
+ * cb200_set_callback_handler().
+ */
+#ifndef CHANGA_B200_API_H
+#define CHANGA_B200_API_H
+
+#include "changa_b200_types.h"
+
+/* ======================= PART 1: reference-compatible ==================== */
+#ifdef __cplusplus
+
+/* HostCUDA.h:99-100; callers Compute.cpp:1061-1064,1153-1156,2045-2054,
+ * DataManager.cpp:513-515,847-848,970.  size==0 asserts, like the reference. */
+void allocatePinnedHostMemory(void **ptr, size_t size);
+void freePinnedHostMemory(void *ptr);
+
+/* HostCUDA.h:102-107; caller DataManager.cpp:903.  Uploads the node-level
+ * tree, returns three device arrays the CALLER later cudaFree()s
+ * (DataManager.cpp:992-996), leaves d_varParts zeroed for numParticles rows. */
+void DataManagerTransferLocalTree(void *moments, size_t sMoments,
+                                  void *compactParts, size_t sCompactParts,
+                                  void *varParts, size_t sVarParts,
+                                  void **d_localMoments, void **d_compactParts,
+                                  void **d_varParts, cudaStream_t stream,
+                                  int numParticles, void *callback);
+
+/* HostCUDA.h:108-112; caller DataManager.cpp:590. */
+void DataManagerTransferRemoteChunk(void *moments, size_t sMoments,
+                                    void *compactParts, size_t sCompactParts,
+                                    void **d_remoteMoments, void **d_remoteParts,
+                                    cudaStream_t stream, void *callback);
+
+/* HostCUDA.h:114; caller DataManager.cpp:986. */
+void TransferParticleVarsBack(VariablePartData *hostBuffer, size_t size,
+                              void *d_varParts, cudaStream_t stream, void *cb);
+
+/* HostCUDA.h:116-118; callers Compute.cpp:2133,2139,2151 (particle-cell). */
+void TreePieceCellListDataTransferLocal(CudaRequest *data);
+void TreePieceCellListDataTransferRemote(CudaRequest *data);
+void TreePieceCellListDataTransferRemoteResume(CudaRequest *data);
+
+/* HostCUDA.h:121-124; callers Compute.cpp:2228,2233,2241,2253 (particle-particle). */
+void TreePiecePartListDataTransferLocal(CudaRequest *data);
+void TreePiecePartListDataTransferLocalSmallPhase(CudaRequest *data,
+                                                  CompactPartData *parts, int len);
+void TreePiecePartListDataTransferRemote(CudaRequest *data);
+void TreePiecePartListDataTransferRemoteResume(CudaRequest *data);
+
+/* CudaFunctions.h:7-8.  Kept for ABI completeness; the library itself no
+ * longer allocates per request (see DESIGN.md "device arena"). */
+void TreePieceDataTransferBasic(CudaRequest *data, CudaDevPtr *ptr);
+void TreePieceDataTransferBasicCleanup(CudaDevPtr *ptr);
+
+/* EwaldCUDA.h:59-62; callers Ewald.cpp:403,527,539. */
+void EwaldHostMemorySetup(EwaldData *h_idata, int size, int nEwhLoop, int largephase);
+void EwaldHostMemoryFree(EwaldData *h_idata, int largephase);
+void EwaldHost(CompactPartData *d_localParts, VariablePartData *d_localVars,
+               EwaldData *h_idata, cudaStream_t stream, void *cb, int myIndex,
+               int largephase);
+
+extern "C" {
+#endif /* __cplusplus */
+
+/* ============================ PART 2: C ABI ============================== */
+
+/* --- introspection ------------------------------------------------------- */
+int cb200_abi_version(void);          /* bumps when a signature changes      */
+int cb200_real_bytes(void);           /* sizeof(cudatype): 4, or 8 in FP64   */
+const char *cb200_build_info(void);   /* arch, flags, kernel variants        */
+
+/* completion tokens: standalone stand-in for Charm++ HAPI.  handler(cb) runs
+ * on a CUDA host-callback thread once the stream reaches the signal point. */
+typedef void (*cb200_callback_fn)(void *cb);
+void cb200_set_callback_handler(cb200_callback_fn handler);
+
+/* streams for FFI users that cannot create a cudaStream_t themselves */
+void *cb200_stream_create(void);
+void cb200_stream_destroy(void *stream);
+void cb200_stream_synchronize(void *stream);
+void cb200_device_synchronize(void);
+void cb200_set_device(int ordinal);
+void cb200_device_free(void *dptr);   /* what DataManager's cudaFree() does  */
+
+/* --- the reference surface, one-to-one ------------------------------------ */
+void cb200_allocatePinnedHostMemory(void **ptr, size_t size);
+void cb200_freePinnedHostMemory(void *ptr);
+void cb200_DataManagerTransferLocalTree(void *moments, size_t sMoments,
+                                        void *compactParts, size_t sCompactParts,
+                                        void *varParts, size_t sVarParts,
+                                        void **d_localMoments, void **d_compactParts,
+                                        void **d_varParts, void *stream,
+                                        int numParticles, void *callback);
+void cb200_DataManagerTransferRemoteChunk(void *moments, size_t sMoments,
+                                          void *compactParts, size_t sCompactParts,
+                                          void **d_remoteMoments, void **d_remoteParts,
+                                          void *stream, void *callback);
+void cb200_TransferParticleVarsBack(void *hostBuffer, size_t size, void *d_varParts,
+                                    void *stream, void *cb);
+void cb200_TreePieceCellListDataTransferLocal(CudaRequest *data);
+void cb200_TreePieceCellListDataTransferRemote(CudaRequest *data);
+void cb200_TreePieceCellListDataTransferRemoteResume(CudaRequest *data);
+void cb200_TreePiecePartListDataTransferLocal(CudaRequest *data);
+void cb200_TreePiecePartListDataTransferLocalSmallPhase(CudaRequest *data,
+                                                        CompactPartData *parts, int len);
+void cb200_TreePiecePartListDataTransferRemote(CudaRequest *data);
+void cb200_TreePiecePartListDataTransferRemoteResume(CudaRequest *data);
+void cb200_EwaldHostMemorySetup(EwaldData *h_idata, int size, int nEwhLoop, int largephase);
+void cb200_EwaldHostMemoryFree(EwaldData *h_idata, int largephase);
+void cb200_EwaldHost(void *d_localParts, void *d_localVars, EwaldData *h_idata,
+                     void *stream, void *cb, int myIndex, int largephase);
+
+/* --- device-resident variants (inputs already in HBM) ---------------------
+ * Same kernels as the *ListDataTransfer* entry points, but the flattened
+ * list / markers / starts / sizes are device pointers: no H2D copy is issued.
+ * Used by the multi-GPU driver (lists built or staged on the device) and by
+ * bench.py's kernel-only timing.  `moments`/`sources` choose the gather array
+ * (local, remote chunk, or a missed-data buffer). */
+void cb200_cell_list_device(void *d_parts, void *d_vars, void *d_moments,
+                            const ILCell *d_list, const int *d_markers,
+                            const int *d_starts, const int *d_sizes,
+                            int numBuckets, cudatype fperiod, void *stream);
+void cb200_part_list_device(void *d_parts, void *d_vars, void *d_sources,
+                            const ILCell *d_list, const int *d_markers,
+                            const int *d_starts, const int *d_sizes,
+                            int numBuckets, cudatype fperiod, void *stream);
+void cb200_ewald_device(void *d_parts, void *d_vars, const int *d_markers,
+                        int nActive, const EwaldReadOnlyData *h_ro,
+                        const EwtData *h_ewt, void *stream);
+
+/* --- timing taps (CUDA events recorded around every kernel we launch) ------ */
+void cb200_timing_enable(int on);
+void cb200_timing_reset(void);
+/* out[0..2] = ms in p-c, p-p, Ewald kernels; out[3..5] = launches of each */
+void cb200_timing_read(double out[6]);
+long long cb200_kernel_launches(void);
+
+/* --- new: tree-moment build on the device (oracle = moments.c) -- */
+/* Leaves: per-bucket hexadecapole FMOMR about the bucket centre of mass,
+ * radius = farthest particle.  Internal nodes: children combined bottom-up,
+ * radius = farthest box corner.  Topology arrays are int32, nodes in BFS
+ * order (child index > parent index), child -1 = absent.  All math FP64;
+ * output converted to CudaMultipoleMoments (cudatype). */
+void cb200_build_moments(const double *d_pos_xyz, const double *d_mass,
+                         const double *d_soft, int numParticles,
+                         const int *d_child0, const int *d_child1,
+                         const int *d_firstPart, const int *d_lastPart,
+                         const double *d_boxlo_xyz, const double *d_boxhi_xyz,
+                         const int *d_levelStart, int numLevels, int numNodes,
+                         void *d_moments_out, double *d_moments_f64_out,
+                         void *stream);
+
+/* --- new: per-GPU bucket partitioner --------------------------- */
+/* Cuts numBuckets SFC-ordered buckets into nRanks contiguous ranges of equal
+ * summed cost; cuts[0]=0 .. cuts[nRanks]=numBuckets.  Host-side, O(n). */
+void cb200_partition_buckets(const double *cost, int numBuckets, int nRanks,
+                             int *cuts);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* CHANGA_B200_API_H */

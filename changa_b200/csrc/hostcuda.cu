@@ -1,0 +1,675 @@
+/* hostcuda.cu -- the host side of the B200 gravity library: the entry points
+ * ChaNGa's Charm++ code calls (include/changa_b200_api.h PART 1, same C++
+ * signatures as the reference's HostCUDA.h:99-126 / EwaldCUDA.h:59-62), their
+ * C-ABI twins (PART 2), and the runtime under them.
+ *
+ * What differs from the reference's HostCUDA.cu host code:
+ *   - no cudaMalloc / cudaFree per request (HostCUDA.cu:578-613 does 4 + 4,
+ *     cudaFree being device-synchronising): every transient buffer comes from
+ *     the device's stream-ordered memory pool (release threshold = keep
+ *     everything), one sub-allocated block per request, freed in stream order;
+ *   - moments and particles are re-laid out on the device at upload time
+ *     (device_layout.cuh) so the kernels can use 128-bit accesses;
+ *   - Ewald constants travel as a kernel argument, not through process-global
+ *     __constant__ symbols: the entry points are safe to call concurrently
+ *     from several threads on different streams;
+ *   - completion callbacks go to Charm++ HAPI when built inside ChaNGa
+ *     (-DCB200_WITH_CHARM_HAPI) and to a registered C handler otherwise.
+ *
+ * There is no CPU fallback: without a CUDA device every entry point aborts
+ * with the reference's "Fatal CUDA Error" message (HostCUDA.cu:39-47).
+ */
+#include <atomic>
+#include <cassert>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/changa_b200_api.h"
+#include "gravity_kernels.cuh"
+#include "moments_build.cuh"
+
+#ifdef CB200_WITH_CHARM_HAPI
+#include "hapi.h"
+#endif
+
+using namespace cb200;
+
+/* ------------------------------------------------------------- error policy */
+#define cudaChk(code) cb200_cuda_assert((code), __FILE__, __LINE__)
+static inline void cb200_cuda_assert(cudaError_t code, const char *file, int line) {
+  if (code != cudaSuccess) {
+    fprintf(stderr, "Fatal CUDA Error %s at %s:%d\n", cudaGetErrorString(code), file, line);
+    abort();
+  }
+}
+
+/* ------------------------------------------------------- completion callbacks */
+static std::atomic<cb200_callback_fn> g_handler{nullptr};
+
+#ifndef CB200_WITH_CHARM_HAPI
+static void CUDART_CB cb200_trampoline(void *cb) {
+  cb200_callback_fn h = g_handler.load(std::memory_order_acquire);
+  if (h) h(cb);
+}
+/* stand-in for Charm++'s hapiAddCallback(stream, cb): run the registered
+ * handler on a CUDA callback thread once the stream reaches this point */
+static void hapiAddCallback(cudaStream_t stream, void *cb) {
+  if (!cb || !g_handler.load(std::memory_order_acquire)) return;
+  cudaChk(cudaLaunchHostFunc(stream, cb200_trampoline, cb));
+}
+#endif
+
+/* --------------------------------------------------------- per-device state */
+struct DeviceInfo {
+  bool ready = false;
+  int sms = 0;
+};
+static DeviceInfo g_dev[64];
+static std::mutex g_devMutex;
+
+static const DeviceInfo &device_info() {
+  int dev = 0;
+  cudaChk(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  DeviceInfo &d = g_dev[dev];
+  if (!d.ready) {
+    std::lock_guard<std::mutex> lock(g_devMutex);
+    if (!d.ready) {
+      cudaChk(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+      cudaMemPool_t pool;
+      cudaChk(cudaDeviceGetDefaultMemPool(&pool, dev));
+      uint64_t keep = UINT64_MAX; /* the arena: never hand memory back to the driver */
+      cudaChk(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      d.ready = true;
+    }
+  }
+  return d;
+}
+
+static void *pool_alloc(size_t bytes, cudaStream_t stream) {
+  void *p = nullptr;
+  if (bytes == 0) return nullptr;
+  device_info();
+  cudaChk(cudaMallocAsync(&p, bytes, stream));
+  return p;
+}
+static void pool_free(void *p, cudaStream_t stream) {
+  if (p) cudaChk(cudaFreeAsync(p, stream));
+}
+
+/* ------------------------------------------------------------- timing taps */
+enum { TAP_CELL = 0, TAP_PART = 1, TAP_EWALD = 2, TAP_N = 3 };
+struct Tap { cudaEvent_t a, b; int kind; };
+static std::atomic<int> g_timing{0};
+static std::mutex g_tapMutex;
+static std::vector<Tap> g_taps;
+static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_kindLaunches[TAP_N];
+
+struct TapScope {
+  cudaStream_t stream;
+  Tap tap;
+  bool on;
+  TapScope(int kind, cudaStream_t s) : stream(s), on(g_timing.load() != 0) {
+    g_launches.fetch_add(1);
+    g_kindLaunches[kind].fetch_add(1);
+    if (!on) return;
+    tap.kind = kind;
+    cudaChk(cudaEventCreate(&tap.a));
+    cudaChk(cudaEventCreate(&tap.b));
+    cudaChk(cudaEventRecord(tap.a, stream));
+  }
+  ~TapScope() {
+    if (!on) return;
+    cudaChk(cudaEventRecord(tap.b, stream));
+    std::lock_guard<std::mutex> lock(g_tapMutex);
+    g_taps.push_back(tap);
+  }
+};
+
+/* ---------------------------------------------------------- kernel launchers */
+template <typename K>
+static int resident_ctas(K kernel, size_t smem) {
+  int n = 0;
+  cudaChk(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaChk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kListWarps * 32, smem));
+  return n > 0 ? n : 1;
+}
+
+static int list_grid(int nBuckets, int ctasPerSm) {
+  int need = (nBuckets + kListWarps - 1) / kListWarps;
+  int cap = device_info().sms * ctasPerSm; /* persistent: one wave, sized to the SM count */
+  return need < cap ? need : cap;
+}
+
+template <int PB, int MINB>
+static void launch_cell_list(const PackedPart *parts, VariablePartData *vars, const PackedCell *cells,
+                             const ILCell *list, const int *markers, const int *starts,
+                             const int *sizes, int nBuckets, real fperiod, unsigned *counter,
+                             cudaStream_t stream) {
+  static int ctas = resident_ctas(cell_list_kernel<PB, MINB>, cell_list_smem_bytes<PB>());
+  cell_list_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, cell_list_smem_bytes<PB>(), stream>>>(
+      parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter);
+  cudaChk(cudaPeekAtLastError());
+}
+
+template <int PB, int MINB>
+static void launch_part_list(const PackedPart *parts, VariablePartData *vars, const PackedPart *sources,
+                             const ILCell *list, const int *markers, const int *starts,
+                             const int *sizes, int nBuckets, real fperiod, unsigned *counter,
+                             cudaStream_t stream) {
+  static int ctas = resident_ctas(part_list_kernel<PB, MINB>, part_list_smem_bytes<PB>());
+  part_list_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, part_list_smem_bytes<PB>(), stream>>>(
+      parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter);
+  cudaChk(cudaPeekAtLastError());
+}
+
+/* maxBucket picks the register tile: targets per pass */
+static void dispatch_cell_list(int maxBucket, const PackedPart *parts, VariablePartData *vars,
+                               const PackedCell *cells, const ILCell *list, const int *markers,
+                               const int *starts, const int *sizes, int nBuckets, real fperiod,
+                               unsigned *counter, cudaStream_t stream) {
+  TapScope tap(TAP_CELL, stream);
+#ifdef CUDA_USE_DOUBLE
+  /* doubles take two registers each: 8 targets per pass is what fits in 255 */
+  (void)maxBucket;
+  launch_cell_list<8, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+#else
+  if (maxBucket <= 8)
+    launch_cell_list<8, 4>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else if (maxBucket <= 12)
+    launch_cell_list<12, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else
+    launch_cell_list<16, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+#endif
+}
+
+static void dispatch_part_list(int maxBucket, const PackedPart *parts, VariablePartData *vars,
+                               const PackedPart *sources, const ILCell *list, const int *markers,
+                               const int *starts, const int *sizes, int nBuckets, real fperiod,
+                               unsigned *counter, cudaStream_t stream) {
+  TapScope tap(TAP_PART, stream);
+#ifdef CUDA_USE_DOUBLE
+  (void)maxBucket;
+  launch_part_list<8, 2>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+#else
+  if (maxBucket <= 8)
+    launch_part_list<8, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else if (maxBucket <= 12)
+    launch_part_list<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else
+    launch_part_list<16, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+#endif
+}
+
+static void repack_cells(const void *d_raw, PackedCell *d_out, int n, cudaStream_t stream) {
+  if (n <= 0) return;
+  repack_cells_kernel<<<(n + 127) / 128, 128, 0, stream>>>((const real *)d_raw, d_out, n);
+  cudaChk(cudaPeekAtLastError());
+  g_launches.fetch_add(1);
+}
+static void repack_parts(const void *d_raw, PackedPart *d_out, int n, cudaStream_t stream) {
+  if (n <= 0) return;
+  repack_parts_kernel<<<(n + 255) / 256, 256, 0, stream>>>((const real *)d_raw, d_out, n);
+  cudaChk(cudaPeekAtLastError());
+  g_launches.fetch_add(1);
+}
+
+/* upload caller records into pool scratch, rewrite them into `packed` */
+static void upload_cells(const void *h_raw, size_t bytes, PackedCell *packed, cudaStream_t stream) {
+  int n = (int)(bytes / sizeof(CudaMultipoleMoments));
+  if (n == 0) return;
+  void *raw = pool_alloc(bytes, stream);
+  cudaChk(cudaMemcpyAsync(raw, h_raw, bytes, cudaMemcpyHostToDevice, stream));
+  repack_cells(raw, packed, n, stream);
+  pool_free(raw, stream);
+}
+static void upload_parts(const void *h_raw, size_t bytes, PackedPart *packed, cudaStream_t stream) {
+  int n = (int)(bytes / sizeof(CompactPartData));
+  if (n == 0) return;
+  void *raw = pool_alloc(bytes, stream);
+  cudaChk(cudaMemcpyAsync(raw, h_raw, bytes, cudaMemcpyHostToDevice, stream));
+  repack_parts(raw, packed, n, stream);
+  pool_free(raw, stream);
+}
+
+/* =================== PART 1: the reference's entry points ================== */
+
+void allocatePinnedHostMemory(void **ptr, size_t size) {
+  if (size <= 0) { /* HostCUDA.cu:67-74 */
+    *ptr = NULL;
+    fprintf(stderr, "allocatePinnedHostMemory: 0 size!\n");
+    assert(0);
+    return;
+  }
+#ifdef CB200_WITH_CHARM_HAPI
+  hapiMallocHost(ptr, size, true);
+#else
+  cudaChk(cudaHostAlloc(ptr, size, cudaHostAllocPortable));
+#endif
+}
+
+void freePinnedHostMemory(void *ptr) {
+  if (ptr == NULL) { /* HostCUDA.cu:87-92 */
+    fprintf(stderr, "freePinnedHostMemory: NULL ptr!\n");
+    assert(0);
+    return;
+  }
+#ifdef CB200_WITH_CHARM_HAPI
+  hapiFreeHost(ptr, true);
+#else
+  cudaChk(cudaFreeHost(ptr));
+#endif
+}
+
+void DataManagerTransferLocalTree(void *moments, size_t sMoments, void *compactParts,
+                                  size_t sCompactParts, void *varParts, size_t sVarParts,
+                                  void **d_localMoments, void **d_compactParts, void **d_varParts,
+                                  cudaStream_t stream, int numParticles, void *callback) {
+  const size_t nCells = sMoments / sizeof(CudaMultipoleMoments);
+  const size_t nParts = sCompactParts / sizeof(CompactPartData);
+  *d_localMoments = pool_alloc(nCells * sizeof(PackedCell), stream);
+  *d_compactParts = pool_alloc(nParts * sizeof(PackedPart), stream);
+  *d_varParts = pool_alloc(sVarParts, stream);
+  upload_cells(moments, sMoments, (PackedCell *)*d_localMoments, stream);
+  upload_parts(compactParts, sCompactParts, (PackedPart *)*d_compactParts, stream);
+  /* the accumulators start at zero whatever the host buffer holds
+   * (ZeroVars, HostCUDA.cu:141-143); rows past numParticles keep the
+   * caller's values like the reference's upload at :139 */
+  size_t zeroed = (size_t)numParticles * sizeof(VariablePartData);
+  if (zeroed > sVarParts) zeroed = sVarParts;
+  if (zeroed) cudaChk(cudaMemsetAsync(*d_varParts, 0, zeroed, stream));
+  if (sVarParts > zeroed)
+    cudaChk(cudaMemcpyAsync((char *)*d_varParts + zeroed, (char *)varParts + zeroed, sVarParts - zeroed,
+                            cudaMemcpyHostToDevice, stream));
+  hapiAddCallback(stream, callback);
+}
+
+void DataManagerTransferRemoteChunk(void *moments, size_t sMoments, void *remoteParts,
+                                    size_t sRemoteParts, void **d_remoteMoments,
+                                    void **d_remoteParts, cudaStream_t stream, void *callback) {
+  const size_t nCells = sMoments / sizeof(CudaMultipoleMoments);
+  const size_t nParts = sRemoteParts / sizeof(CompactPartData);
+  *d_remoteMoments = pool_alloc(nCells * sizeof(PackedCell), stream);
+  *d_remoteParts = pool_alloc(nParts * sizeof(PackedPart), stream);
+  upload_cells(moments, sMoments, (PackedCell *)*d_remoteMoments, stream);
+  upload_parts(remoteParts, sRemoteParts, (PackedPart *)*d_remoteParts, stream);
+  hapiAddCallback(stream, callback);
+}
+
+void TransferParticleVarsBack(VariablePartData *hostBuffer, size_t size, void *d_varParts,
+                              cudaStream_t stream, void *cb) {
+  if (size) cudaChk(cudaMemcpyAsync(hostBuffer, d_varParts, size, cudaMemcpyDeviceToHost, stream));
+  hapiAddCallback(stream, cb);
+}
+
+/* one request = one pool block: [counter | markers | starts | sizes | list | missed] */
+struct RequestScratch {
+  char *base = nullptr;
+  unsigned *counter = nullptr;
+  int *markers = nullptr, *starts = nullptr, *sizes = nullptr;
+  ILCell *list = nullptr;
+  void *missedPacked = nullptr;
+  void *missedRaw = nullptr;
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int max_bucket_size(const int *sizes, int n) {
+  int m = 0;
+  for (int i = 0; i < n; ++i) m = sizes[i] > m ? sizes[i] : m;
+  return m;
+}
+
+static RequestScratch stage_request(CudaRequest *data, size_t missedPackedBytes, size_t missedRawBytes) {
+  cudaStream_t stream = data->stream;
+  const int nb = data->numBucketsPlusOne - 1;
+  const size_t sList = (size_t)data->numInteractions * sizeof(ILCell);
+  const size_t sMark = (size_t)(nb + 1) * sizeof(int), sStart = (size_t)nb * sizeof(int);
+  size_t off = 0;
+  const size_t oCounter = off; off += 256;
+  const size_t oMark = off; off += align_up(sMark);
+  const size_t oStart = off; off += align_up(sStart);
+  const size_t oSize = off; off += align_up(sStart);
+  const size_t oList = off; off += align_up(sList);
+  const size_t oMissP = off; off += align_up(missedPackedBytes);
+  const size_t oMissR = off; off += align_up(missedRawBytes);
+  RequestScratch s;
+  s.base = (char *)pool_alloc(off, stream);
+  s.counter = (unsigned *)(s.base + oCounter);
+  s.markers = (int *)(s.base + oMark);
+  s.starts = (int *)(s.base + oStart);
+  s.sizes = (int *)(s.base + oSize);
+  s.list = (ILCell *)(s.base + oList);
+  s.missedPacked = s.base + oMissP;
+  s.missedRaw = s.base + oMissR;
+  cudaChk(cudaMemsetAsync(s.counter, 0, 256, stream));
+  cudaChk(cudaMemcpyAsync(s.markers, data->bucketMarkers, sMark, cudaMemcpyHostToDevice, stream));
+  if (sStart) {
+    cudaChk(cudaMemcpyAsync(s.starts, data->bucketStarts, sStart, cudaMemcpyHostToDevice, stream));
+    cudaChk(cudaMemcpyAsync(s.sizes, data->bucketSizes, sStart, cudaMemcpyHostToDevice, stream));
+  }
+  if (sList) cudaChk(cudaMemcpyAsync(s.list, data->list, sList, cudaMemcpyHostToDevice, stream));
+  return s;
+}
+
+enum Gather { G_LOCAL, G_REMOTE, G_MISSED };
+
+static void cell_list_request(CudaRequest *data, Gather g) {
+  cudaStream_t stream = data->stream;
+  const int nb = data->numBucketsPlusOne - 1;
+  if (nb <= 0) { hapiAddCallback(stream, data->cb); return; }
+  const size_t nMissed = (g == G_MISSED) ? data->sMissed / sizeof(CudaMultipoleMoments) : 0;
+  RequestScratch s = stage_request(data, nMissed * sizeof(PackedCell), (g == G_MISSED) ? data->sMissed : 0);
+  const PackedCell *cells = (const PackedCell *)(g == G_LOCAL ? data->d_localMoments : data->d_remoteMoments);
+  if (g == G_MISSED) { /* moments travel with the request (HostCUDA.cu:296-342) */
+    cudaChk(cudaMemcpyAsync(s.missedRaw, data->missedNodes, data->sMissed, cudaMemcpyHostToDevice, stream));
+    repack_cells(s.missedRaw, (PackedCell *)s.missedPacked, (int)nMissed, stream);
+    cells = (const PackedCell *)s.missedPacked;
+  }
+  dispatch_cell_list(max_bucket_size(data->bucketSizes, nb), (const PackedPart *)data->d_localParts,
+                     data->d_localVars, cells, s.list, s.markers, s.starts, s.sizes, nb, data->fperiod,
+                     s.counter, stream);
+  pool_free(s.base, stream);
+  hapiAddCallback(stream, data->cb);
+}
+
+static void part_list_request(CudaRequest *data, Gather g, const CompactPartData *h_small, int nSmall) {
+  cudaStream_t stream = data->stream;
+  const int nb = data->numBucketsPlusOne - 1;
+  if (nb <= 0) { hapiAddCallback(stream, data->cb); return; }
+  const void *h_extra = nullptr;
+  size_t sExtra = 0;
+  if (g == G_MISSED) { h_extra = h_small ? (const void *)h_small : data->missedParts;
+                       sExtra = h_small ? (size_t)nSmall * sizeof(CompactPartData) : data->sMissed; }
+  const size_t nExtra = sExtra / sizeof(CompactPartData);
+  RequestScratch s = stage_request(data, nExtra * sizeof(PackedPart), sExtra);
+  const PackedPart *src = (const PackedPart *)(g == G_LOCAL ? data->d_localParts : data->d_remoteParts);
+  if (g == G_MISSED) {
+    cudaChk(cudaMemcpyAsync(s.missedRaw, h_extra, sExtra, cudaMemcpyHostToDevice, stream));
+    repack_parts(s.missedRaw, (PackedPart *)s.missedPacked, (int)nExtra, stream);
+    src = (const PackedPart *)s.missedPacked;
+  }
+  dispatch_part_list(max_bucket_size(data->bucketSizes, nb), (const PackedPart *)data->d_localParts,
+                     data->d_localVars, src, s.list, s.markers, s.starts, s.sizes, nb, data->fperiod,
+                     s.counter, stream);
+  pool_free(s.base, stream);
+  hapiAddCallback(stream, data->cb);
+}
+
+void TreePieceCellListDataTransferLocal(CudaRequest *data) { cell_list_request(data, G_LOCAL); }
+void TreePieceCellListDataTransferRemote(CudaRequest *data) { cell_list_request(data, G_REMOTE); }
+void TreePieceCellListDataTransferRemoteResume(CudaRequest *data) { cell_list_request(data, G_MISSED); }
+
+void TreePiecePartListDataTransferLocal(CudaRequest *data) { part_list_request(data, G_LOCAL, nullptr, 0); }
+void TreePiecePartListDataTransferRemote(CudaRequest *data) { part_list_request(data, G_REMOTE, nullptr, 0); }
+void TreePiecePartListDataTransferRemoteResume(CudaRequest *data) { part_list_request(data, G_MISSED, nullptr, 0); }
+/* sources are an ad-hoc host array shipped with the request (HostCUDA.cu:345-408) */
+void TreePiecePartListDataTransferLocalSmallPhase(CudaRequest *data, CompactPartData *parts, int len) {
+  part_list_request(data, G_MISSED, parts, len);
+}
+
+/* CudaFunctions.h:7-8 -- kept for callers that stage a request themselves */
+void TreePieceDataTransferBasic(CudaRequest *data, CudaDevPtr *ptr) {
+  cudaStream_t stream = data->stream;
+  const int nb = data->numBucketsPlusOne - 1;
+  const size_t sList = (size_t)data->numInteractions * sizeof(ILCell);
+  const size_t sMark = (size_t)(nb + 1) * sizeof(int), sStart = (size_t)nb * sizeof(int);
+  ptr->d_list = pool_alloc(sList, stream);
+  ptr->d_bucketMarkers = (int *)pool_alloc(sMark, stream);
+  ptr->d_bucketStarts = (int *)pool_alloc(sStart, stream);
+  ptr->d_bucketSizes = (int *)pool_alloc(sStart, stream);
+  if (sList) cudaChk(cudaMemcpyAsync(ptr->d_list, data->list, sList, cudaMemcpyHostToDevice, stream));
+  cudaChk(cudaMemcpyAsync(ptr->d_bucketMarkers, data->bucketMarkers, sMark, cudaMemcpyHostToDevice, stream));
+  if (sStart) {
+    cudaChk(cudaMemcpyAsync(ptr->d_bucketStarts, data->bucketStarts, sStart, cudaMemcpyHostToDevice, stream));
+    cudaChk(cudaMemcpyAsync(ptr->d_bucketSizes, data->bucketSizes, sStart, cudaMemcpyHostToDevice, stream));
+  }
+}
+void TreePieceDataTransferBasicCleanup(CudaDevPtr *ptr) {
+  cudaChk(cudaFree(ptr->d_list));
+  cudaChk(cudaFree(ptr->d_bucketMarkers));
+  cudaChk(cudaFree(ptr->d_bucketStarts));
+  cudaChk(cudaFree(ptr->d_bucketSizes));
+}
+
+/* ------------------------------------------------------------------ Ewald */
+void EwaldHostMemorySetup(EwaldData *h_idata, int nParticles, int nEwhLoop, int largephase) {
+  if (largephase)
+    allocatePinnedHostMemory((void **)&(h_idata->EwaldMarkers), (size_t)nParticles * sizeof(int));
+  else
+    h_idata->EwaldMarkers = NULL;
+  allocatePinnedHostMemory((void **)&(h_idata->ewt), (size_t)nEwhLoop * sizeof(EwtData));
+  allocatePinnedHostMemory((void **)&(h_idata->cachedData), sizeof(EwaldReadOnlyData));
+}
+
+void EwaldHostMemoryFree(EwaldData *h_idata, int largephase) {
+  if (largephase) freePinnedHostMemory(h_idata->EwaldMarkers);
+  freePinnedHostMemory(h_idata->ewt);
+  freePinnedHostMemory(h_idata->cachedData);
+}
+
+static void launch_ewald(const PackedPart *parts, VariablePartData *vars, const int *d_markers,
+                         int first, int last, int n, const EwaldReadOnlyData *ro, const EwtData *ewt,
+                         cudaStream_t stream) {
+  if (n <= 0) return;
+  assert(ro->nEwhLoop <= NEWH); /* HostCUDA.cu:1923 */
+  EwaldParams P;
+  memset(&P, 0, sizeof P);
+  P.ro = *ro;
+  memcpy(P.ewt, ewt, (size_t)ro->nEwhLoop * sizeof(EwtData));
+  TapScope tap(TAP_EWALD, stream);
+  ewald_kernel<<<(n + kEwaldThreads - 1) / kEwaldThreads, kEwaldThreads, 0, stream>>>(parts, vars, d_markers,
+                                                                                    first, last, P);
+  cudaChk(cudaPeekAtLastError());
+}
+
+void EwaldHost(CompactPartData *d_localParts, VariablePartData *d_localVars, EwaldData *h_idata,
+               cudaStream_t stream, void *cb, int myIndex, int largephase) {
+  (void)myIndex;
+  const int n = h_idata->cachedData->n;
+  int *d_markers = nullptr;
+  if (largephase && n > 0) {
+    d_markers = (int *)pool_alloc((size_t)n * sizeof(int), stream);
+    cudaChk(cudaMemcpyAsync(d_markers, h_idata->EwaldMarkers, (size_t)n * sizeof(int),
+                            cudaMemcpyHostToDevice, stream));
+  }
+  if (!largephase || d_markers)
+    launch_ewald((const PackedPart *)d_localParts, d_localVars, d_markers, h_idata->EwaldRange[0],
+                 h_idata->EwaldRange[1], n, h_idata->cachedData, h_idata->ewt, stream);
+  pool_free(d_markers, stream);
+  hapiAddCallback(stream, cb);
+}
+
+/* ============================ PART 2: the C ABI ============================ */
+extern "C" {
+
+int cb200_abi_version(void) { return 1; }
+int cb200_real_bytes(void) { return (int)sizeof(cudatype); }
+const char *cb200_build_info(void) {
+#ifdef CUDA_USE_DOUBLE
+  return "changa_b200 sm_100a real=f64 hexadecapole kernels: cell_list{8} part_list{8} ewald moments";
+#else
+  return "changa_b200 sm_100a real=f32 hexadecapole kernels: cell_list{8,12,16} part_list{8,12,16} ewald moments";
+#endif
+}
+
+void cb200_set_callback_handler(cb200_callback_fn handler) { g_handler.store(handler, std::memory_order_release); }
+
+void *cb200_stream_create(void) {
+  cudaStream_t s;
+  cudaChk(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return (void *)s;
+}
+void cb200_stream_destroy(void *stream) { cudaChk(cudaStreamDestroy((cudaStream_t)stream)); }
+void cb200_stream_synchronize(void *stream) { cudaChk(cudaStreamSynchronize((cudaStream_t)stream)); }
+void cb200_device_synchronize(void) { cudaChk(cudaDeviceSynchronize()); }
+void cb200_set_device(int ordinal) { cudaChk(cudaSetDevice(ordinal)); }
+void cb200_device_free(void *dptr) { cudaChk(cudaFree(dptr)); }
+
+void cb200_allocatePinnedHostMemory(void **ptr, size_t size) { allocatePinnedHostMemory(ptr, size); }
+void cb200_freePinnedHostMemory(void *ptr) { freePinnedHostMemory(ptr); }
+void cb200_DataManagerTransferLocalTree(void *moments, size_t sMoments, void *compactParts,
+                                        size_t sCompactParts, void *varParts, size_t sVarParts,
+                                        void **d_localMoments, void **d_compactParts, void **d_varParts,
+                                        void *stream, int numParticles, void *callback) {
+  DataManagerTransferLocalTree(moments, sMoments, compactParts, sCompactParts, varParts, sVarParts,
+                               d_localMoments, d_compactParts, d_varParts, (cudaStream_t)stream,
+                               numParticles, callback);
+}
+void cb200_DataManagerTransferRemoteChunk(void *moments, size_t sMoments, void *compactParts,
+                                          size_t sCompactParts, void **d_remoteMoments,
+                                          void **d_remoteParts, void *stream, void *callback) {
+  DataManagerTransferRemoteChunk(moments, sMoments, compactParts, sCompactParts, d_remoteMoments,
+                                 d_remoteParts, (cudaStream_t)stream, callback);
+}
+void cb200_TransferParticleVarsBack(void *hostBuffer, size_t size, void *d_varParts, void *stream, void *cb) {
+  TransferParticleVarsBack((VariablePartData *)hostBuffer, size, d_varParts, (cudaStream_t)stream, cb);
+}
+void cb200_TreePieceCellListDataTransferLocal(CudaRequest *d) { TreePieceCellListDataTransferLocal(d); }
+void cb200_TreePieceCellListDataTransferRemote(CudaRequest *d) { TreePieceCellListDataTransferRemote(d); }
+void cb200_TreePieceCellListDataTransferRemoteResume(CudaRequest *d) { TreePieceCellListDataTransferRemoteResume(d); }
+void cb200_TreePiecePartListDataTransferLocal(CudaRequest *d) { TreePiecePartListDataTransferLocal(d); }
+void cb200_TreePiecePartListDataTransferLocalSmallPhase(CudaRequest *d, CompactPartData *parts, int len) {
+  TreePiecePartListDataTransferLocalSmallPhase(d, parts, len);
+}
+void cb200_TreePiecePartListDataTransferRemote(CudaRequest *d) { TreePiecePartListDataTransferRemote(d); }
+void cb200_TreePiecePartListDataTransferRemoteResume(CudaRequest *d) { TreePiecePartListDataTransferRemoteResume(d); }
+void cb200_EwaldHostMemorySetup(EwaldData *h, int size, int nEwhLoop, int largephase) {
+  EwaldHostMemorySetup(h, size, nEwhLoop, largephase);
+}
+void cb200_EwaldHostMemoryFree(EwaldData *h, int largephase) { EwaldHostMemoryFree(h, largephase); }
+void cb200_EwaldHost(void *d_localParts, void *d_localVars, EwaldData *h, void *stream, void *cb,
+                     int myIndex, int largephase) {
+  EwaldHost((CompactPartData *)d_localParts, (VariablePartData *)d_localVars, h, (cudaStream_t)stream, cb,
+            myIndex, largephase);
+}
+
+/* ---- device-resident variants: lists already in HBM, no copy issued ---- */
+static int device_max_bucket(const int *d_sizes, int n, int hint) {
+  (void)d_sizes; (void)n;
+  return hint > 0 ? hint : 16; /* unknown: the widest register tile handles any size */
+}
+
+void cb200_cell_list_device(void *d_parts, void *d_vars, void *d_moments, const ILCell *d_list,
+                            const int *d_markers, const int *d_starts, const int *d_sizes,
+                            int numBuckets, cudatype fperiod, void *stream) {
+  cb200_cell_list_device_ex(d_parts, d_vars, d_moments, d_list, d_markers, d_starts, d_sizes, numBuckets,
+                            fperiod, 0, stream);
+}
+void cb200_cell_list_device_ex(void *d_parts, void *d_vars, void *d_moments, const ILCell *d_list,
+                               const int *d_markers, const int *d_starts, const int *d_sizes,
+                               int numBuckets, cudatype fperiod, int maxBucketSize, void *stream) {
+  if (numBuckets <= 0) return;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned *counter = (unsigned *)pool_alloc(256, s);
+  cudaChk(cudaMemsetAsync(counter, 0, 256, s));
+  dispatch_cell_list(device_max_bucket(d_sizes, numBuckets, maxBucketSize), (const PackedPart *)d_parts,
+                     (VariablePartData *)d_vars, (const PackedCell *)d_moments, d_list, d_markers, d_starts,
+                     d_sizes, numBuckets, fperiod, counter, s);
+  pool_free(counter, s);
+}
+void cb200_part_list_device(void *d_parts, void *d_vars, void *d_sources, const ILCell *d_list,
+                            const int *d_markers, const int *d_starts, const int *d_sizes,
+                            int numBuckets, cudatype fperiod, void *stream) {
+  cb200_part_list_device_ex(d_parts, d_vars, d_sources, d_list, d_markers, d_starts, d_sizes, numBuckets,
+                            fperiod, 0, stream);
+}
+void cb200_part_list_device_ex(void *d_parts, void *d_vars, void *d_sources, const ILCell *d_list,
+                               const int *d_markers, const int *d_starts, const int *d_sizes,
+                               int numBuckets, cudatype fperiod, int maxBucketSize, void *stream) {
+  if (numBuckets <= 0) return;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned *counter = (unsigned *)pool_alloc(256, s);
+  cudaChk(cudaMemsetAsync(counter, 0, 256, s));
+  dispatch_part_list(device_max_bucket(d_sizes, numBuckets, maxBucketSize), (const PackedPart *)d_parts,
+                     (VariablePartData *)d_vars, (const PackedPart *)d_sources, d_list, d_markers, d_starts,
+                     d_sizes, numBuckets, fperiod, counter, s);
+  pool_free(counter, s);
+}
+void cb200_ewald_device(void *d_parts, void *d_vars, const int *d_markers, int nActive,
+                        const EwaldReadOnlyData *h_ro, const EwtData *h_ewt, void *stream) {
+  launch_ewald((const PackedPart *)d_parts, (VariablePartData *)d_vars, d_markers, 0, nActive - 1, nActive,
+               h_ro, h_ewt, (cudaStream_t)stream);
+}
+
+/* layout conversion for callers that keep their own device arrays (multi-GPU
+ * driver: records arrive by all-gather, not from the host) */
+void cb200_pack_moments_device(const void *d_raw, void *d_packed, int n, void *stream) {
+  repack_cells(d_raw, (PackedCell *)d_packed, n, (cudaStream_t)stream);
+}
+void cb200_pack_particles_device(const void *d_raw, void *d_packed, int n, void *stream) {
+  repack_parts(d_raw, (PackedPart *)d_packed, n, (cudaStream_t)stream);
+}
+size_t cb200_packed_moment_bytes(void) { return sizeof(PackedCell); }
+size_t cb200_packed_particle_bytes(void) { return sizeof(PackedPart); }
+
+/* ---- timing taps ---- */
+void cb200_timing_enable(int on) { g_timing.store(on); }
+void cb200_timing_reset(void) {
+  std::lock_guard<std::mutex> lock(g_tapMutex);
+  for (Tap &t : g_taps) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  g_taps.clear();
+  for (int k = 0; k < TAP_N; ++k) g_kindLaunches[k].store(0);
+}
+void cb200_timing_read(double out[6]) {
+  std::lock_guard<std::mutex> lock(g_tapMutex);
+  for (int k = 0; k < 6; ++k) out[k] = 0.0;
+  for (Tap &t : g_taps) {
+    float ms = 0.f;
+    cudaChk(cudaEventSynchronize(t.b));
+    cudaChk(cudaEventElapsedTime(&ms, t.a, t.b));
+    out[t.kind] += ms;
+  }
+  for (int k = 0; k < TAP_N; ++k) out[3 + k] = (double)g_kindLaunches[k].load();
+}
+long long cb200_kernel_launches(void) { return g_launches.load(); }
+
+/* ---- device moment build ---- */
+void cb200_build_moments(const double *d_pos_xyz, const double *d_mass, const double *d_soft,
+                         int numParticles, const int *d_child0, const int *d_child1,
+                         const int *d_firstPart, const int *d_lastPart, const double *d_geolo_xyz,
+                         const double *d_geohi_xyz, const double *d_boxlo_xyz, const double *d_boxhi_xyz,
+                         const int *h_levelStart, int numLevels, int numNodes, void *d_moments_out,
+                         double *d_moments_f64_out, void *stream) {
+  (void)numParticles;
+  if (numNodes <= 0) return;
+  cudaStream_t s = (cudaStream_t)stream;
+  MomentNode *work = (MomentNode *)pool_alloc((size_t)numNodes * sizeof(MomentNode), s);
+  for (int lvl = numLevels - 1; lvl >= 0; --lvl) { /* bottom-up: children are on deeper levels */
+    const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
+    if (n <= 0) continue;
+    build_moments_level_kernel<<<(n + 63) / 64, 64, 0, s>>>(
+        d_pos_xyz, d_mass, d_soft, d_child0, d_child1, d_firstPart, d_lastPart, d_geolo_xyz, d_geohi_xyz,
+        d_boxlo_xyz, d_boxhi_xyz, lo, n, work, (real *)d_moments_out, d_moments_f64_out);
+    cudaChk(cudaPeekAtLastError());
+    g_launches.fetch_add(1);
+  }
+  pool_free(work, s);
+}
+
+/* ---- bucket partitioner: contiguous SFC ranges of equal cost ---- */
+void cb200_partition_buckets(const double *cost, int numBuckets, int nRanks, int *cuts) {
+  double total = 0.0;
+  for (int i = 0; i < numBuckets; ++i) total += cost[i];
+  cuts[0] = 0;
+  double run = 0.0;
+  int b = 0;
+  for (int r = 1; r < nRanks; ++r) {
+    const double target = total * r / nRanks;
+    /* advance while adding the next bucket keeps us at or below the target,
+     * or lands closer to it than stopping short would */
+    while (b < numBuckets && (run + cost[b] <= target || (target - run) > (run + cost[b] - target))) {
+      run += cost[b];
+      ++b;
+    }
+    cuts[r] = b;
+  }
+  cuts[nRanks] = numBuckets;
+}
+
+} /* extern "C" */

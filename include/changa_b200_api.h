@@ -138,9 +138,32 @@ void cb200_part_list_device(void *d_parts, void *d_vars, void *d_sources,
                             const ILCell *d_list, const int *d_markers,
                             const int *d_starts, const int *d_sizes,
                             int numBuckets, cudatype fperiod, void *stream);
+/* same, with the largest bucket size of the request stated by the caller (the
+ * host entry points scan CudaRequest::bucketSizes for it); it selects how many
+ * target particles a warp keeps in registers per pass.  0 = unknown. */
+void cb200_cell_list_device_ex(void *d_parts, void *d_vars, void *d_moments,
+                               const ILCell *d_list, const int *d_markers,
+                               const int *d_starts, const int *d_sizes,
+                               int numBuckets, cudatype fperiod, int maxBucketSize,
+                               void *stream);
+void cb200_part_list_device_ex(void *d_parts, void *d_vars, void *d_sources,
+                               const ILCell *d_list, const int *d_markers,
+                               const int *d_starts, const int *d_sizes,
+                               int numBuckets, cudatype fperiod, int maxBucketSize,
+                               void *stream);
 void cb200_ewald_device(void *d_parts, void *d_vars, const int *d_markers,
                         int nActive, const EwaldReadOnlyData *h_ro,
                         const EwtData *h_ewt, void *stream);
+
+/* device layout (DESIGN.md "data layout in HBM"): the d_localMoments /
+ * d_localParts handles returned by the transfer functions address arrays of
+ * packed rows, not the caller's AoS records.  Callers that fill device arrays
+ * themselves (multi-GPU driver: records arrive by NCCL all-gather) convert
+ * with these; d_raw holds CudaMultipoleMoments / CompactPartData records. */
+size_t cb200_packed_moment_bytes(void);   /* bytes per cell row      */
+size_t cb200_packed_particle_bytes(void); /* bytes per particle row  */
+void cb200_pack_moments_device(const void *d_raw, void *d_packed, int n, void *stream);
+void cb200_pack_particles_device(const void *d_raw, void *d_packed, int n, void *stream);
 
 /* --- timing taps (CUDA events recorded around every kernel we launch) ------ */
 void cb200_timing_enable(int on);
@@ -150,17 +173,22 @@ void cb200_timing_read(double out[6]);
 long long cb200_kernel_launches(void);
 
 /* --- new: tree-moment build on the device (oracle = moments.c) -- */
-/* Leaves: per-bucket hexadecapole FMOMR about the bucket centre of mass,
- * radius = farthest particle.  Internal nodes: children combined bottom-up,
- * radius = farthest box corner.  Topology arrays are int32, nodes in BFS
- * order (child index > parent index), child -1 = absent.  All math FP64;
- * output converted to CudaMultipoleMoments (cudatype). */
+/* Leaves: particles added in index order about the running centre of mass,
+ * radius = farthest particle.  Internal nodes: children combined bottom-up in
+ * order 0,1, radius = farthest corner of the node's bounding box.  Topology
+ * arrays are int32 device arrays, nodes in BFS order (child index > parent
+ * index, levels contiguous), child -1 = absent.  geo* = the box a bucket got
+ * from its parent's split (initial scale), box* = tight bounding boxes.
+ * h_levelStart is a HOST array of numLevels+1 node offsets.  All math FP64;
+ * d_moments_out receives CudaMultipoleMoments records (cudatype),
+ * d_moments_f64_out (optional) the same 27 values in double. */
 void cb200_build_moments(const double *d_pos_xyz, const double *d_mass,
                          const double *d_soft, int numParticles,
                          const int *d_child0, const int *d_child1,
                          const int *d_firstPart, const int *d_lastPart,
+                         const double *d_geolo_xyz, const double *d_geohi_xyz,
                          const double *d_boxlo_xyz, const double *d_boxhi_xyz,
-                         const int *d_levelStart, int numLevels, int numNodes,
+                         const int *h_levelStart, int numLevels, int numNodes,
                          void *d_moments_out, double *d_moments_f64_out,
                          void *stream);
 

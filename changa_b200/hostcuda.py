@@ -286,6 +286,13 @@ class ForceStep:
         self.vars_in.array[:] = 0
         self.cell = StagedLists(hc, *wl["cell"], NODE_INTERACTIONS_PER_REQUEST) if wl.get("cell") else None
         self.part = StagedLists(hc, *wl["part"], PART_INTERACTIONS_PER_REQUEST) if wl.get("part") else None
+        # softened cells (Compute.cpp:1683-1699): a p-p request whose sources travel with it
+        self.soft, self.soft_src = None, None
+        if wl.get("softcell"):
+            self.soft = StagedLists(hc, *wl["softcell"][:4], PART_INTERACTIONS_PER_REQUEST)
+            src = wl["softcell"][4]
+            self.soft_src = hc.allocatePinnedHostMemory(src.shape, rt)
+            self.soft_src.array[:] = src
         self.streams = [hc.stream_create() for _ in range(n_streams)]
         self.ewald = None
         ew = wl.get("ewald")
@@ -302,9 +309,11 @@ class ForceStep:
     @property
     def h2d_bytes(self):
         n = self.moments.nbytes + self.parts.nbytes
-        for s in (self.cell, self.part):
+        for s in (self.cell, self.part, self.soft):
             if s:
                 n += s.h2d_bytes
+        if self.soft_src is not None:
+            n += self.soft_src.nbytes * len(self.soft.chunks)
         if self.ewald:
             n += 4 * self.ewald.cachedData.contents.n
         return n
@@ -332,6 +341,13 @@ class ForceStep:
                 req = hc.make_request(st, dm, dp, dv, pl.array, pm.array, ps.array, pz.array, self.fperiod,
                                       node=node)
                 call(req)
+        if self.soft:
+            for pl, pm, ps, pz, n in self.soft.chunks:
+                st = self.streams[k % len(self.streams)]
+                k += 1
+                req = hc.make_request(st, dm, dp, dv, pl.array, pm.array, ps.array, pz.array, self.fperiod,
+                                      node=False)
+                hc.TreePiecePartListDataTransferLocalSmallPhase(req, self.soft_src.array)
         if self.ewald:
             hc.EwaldHost(dp, dv, self.ewald, self.streams[k % len(self.streams)])
         if len(self.streams) > 1:
@@ -347,9 +363,11 @@ class ForceStep:
     def free(self):
         for b in (self.moments, self.parts, self.vars_in, self.vars_out):
             b.free()
-        for s in (self.cell, self.part):
+        for s in (self.cell, self.part, self.soft):
             if s:
                 s.free()
+        if self.soft_src is not None:
+            self.soft_src.free()
         if self.ewald:
             self.hc.EwaldHostMemoryFree(self.ewald, 1)
         for s in self.streams:

@@ -7,6 +7,9 @@ points after serialisation:
   cell     (ilist (Li,2) int32 {index, offsetID}, markers (nb+1), starts (nb), sizes (nb))
   part     same, entries index particles (already expanded per source particle)
   fperiod  scalar period applied on all axes
+  softcell None | (ilist, markers, starts, sizes, sources (Ns,5)): cells the reference's host
+           evaluates as softened monopoles (Compute.cpp:1683-1699); here they travel as ad-hoc
+           source particles {M, soft, cm} of a p-p request
   ewald    None | {root (27), momc (32), ewt (nh,5), L, fEwCut, nReps, active}
 Arrays are float64 here; the C-ABI front end converts to cudatype on staging.
 """
@@ -90,10 +93,148 @@ def interaction_counts(wl):
     """pair interactions the way ChaNGa counts them (Compute.cpp:1643-1651):
     list entries x target particles of the bucket."""
     out = {}
-    for key in ("cell", "part"):
+    for key in ("cell", "part", "softcell"):
         if wl.get(key):
-            _, m, _, sz = wl[key]
+            _, m, _, sz = wl[key][:4]
             out[key] = int((np.diff(m).astype(np.int64) * sz.astype(np.int64)).sum())
         else:
             out[key] = 0
     return out
+
+
+# ---------------------------------------------------------------------------
+# particle sets of BASELINE.json's configs and the tree workloads built on them
+# ---------------------------------------------------------------------------
+def uniform_box(n, seed=1, xmin=-0.5, xmax=0.5):
+    """Poisson box exactly as the reference's testdata/ppartt.c:34-65 makes it: glibc
+    srand(seed); x,y,z = xmin + rand()/RAND_MAX*(xmax-xmin) per particle in that order;
+    m = 1/N; eps = N^(-1/3) (xmax-xmin)/20.  Returns (pos, mass, soft)."""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(int(seed))
+    libc.rand.restype = ctypes.c_int
+    rand_max = 2147483647.0
+    rand = libc.rand
+    r = np.fromiter((rand() for _ in range(3 * n)), dtype=np.float64, count=3 * n)
+    pos = xmin + r.reshape(n, 3) / rand_max * (xmax - xmin)
+    mass = np.full(n, 1.0 / n)
+    soft = np.full(n, n ** (-1.0 / 3.0) * (xmax - xmin) / 20.0)
+    return pos, mass, soft
+
+
+def clustered_box(n, seed=2, n_halos=None, frac_halo=0.7, rs_range=(2e-4, 2e-2)):
+    """SURVEY 8d config C4 recipe: (1-frac_halo) uniform background + frac_halo in Plummer
+    spheres (centres uniform, scale radii log-uniform in rs_range, halo mass ~ r_s), wrapped
+    into [-0.5,0.5); m = 1/N, eps = N^(-1/3)/20."""
+    rng = np.random.default_rng(seed)
+    n_halos = n_halos or max(8, n // 16384)
+    nh = int(frac_halo * n)
+    nb = n - nh
+    bg = rng.uniform(-0.5, 0.5, (nb, 3))
+    cen = rng.uniform(-0.5, 0.5, (n_halos, 3))
+    rs = np.exp(rng.uniform(np.log(rs_range[0]), np.log(rs_range[1]), n_halos))
+    which = rng.choice(n_halos, nh, p=rs / rs.sum())
+    # Plummer radius from the cumulative mass profile, truncated at 10 r_s
+    u = rng.uniform(0, 0.985, nh)
+    r = rs[which] / np.sqrt(u ** (-2.0 / 3.0) - 1.0)
+    d = rng.normal(size=(nh, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    halo = cen[which] + d * r[:, None]
+    pos = np.concatenate([bg, halo])
+    pos = (pos + 0.5) % 1.0 - 0.5
+    pos = pos[rng.permutation(n)]
+    return pos, np.full(n, 1.0 / n), np.full(n, n ** (-1.0 / 3.0) / 20.0)
+
+
+def cosmo_box(n_side=48, seed=300, growth=0.035):
+    """Stand-in for testcosmo/cube300.tbin (48^3 = 110592 dark particles, periodic unit box,
+    the fixture itself stays in the reference tree): a grid displaced by a Gaussian random
+    field with a P(k) ~ k^-2 spectrum (Zel'dovich), which gives the filament/void clustering
+    of an evolved box.  m = 1/N, eps = N^(-1/3)/20."""
+    rng = np.random.default_rng(seed)
+    n = n_side
+    k = np.fft.fftfreq(n) * n
+    kx, ky, kz = np.meshgrid(k, k, np.fft.rfftfreq(n) * n, indexing="ij")
+    k2 = kx ** 2 + ky ** 2 + kz ** 2
+    k2[0, 0, 0] = 1.0
+    amp = k2 ** (-1.0) * np.exp(-k2 / (0.35 * n) ** 2)
+    amp[0, 0, 0] = 0.0
+    delta = (rng.normal(size=k2.shape) + 1j * rng.normal(size=k2.shape)) * amp
+    disp = [np.fft.irfftn(1j * kk / k2 * delta, s=(n, n, n), axes=(0, 1, 2)) for kk in (kx, ky, kz)]
+    disp = np.stack(disp, axis=-1)
+    disp *= growth / disp.std()
+    g = (np.arange(n) + 0.5) / n - 0.5
+    q = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1)
+    pos = ((q + disp + 0.5) % 1.0 - 0.5).reshape(-1, 3)
+    np_ = n ** 3
+    return pos, np.full(np_, 1.0 / np_), np.full(np_, np_ ** (-1.0 / 3.0) / 20.0)
+
+
+def read_tipsy(path):
+    """Standard (big-endian XDR) Tipsy snapshot -> (pos, mass, soft) of all particles
+    (testdata/tipsydefs.h:4-110: gas 12 floats, dark 9, star 11; header 28 bytes + pad)."""
+    import struct
+    with open(path, "rb") as f:
+        raw = f.read()
+    time, nbodies, ndim, nsph, ndark, nstar = struct.unpack(">diiiii", raw[:28])
+    off = 32 if len(raw) >= 32 + 4 * (12 * nsph + 9 * ndark + 11 * nstar) else 28
+    out = []
+    for cnt, width, soft_col in ((nsph, 12, 9), (ndark, 9, 7), (nstar, 11, 9)):
+        a = np.frombuffer(raw, dtype=">f4", count=cnt * width, offset=off).reshape(cnt, width).astype(np.float64)
+        off += 4 * cnt * width
+        out.append((a[:, 1:4], a[:, 0], a[:, soft_col]))
+    pos = np.concatenate([o[0] for o in out])
+    return pos, np.concatenate([o[1] for o in out]), np.concatenate([o[2] for o in out])
+
+
+CONFIGS = {
+    # name: (generator, kwargs, theta, nReplicas, periodic/Ewald)
+    "cube300": dict(gen="cosmo", n_side=48, theta=0.7, n_replicas=1, ewald=True),
+    "king": dict(gen="plummer", n=36000, theta=0.7, n_replicas=0, ewald=False),
+    "uniform": dict(gen="uniform", n=1 << 20, theta=0.7, n_replicas=1, ewald=True),
+    "clustered": dict(gen="clustered", n=1 << 20, theta=0.7, n_replicas=1, ewald=True),
+}
+
+
+def plummer_sphere(n, seed=7, rs=1.0, soft=0.05):
+    """stand-in for teststep/king_soft.bin (36000 equal-mass particles, isolated cluster)"""
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(0, 0.99, n)
+    r = rs / np.sqrt(u ** (-2.0 / 3.0) - 1.0)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return d * r[:, None], np.full(n, 1.0 / n), np.full(n, soft)
+
+
+def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_range_of=None, **over):
+    """Tree workload for one of BASELINE.json's configs.  bucket_range_of=(rank, world):
+    lists only for that rank's contiguous SFC share of the buckets (equal particle counts);
+    the whole tree (particles + moments) stays in the workload, as after the all-gather."""
+    from .tree import Tree, tree_workload
+    cfg = dict(CONFIGS[name])
+    cfg.update(over)
+    if cfg["gen"] == "cosmo":
+        side = cfg["n_side"] if n is None else int(round(n ** (1.0 / 3.0)))
+        pos, mass, soft = cosmo_box(side, seed=seed or 300)
+    elif cfg["gen"] == "uniform":
+        pos, mass, soft = uniform_box(n or cfg["n"], seed=seed or 1)
+    elif cfg["gen"] == "clustered":
+        pos, mass, soft = clustered_box(n or cfg["n"], seed=seed or 2)
+    else:
+        pos, mass, soft = plummer_sphere(n or cfg["n"], seed=seed or 7)
+    root_lo, root_hi = (-0.5,) * 3, (0.5,) * 3
+    if not cfg["ewald"]:
+        ext = float(np.abs(pos).max()) * 1.0001
+        root_lo, root_hi = (-ext,) * 3, (ext,) * 3
+    t = Tree(pos, mass, soft, max_bucket=max_bucket, root_lo=root_lo, root_hi=root_hi)
+    rng_b = None
+    if bucket_range_of is not None:
+        rank, world = bucket_range_of
+        cuts = np.searchsorted(np.cumsum(t.bucket_sizes), np.arange(1, world) * t.n / world, side="left") + 1
+        cuts = np.concatenate([[0], cuts, [t.num_buckets]])
+        rng_b = (int(cuts[rank]), int(cuts[rank + 1]))
+    wl = tree_workload(None, None, None, theta=cfg["theta"], n_replicas=cfg["n_replicas"], period=1.0,
+                       ewald={} if cfg["ewald"] else None, bucket_range=rng_b, tree=t,
+                       name=f"{name}(N={t.n},theta={cfg['theta']},nReplicas={cfg['n_replicas']},bucket={max_bucket})")
+    wl["bucket_range"] = rng_b or (0, t.num_buckets)
+    return wl

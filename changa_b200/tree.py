@@ -151,7 +151,7 @@ def tree_workload(pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, max_buck
     t = tree or Tree(pos, mass, soft, max_bucket=max_bucket)
     w = t.walk(theta=theta, n_replicas=n_replicas, period=period, bucket_active=bucket_active,
                bucket_range=bucket_range)
-    wl = {"parts": t.parts, "moments": t.moments, "fperiod": float(period) if n_replicas or ewald else 0.0,
+    wl = {"parts": t.parts, "moments": t.moments, "fperiod": float(period) if (n_replicas or ewald is not None) else 0.0,
           "order": t.order, "name": name, "tree": t,
           "walk_stats": {k: w[k] for k in ("mac_tests", "mac_opened")}}
     wl["cell"] = serialize(w["cell"], w["cell_mark"], t.bucket_starts, t.bucket_sizes)[:4]
@@ -166,7 +166,7 @@ def tree_workload(pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, max_buck
         il = np.column_stack([inv.astype(np.int32), w["soft"][:, 1]]).astype(np.int32)
         wl["softcell"] = serialize(il, w["soft_mark"], t.bucket_starts, t.bucket_sizes)[:4] + (src,)
     wl["ewald"] = None
-    if ewald:
+    if ewald is not None:
         momc, ewt = ewald_tables(t.moments[0], period, ewald.get("dEwhCut", 2.8))
         act = None
         if bucket_active is not None or bucket_range is not None:

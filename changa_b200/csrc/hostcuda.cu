@@ -605,6 +605,9 @@ void cb200_pack_moments_device(const void *d_raw, void *d_packed, int n, void *s
 void cb200_pack_particles_device(const void *d_raw, void *d_packed, int n, void *stream) {
   repack_parts(d_raw, (PackedPart *)d_packed, n, (cudaStream_t)stream);
 }
+void cb200_zero_vars_device(void *d_vars, int n, void *stream) {
+  if (n > 0) cudaChk(cudaMemsetAsync(d_vars, 0, (size_t)n * sizeof(VariablePartData), (cudaStream_t)stream));
+}
 size_t cb200_packed_moment_bytes(void) { return sizeof(PackedCell); }
 size_t cb200_packed_particle_bytes(void) { return sizeof(PackedPart); }
 

@@ -101,7 +101,7 @@ C_ABI_SYMBOLS = [
     "cb200_cell_list_device", "cb200_part_list_device", "cb200_cell_list_device_ex",
     "cb200_part_list_device_ex", "cb200_ewald_device",
     "cb200_packed_moment_bytes", "cb200_packed_particle_bytes",
-    "cb200_pack_moments_device", "cb200_pack_particles_device",
+    "cb200_pack_moments_device", "cb200_pack_particles_device", "cb200_zero_vars_device",
     "cb200_timing_enable", "cb200_timing_reset", "cb200_timing_read", "cb200_kernel_launches",
     "cb200_build_moments", "cb200_partition_buckets",
 ]
@@ -159,6 +159,7 @@ def load(double=False):
     L.cb200_packed_particle_bytes.restype = sz
     L.cb200_pack_moments_device.argtypes = [vp, vp, i, vp]
     L.cb200_pack_particles_device.argtypes = [vp, vp, i, vp]
+    L.cb200_zero_vars_device.argtypes = [vp, i, vp]
     L.cb200_timing_enable.argtypes = [i]
     L.cb200_timing_read.argtypes = [C.POINTER(C.c_double * 6)]
     L.cb200_kernel_launches.restype = C.c_longlong

@@ -196,7 +196,7 @@ CONFIGS = {
 }
 
 
-def plummer_sphere(n, seed=7, rs=1.0, soft=0.05):
+def plummer_sphere(n, seed=7, rs=2.0, soft=0.2):
     """stand-in for teststep/king_soft.bin (36000 equal-mass particles, isolated cluster)"""
     rng = np.random.default_rng(seed)
     u = rng.uniform(0, 0.99, n)
@@ -206,7 +206,8 @@ def plummer_sphere(n, seed=7, rs=1.0, soft=0.05):
     return d * r[:, None], np.full(n, 1.0 / n), np.full(n, soft)
 
 
-def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_range_of=None, **over):
+def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_range_of=None, gen_kwargs=None,
+                    **over):
     """Tree workload for one of BASELINE.json's configs.  bucket_range_of=(rank, world):
     lists only for that rank's contiguous SFC share of the buckets (equal particle counts);
     the whole tree (particles + moments) stays in the workload, as after the all-gather."""
@@ -221,7 +222,7 @@ def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_ran
     elif cfg["gen"] == "clustered":
         pos, mass, soft = clustered_box(n or cfg["n"], seed=seed or 2)
     else:
-        pos, mass, soft = plummer_sphere(n or cfg["n"], seed=seed or 7)
+        pos, mass, soft = plummer_sphere(n or cfg["n"], seed=seed or 7, **(gen_kwargs or {}))
     root_lo, root_hi = (-0.5,) * 3, (0.5,) * 3
     if not cfg["ewald"]:
         ext = float(np.abs(pos).max()) * 1.0001

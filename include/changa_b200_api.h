@@ -164,6 +164,8 @@ size_t cb200_packed_moment_bytes(void);   /* bytes per cell row      */
 size_t cb200_packed_particle_bytes(void); /* bytes per particle row  */
 void cb200_pack_moments_device(const void *d_raw, void *d_packed, int n, void *stream);
 void cb200_pack_particles_device(const void *d_raw, void *d_packed, int n, void *stream);
+/* what ZeroVars does (HostCUDA.cu:2195-2205): clear n VariablePartData rows */
+void cb200_zero_vars_device(void *d_vars, int n, void *stream);
 
 /* --- timing taps (CUDA events recorded around every kernel we launch) ------ */
 void cb200_timing_enable(int on);

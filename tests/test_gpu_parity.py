@@ -127,3 +127,51 @@ def test_callbacks_fire_once_per_request(hc):
     hc.stream_destroy(s)
     for b in (mom, par, var, out):
         b.free()
+
+
+def oracle_forces_tree(wl, np_real=np.float32):
+    v = oracle_forces(wl, np_real)
+    if wl.get("softcell"):
+        parts = np.ascontiguousarray(wl["parts"].astype(np_real).astype(np.float64))
+        src = np.ascontiguousarray(wl["softcell"][4].astype(np_real).astype(np.float64))
+        orc.part_list(parts, src, *wl["softcell"][:4], float(np_real(wl["fperiod"])), v)
+    return v
+
+
+@pytest.mark.parametrize("name,n", [("cube300", 16 ** 3), ("king", 4000)])
+def test_tree_workloads_match_oracle(hc, name, n):
+    """real trees, real walks: periodic box with Ewald (config 2) and an isolated cluster whose
+    dense core produces softened cells (config 1), full step through the C ABI"""
+    from changa_b200.hostcuda import ForceStep
+    from changa_b200.workloads import config_workload
+    wl = config_workload(name, n=n, gen_kwargs=dict(rs=1.0) if name == "king" else None)
+    if name == "king":
+        assert wl["softcell"] is not None
+    step = ForceStep(hc, wl)
+    try:
+        got = step.run().copy()
+    finally:
+        step.free()
+    # Ewald's erfc/exp chain in float costs a little more than the list kernels
+    compare(got, oracle_forces_tree(wl), median_tol=5e-6, max_tol=1e-3, pot_tol=2e-5)
+
+
+def test_resident_path_equals_abi_path(hc):
+    """device-pointer entry points (bench.py's resident step) give the same bits as the
+    host-buffer entry points"""
+    import torch
+    from changa_b200.hostcuda import ForceStep
+    from changa_b200.workloads import config_workload
+    import bench
+    wl = config_workload("cube300", n=12 ** 3)
+    step = ForceStep(hc, wl)
+    try:
+        a = step.run().copy()
+    finally:
+        step.free()
+    rs = bench.ResidentStep(hc, wl, torch, None, 0, 1)
+    with torch.cuda.stream(rs.ext):
+        rs.step()
+    torch.cuda.synchronize()
+    b = rs.vars.cpu().numpy()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

@@ -326,6 +326,323 @@ cell_list_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restr
   }
 }
 
+#ifndef CUDA_USE_DOUBLE
+/* ------------------------------------------- particle-cell, packed f32x2 math */
+/* Blackwell's FMA pipe issues a 3-register FFMA every other cycle per SM
+ * sub-partition but a packed FFMA2 (fma.rn.f32x2: two lanes of a 64-bit
+ * register pair) at the same cadence -- twice the flops per issue slot, and the
+ * only way to the FP32 peak with register operands (tools/fp32_peak.cu:
+ * 3-register FFMA 49 TFLOP/s, FFMA2 74 TFLOP/s).  FFMA2 also takes a 32-bit
+ * operand broadcast to both halves (SASS `Rn.F32`), so a lane keeps ONE cell's
+ * coefficients as scalars and evaluates it against TWO target particles per
+ * instruction.  Targets sit in shared memory as pairs {x0,x1 | y0,y1 | z0,z1 |
+ * m0,m1}; accumulators are packed pairs too.  Same series as pc_pair above. */
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 bc2(float c) { return pk2(c, c); } /* ptxas folds this into an .F32 operand */
+__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+/* sign flips fold into the consuming instruction's operand modifier */
+__device__ __forceinline__ f32x2 neg2(f32x2 a) {
+  float lo, hi;
+  unpk2(a, lo, hi);
+  return pk2(-lo, -hi);
+}
+/* a*s + c and a*s with a scalar s */
+__device__ __forceinline__ f32x2 fma2s(float s, f32x2 a, f32x2 c) { return fma2(bc2(s), a, c); }
+__device__ __forceinline__ f32x2 mul2s(float s, f32x2 a) { return mul2(bc2(s), a); }
+
+struct TargetPair { f32x2 x, y, z, m; }; /* 32 bytes: two LDS.128 */
+
+__device__ __forceinline__ void pc_pair2(const float *__restrict__ c, float ccx, float ccy, float ccz,
+                                         const TargetPair &p, f32x2 &ax, f32x2 &ay, f32x2 &az, f32x2 &pot,
+                                         float &idt0, float &idt1) {
+  const float third = 1.0f / 3.0f, sixth = 1.0f / 6.0f;
+  const f32x2 rx = sub2(p.x, bc2(ccx)), ry = sub2(p.y, bc2(ccy)), rz = sub2(p.z, bc2(ccz));
+  const f32x2 rsq = fma2(rz, rz, fma2(ry, ry, mul2(rx, rx)));
+  float q0, q1;
+  unpk2(rsq, q0, q1);
+  float d0 = rsqrt_dev(q0), d1 = rsqrt_dev(q1);
+  d0 = (q0 != 0.0f) ? d0 : 0.0f; /* r == 0: the pair is skipped (HostCUDA.cu:1103) */
+  d1 = (q1 != 0.0f) ? d1 : 0.0f;
+  const f32x2 d = pk2(d0, d1);
+  const f32x2 d2 = mul2(d, d);
+  const f32x2 s = mul2s(c[PK_RADIUS], d2);
+  const f32x2 X = mul2(rx, s), Y = mul2(ry, s), Z = mul2(rz, s);
+
+  /* monomials xi^alpha / alpha!, with the z-traces already removed (20 ops):
+   *   xxm = (X^2 - Z^2)/2            xxx = X (X^2/6 - Z^2/2)
+   *   xxz = Z (X^2/2 - Z^2/6) = Z (xxm + Z^2/3)        (same with y) */
+  const f32x2 a = mul2(X, X), b = mul2(Y, Y), cz = mul2(Z, Z);
+  const f32x2 nhc = mul2s(-0.5f, cz);
+  const f32x2 xxm = fma2s(0.5f, a, nhc), yym = fma2s(0.5f, b, nhc);
+  const f32x2 xxx = mul2(X, fma2s(sixth, a, nhc)), yyy = mul2(Y, fma2s(sixth, b, nhc));
+  const f32x2 xxz = mul2(Z, fma2s(third, cz, xxm)), yyz = mul2(Z, fma2s(third, cz, yym));
+  const f32x2 xy = mul2(X, Y), xz = mul2(X, Z), yz = mul2(Y, Z);
+  const f32x2 xxy = mul2(Y, xxm), xyy = mul2(X, yym), xyz = mul2(xy, Z);
+
+  /* T accumulates the contracted vectors order by order (4, then 4+3, then
+   * 4+3+2); A4, A34, A234 are its projections on xi at each stage, so that
+   *   s4 = A4, s3 = A34 - A4, s2 = A234 - A34. */
+  f32x2 tx = mul2s(c[PK_XXXX], xxx);
+  tx = fma2s(c[PK_XYYY], yyy, tx); tx = fma2s(c[PK_XXXY], xxy, tx); tx = fma2s(c[PK_XXXZ], xxz, tx);
+  tx = fma2s(c[PK_XXYY], xyy, tx); tx = fma2s(c[PK_XXYZ], xyz, tx); tx = fma2s(c[PK_XYYZ], yyz, tx);
+  f32x2 ty = mul2s(c[PK_XYYY], xyy);
+  ty = fma2s(c[PK_XXXY], xxx, ty); ty = fma2s(c[PK_YYYY], yyy, ty); ty = fma2s(c[PK_YYYZ], yyz, ty);
+  ty = fma2s(c[PK_XXYY], xxy, ty); ty = fma2s(c[PK_XXYZ], xxz, ty); ty = fma2s(c[PK_XYYZ], xyz, ty);
+  f32x2 tz = mul2s(c[PK_XXXZ], xxx);
+  tz = fma2s(c[PK_YYYZ], yyy, tz); tz = fma2s(c[PK_XXYZ], xxy, tz); tz = fma2s(c[PK_XYYZ], xyy, tz);
+  tz = fma2s(-c[PK_XXXX], xxz, tz); tz = fma2s(-c[PK_XY3S], xyz, tz); tz = fma2s(-c[PK_YYYY], yyz, tz);
+  tz = fma2s(-c[PK_XXYY], add2(xxz, yyz), tz);
+  const f32x2 A4 = fma2(tz, Z, fma2(ty, Y, mul2(tx, X)));
+
+  tx = fma2s(c[PK_XXX], xxm, tx); tx = fma2s(c[PK_XYY], yym, tx); tx = fma2s(c[PK_XXY], xy, tx);
+  tx = fma2s(c[PK_XXZ], xz, tx); tx = fma2s(c[PK_XYZ], yz, tx);
+  ty = fma2s(c[PK_XYY], xy, ty); ty = fma2s(c[PK_XXY], xxm, ty); ty = fma2s(c[PK_YYY], yym, ty);
+  ty = fma2s(c[PK_YYZ], yz, ty); ty = fma2s(c[PK_XYZ], xz, ty);
+  tz = fma2s(c[PK_XZZ], xz, tz); tz = fma2s(c[PK_YZZ], yz, tz); tz = fma2s(c[PK_XXZ], xxm, tz);
+  tz = fma2s(c[PK_YYZ], yym, tz); tz = fma2s(c[PK_XYZ], xy, tz);
+  const f32x2 A34 = fma2(tz, Z, fma2(ty, Y, mul2(tx, X)));
+
+  tx = fma2s(c[PK_XX], X, tx); tx = fma2s(c[PK_XY], Y, tx); tx = fma2s(c[PK_XZ], Z, tx);
+  ty = fma2s(c[PK_YY], Y, ty); ty = fma2s(c[PK_XY], X, ty); ty = fma2s(c[PK_YZ], Z, ty);
+  tz = fma2s(c[PK_ZZ], Z, tz); tz = fma2s(c[PK_XZ], X, tz); tz = fma2s(c[PK_YZ], Y, tz);
+  const f32x2 A234 = fma2(tz, Z, fma2(ty, Y, mul2(tx, X)));
+
+  /* phi = M + s2/2 + s3/3 + s4/4;  G = M + 5/2 s2 + 7/3 s3 + 9/4 s4 = phi + 2 (s2+s3+s4) */
+  const float M = c[PK_MASS];
+  const f32x2 phi = fma2s(-1.0f / 12.0f, A4, fma2s(-sixth, A34, fma2s(0.5f, A234, bc2(M))));
+  const f32x2 G = fma2s(2.0f, A234, phi);
+  const f32x2 d3 = mul2(d2, d);
+  pot = fma2(neg2(d), phi, pot);
+  const f32x2 e = mul2s(c[PK_RADIUS], d3), g = neg2(mul2(G, d3));
+  ax = fma2(g, rx, fma2(e, tx, ax));
+  ay = fma2(g, ry, fma2(e, ty, ay));
+  az = fma2(g, rz, fma2(e, tz, az));
+  float i0, i1;
+  unpk2(mul2(add2(p.m, bc2(M)), d3), i0, i1);
+  idt0 = fmaxf(idt0, i0);
+  idt1 = fmaxf(idt1, i1);
+}
+
+template <int PB>
+constexpr size_t cell_list_x2_smem_bytes() {
+  return (size_t)kListWarps * (2 * 32 * kCellBytes + (PB / 2) * sizeof(TargetPair));
+}
+
+/* Work decomposition as cell_list_kernel (one warp owns one bucket, lane =
+ * list entry, double-buffered cp.async tile of PackedCell rows), with
+ *   - the inner loop over target PAIRS in packed f32x2 math (pc_pair2);
+ *   - the per-bucket reduction through shared memory: every lane parks its
+ *     5*PB partial sums as column `lane` of a [value][32] array laid over the
+ *     (now idle) cell tiles, then lane v adds up row v in a skewed, conflict-
+ *     free order.  Rows are ordered particle-major, so row v IS float v of the
+ *     bucket's contiguous VariablePartData block and the += is one coalesced
+ *     read-modify-write.  ~190 instructions instead of ~600 for 25 butterflies,
+ *     fixed summation order -> bitwise reproducible. */
+struct BucketMeta { int begin, len, first, count; };
+
+__device__ __forceinline__ BucketMeta load_bucket_meta(const int *__restrict__ markers,
+                                                       const int *__restrict__ starts,
+                                                       const int *__restrict__ sizes, int k) {
+  BucketMeta m;
+  m.begin = markers[k];
+  m.len = markers[k + 1] - m.begin;
+  m.first = starts[k];
+  m.count = sizes[k];
+  return m;
+}
+
+template <int PB, int MINB, bool DUAL>
+__global__ void __launch_bounds__(kListWarps * 32, MINB)
+cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
+                    const PackedCell *__restrict__ cells, const ILCell *__restrict__ list,
+                    const int *__restrict__ markers, const int *__restrict__ starts,
+                    const int *__restrict__ sizes, int nBuckets, float fperiod,
+                    unsigned int *__restrict__ nextBucket) {
+  static_assert(PB % 2 == 0 && 5 * PB <= 64, "two reduction rows per lane at most");
+  static_assert(5 * PB * 32 * sizeof(float) <= 2 * 32 * kCellBytes, "reduction scratch fits in the cell tiles");
+  constexpr int NP = PB / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4 *tiles = reinterpret_cast<uint4 *>(smem_raw) + (size_t)warp * (2 * 32 * kCellPieces);
+  float *red = reinterpret_cast<float *>(tiles);
+  TargetPair *sp = reinterpret_cast<TargetPair *>(smem_raw + (size_t)kListWarps * 2 * 32 * kCellBytes) + warp * NP;
+
+  /* Buckets are pulled from a global counter one AHEAD: while bucket k is being
+   * evaluated the warp already knows k+1, has its markers in registers and, from
+   * the last tile of k on, its first two list tiles and its target particles in
+   * flight -- the chain of dependent global round trips (index -> markers ->
+   * list -> cells) is paid once per warp, not once per bucket. */
+  auto grab = [&]() {
+    int k = 0;
+    if (lane == 0) k = (int)atomicAdd(nextBucket, 1u);
+    return __shfl_sync(kFull, k, 0);
+  };
+  const ILCell none = {-1, 0};
+  int k = grab();
+  BucketMeta m = {0, 0, 0, 0};
+  if (k < nBuckets) m = load_bucket_meta(markers, starts, sizes, k);
+  bool havePre = false;
+  ILCell pre0 = none, pre1 = none;
+  float4 preq = {0.f, 0.f, 0.f, 0.f};
+
+  while (k < nBuckets) {
+    const int kn = grab();
+    BucketMeta mn = {0, 0, 0, 0};
+    if (kn < nBuckets) mn = load_bucket_meta(markers, starts, sizes, kn);
+    bool nextPre = false;
+    ILCell npre0 = none, npre1 = none;
+    float4 npreq = {0.f, 0.f, 0.f, 0.f};
+
+    const ILCell *__restrict__ mylist = list + m.begin;
+    const int len = m.len, ntiles = (len + 31) >> 5;
+    for (int p0 = 0; p0 < m.count && len > 0; p0 += PB) { /* one pass unless the bucket outgrows PB */
+      const int np = min(PB, m.count - p0);
+      const int npairs = (np + 1) >> 1;
+      const bool lastPass = p0 + PB >= m.count;
+      __syncwarp();
+      if (lane < 2 * npairs) { /* an odd bucket's last slot repeats its last particle; that half is never stored */
+        float4 q = preq;
+        if (!(havePre && p0 == 0))
+          q = *reinterpret_cast<const float4 *>(parts + m.first + p0 + min(lane, np - 1));
+        float *dst = reinterpret_cast<float *>(sp + (lane >> 1)) + (lane & 1);
+        dst[0] = q.x; dst[2] = q.y; dst[4] = q.z; dst[6] = q.w;
+      }
+      __syncwarp();
+
+      f32x2 ax[NP], ay[NP], az[NP], pot[NP];
+      float idt[PB];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) { ax[j] = ay[j] = az[j] = pot[j] = 0ull; idt[2 * j] = idt[2 * j + 1] = 0.0f; }
+
+      ILCell cur = none, nxt = none;
+      if (havePre && p0 == 0) {
+        cur = pre0; nxt = pre1;
+      } else {
+        if (lane < len) cur = mylist[lane];
+        if (32 + lane < len) nxt = mylist[32 + lane];
+      }
+      stage_cell_tile(tiles, cells, cur.index, lane);
+      cp_async_commit();
+
+      for (int t = 0; t < ntiles; ++t) {
+        uint4 *buf = tiles + (t & 1) * (32 * kCellPieces);
+        if (t + 1 < ntiles) stage_cell_tile(tiles + ((t + 1) & 1) * (32 * kCellPieces), cells, nxt.index, lane);
+        cp_async_commit();
+        ILCell nn = none;
+        if ((t + 2) * 32 + lane < len) nn = mylist[(t + 2) * 32 + lane];
+        if (lastPass && t == ntiles - 1 && mn.len > 0) { /* the next bucket's first loads ride under this tile */
+          const ILCell *nl = list + mn.begin;
+          if (lane < mn.len) npre0 = nl[lane];
+          if (32 + lane < mn.len) npre1 = nl[32 + lane];
+          const int npn = min(PB, mn.count);
+          if (lane < 2 * ((npn + 1) >> 1))
+            npreq = *reinterpret_cast<const float4 *>(parts + mn.first + min(lane, npn - 1));
+          nextPre = true;
+        }
+        cp_async_wait<1>();
+        __syncwarp();
+
+        if (cur.index >= 0) {
+          float c[kCellReals];
+          load_cell_row(buf, lane, c);
+          const float ccx = fmaf(float(replica_x(cur.offsetID)), fperiod, c[PK_CX]);
+          const float ccy = fmaf(float(replica_y(cur.offsetID)), fperiod, c[PK_CY]);
+          const float ccz = fmaf(float(replica_z(cur.offsetID)), fperiod, c[PK_CZ]);
+          if (DUAL) { /* two target pairs per straight-line block: twice the independent FMA chains */
+#pragma unroll
+            for (int j = 0; j < NP; j += 2) {
+              if (j + 1 < NP && j + 1 < npairs) {
+                const TargetPair pa = sp[j], pb = sp[j + 1];
+                pc_pair2(c, ccx, ccy, ccz, pa, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
+                pc_pair2(c, ccx, ccy, ccz, pb, ax[j + 1], ay[j + 1], az[j + 1], pot[j + 1], idt[2 * j + 2],
+                         idt[2 * j + 3]);
+              } else if (j < npairs) {
+                const TargetPair pa = sp[j];
+                pc_pair2(c, ccx, ccy, ccz, pa, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+              if (j < npairs) {
+                const TargetPair p = sp[j];
+                pc_pair2(c, ccx, ccy, ccz, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        cur = nxt;
+        nxt = nn;
+      }
+      cp_async_wait<0>();
+      __syncwarp();
+
+      /* park partial sums: row (particle*5 + component), column lane */
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        if (j < npairs) {
+          float a0, a1, b0, b1, c0, c1, e0, e1;
+          unpk2(ax[j], a0, a1); unpk2(ay[j], b0, b1); unpk2(az[j], c0, c1); unpk2(pot[j], e0, e1);
+          float *r0 = red + (size_t)(2 * j) * 5 * 32 + lane;
+          r0[0] = a0; r0[32] = b0; r0[64] = c0; r0[96] = e0; r0[128] = idt[2 * j];
+          r0[160] = a1; r0[192] = b1; r0[224] = c1; r0[256] = e1; r0[288] = idt[2 * j + 1];
+        }
+      }
+      __syncwarp();
+      float *out = reinterpret_cast<float *>(vars + m.first + p0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = lane + 32 * h;
+        if (v < 5 * np) {
+          const float *row = red + v * 32;
+          const bool isMax = (v % 5) == 4;
+          float acc = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = row[(i + lane) & 31];
+            acc = isMax ? fmaxf(acc, x) : acc + x;
+          }
+          /* accumulate, never overwrite (HostCUDA.cu:1196-1200); dtGrav is a running max */
+          out[v] = isMax ? fmaxf(out[v], acc) : out[v] + acc;
+        }
+      }
+      __syncwarp();
+    }
+    k = kn; m = mn;
+    havePre = nextPre; pre0 = npre0; pre1 = npre1; preq = npreq;
+  }
+}
+#endif /* !CUDA_USE_DOUBLE */
+
 /* ------------------------------------------------------ particle-particle */
 /* Hernquist-Katz spline-softened monopole, SPLINE of gravity.h:147-182.
  * r = (shift + source) - target (HostCUDA.cu:1655-1663). */
@@ -485,6 +802,23 @@ __device__ __forceinline__ void sincos_dev(double x, double *s, double *c) { sin
 
 constexpr int kEwaldThreads = 128;
 
+/* sum_j (-x)^j / (j! (2j + 2n + 1)), Horner from the highest term; enough terms
+ * for rounding-level accuracy up to x = kEwaldSeriesX in the build's precision */
+constexpr double kEwaldSeriesX = 0.64;
+constexpr int kEwaldSeriesTerms = sizeof(real) == 4 ? 10 : 19;
+template <int N>
+__device__ __forceinline__ real ewald_series(real x) {
+  double fact = 1.0;
+  for (int j = 1; j < kEwaldSeriesTerms; ++j) fact *= j;
+  real s = real(1.0 / (fact * (2 * (kEwaldSeriesTerms - 1) + 2 * N + 1)));
+#pragma unroll
+  for (int j = kEwaldSeriesTerms - 2; j >= 0; --j) {
+    fact /= (j + 1);
+    s = fma(-x, s, real(1.0 / (fact * (2 * j + 2 * N + 1))));
+  }
+  return s;
+}
+
 /* One thread per active particle: real-space sum over the (2 nEwReps+1)^3
  * replicas of the root cell's complete hexadecapole expansion, then the
  * reciprocal-space sum over the h-table (BucketEwald, Ewald.cpp:72-281;
@@ -536,18 +870,27 @@ ewald_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict_
       for (int iz = -nE; iz <= nE; ++iz) {
         const bool hole = hxy && (iz >= -nR && iz <= nR);
         const real z = dz + iz * L;
-        real r2 = x * x + y * y + z * z;
+        const real r2 = x * x + y * y + z * z;
         if (r2 > ro.fEwCut2 && !hole) continue;
         real g0, g1, g2, g3, g4, g5;
-        if (r2 < ro.fInner2) { /* series about r = 0 (Ewald.cpp:141-152) */
-          real an = ka;
-          r2 *= alpha2;
-          g0 = an * (third * r2 - real(1));
-          an *= twoa2; g1 = an * (real(1.0 / 5.0) * r2 - third);
-          an *= twoa2; g2 = an * (real(1.0 / 7.0) * r2 - real(1.0 / 5.0));
-          an *= twoa2; g3 = an * (real(1.0 / 9.0) * r2 - real(1.0 / 7.0));
-          an *= twoa2; g4 = an * (real(1.0 / 11.0) * r2 - real(1.0 / 9.0));
-          an *= twoa2; g5 = an * (real(1.0 / 13.0) * r2 - real(1.0 / 11.0));
+        const real xa = r2 * alpha2;
+        if (hole && xa < real(kEwaldSeriesX)) {
+          /* -erf(alpha r)/r and its (1/r d/dr)^n derivatives as a power series in
+           * x = alpha^2 r^2:  g_n = -ka (2 alpha^2)^n sum_j (-x)^j / (j! (2j+2n+1)).
+           * The reference switches to the first two terms of this series only for
+           * r^2 < fInner2 (Ewald.cpp:141-152; 1.2e-3 L^2 on the CPU, 1.1e-2 L^2 on its
+           * GPU, Ewald.cpp:516) and uses the erf/exp recurrences beyond, which in
+           * single precision cancel catastrophically just outside that radius
+           * (measured: 2.5e-3 relative force error at r = 0.11 L).  Summing the series
+           * to rounding over the whole well-conditioned range removes both the
+           * truncation and the cancellation error; ro.fInner2 is not used. */
+          real an = -ka;
+          g0 = an * ewald_series<0>(xa);
+          an *= twoa2; g1 = an * ewald_series<1>(xa);
+          an *= twoa2; g2 = an * ewald_series<2>(xa);
+          an *= twoa2; g3 = an * ewald_series<3>(xa);
+          an *= twoa2; g4 = an * ewald_series<4>(xa);
+          an *= twoa2; g5 = an * ewald_series<5>(xa);
         } else {
           const real dir = rsqrt_dev(r2), dir2 = dir * dir;
           const real r = r2 * dir;

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/changa_b200_api.h"
@@ -84,6 +85,10 @@ static const DeviceInfo &device_info() {
       cudaChk(cudaDeviceGetDefaultMemPool(&pool, dev));
       uint64_t keep = UINT64_MAX; /* the arena: never hand memory back to the driver */
       cudaChk(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      /* a block freed on one stream is re-used on another only once that free has
+       * completed: never by making the allocating (copy) stream wait for a kernel */
+      int off = 0;
+      cudaChk(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
       d.ready = true;
     }
   }
@@ -99,6 +104,62 @@ static void *pool_alloc(size_t bytes, cudaStream_t stream) {
 }
 static void pool_free(void *p, cudaStream_t stream) {
   if (p) cudaChk(cudaFreeAsync(p, stream));
+}
+
+/* ------------------------------------------------------- copy/compute overlap */
+/* A request arrives on ONE caller stream (TreePiece: streams[thisIndex % numStreams],
+ * TreePiece.cpp:5380), and the reference enqueues its host->device list copy and
+ * its kernel there back to back, so the copy engine idles while the SMs work and
+ * vice versa.  Here every caller stream gets a private companion stream: the
+ * request's staging copies go on the companion, an event hands them to the caller
+ * stream, the kernel and the completion callback stay on the caller stream.  The
+ * order the caller observes is unchanged (kernels and callbacks in submission
+ * order; the pinned list buffers are released by the callback, which still fires
+ * after the kernel that waited for the copy), but the copy of request i+1 runs
+ * under the kernel of request i.  CB200_NO_COPY_STREAM=1 restores the serial order. */
+struct Companion {
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev[16];
+  unsigned next = 0;
+};
+static std::mutex g_compMutex;
+static std::unordered_map<cudaStream_t, Companion *> g_comp;
+static bool copy_stream_enabled() {
+  static const bool on = getenv("CB200_NO_COPY_STREAM") == nullptr;
+  return on;
+}
+static Companion *companion(cudaStream_t user) {
+  std::lock_guard<std::mutex> lock(g_compMutex);
+  auto it = g_comp.find(user);
+  if (it != g_comp.end()) return it->second;
+  Companion *c = new Companion;
+  cudaChk(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  for (cudaEvent_t &e : c->ev) cudaChk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  g_comp[user] = c;
+  return c;
+}
+static void drop_companion(cudaStream_t user) {
+  std::lock_guard<std::mutex> lock(g_compMutex);
+  auto it = g_comp.find(user);
+  if (it == g_comp.end()) return;
+  cudaStreamDestroy(it->second->copy);
+  for (cudaEvent_t &e : it->second->ev) cudaEventDestroy(e);
+  delete it->second;
+  g_comp.erase(it);
+}
+/* stream on which a request's staging copies are issued */
+static cudaStream_t staging_stream(cudaStream_t user) { return copy_stream_enabled() ? companion(user)->copy : user; }
+/* everything issued on the staging stream so far becomes visible to `user` */
+static void staging_handoff(cudaStream_t user) {
+  if (!copy_stream_enabled()) return;
+  Companion *c = companion(user);
+  cudaEvent_t e;
+  {
+    std::lock_guard<std::mutex> lock(g_compMutex);
+    e = c->ev[c->next++ % 16];
+  }
+  cudaChk(cudaEventRecord(e, c->copy));
+  cudaChk(cudaStreamWaitEvent(user, e, 0));
 }
 
 /* ------------------------------------------------------------- timing taps */
@@ -157,6 +218,19 @@ static void launch_cell_list(const PackedPart *parts, VariablePartData *vars, co
   cudaChk(cudaPeekAtLastError());
 }
 
+#ifndef CUDA_USE_DOUBLE
+template <int PB, int MINB, bool DUAL>
+static void launch_cell_list_x2(const PackedPart *parts, VariablePartData *vars, const PackedCell *cells,
+                                const ILCell *list, const int *markers, const int *starts,
+                                const int *sizes, int nBuckets, real fperiod, unsigned *counter,
+                                cudaStream_t stream) {
+  static int ctas = resident_ctas(cell_list_x2_kernel<PB, MINB, DUAL>, cell_list_x2_smem_bytes<PB>());
+  cell_list_x2_kernel<PB, MINB, DUAL><<<list_grid(nBuckets, ctas), kListWarps * 32, cell_list_x2_smem_bytes<PB>(), stream>>>(
+      parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter);
+  cudaChk(cudaPeekAtLastError());
+}
+#endif
+
 template <int PB, int MINB>
 static void launch_part_list(const PackedPart *parts, VariablePartData *vars, const PackedPart *sources,
                              const ILCell *list, const int *markers, const int *starts,
@@ -179,12 +253,25 @@ static void dispatch_cell_list(int maxBucket, const PackedPart *parts, VariableP
   (void)maxBucket;
   launch_cell_list<8, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
 #else
-  if (maxBucket <= 8)
-    launch_cell_list<8, 4>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-  else if (maxBucket <= 12)
-    launch_cell_list<12, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-  else
-    launch_cell_list<16, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  static const bool scalar = getenv("CB200_PC_SCALAR") != nullptr; /* A/B switch: the pre-FFMA2 kernel */
+  if (scalar) {
+    if (maxBucket <= 8)
+      launch_cell_list<8, 4>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    else if (maxBucket <= 12)
+      launch_cell_list<12, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    else
+      launch_cell_list<16, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  } else if (maxBucket <= 8) {
+    launch_cell_list_x2<8, 3, false>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  } else {
+    static const int variant = getenv("CB200_PC_VARIANT") ? atoi(getenv("CB200_PC_VARIANT")) : 0; /* tuning switch */
+    if (variant == 1)
+      launch_cell_list_x2<12, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    else if (variant == 2)
+      launch_cell_list_x2<12, 4, false>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    else
+      launch_cell_list_x2<12, 3, false>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  }
 #endif
 }
 
@@ -326,7 +413,7 @@ static int max_bucket_size(const int *sizes, int n) {
 }
 
 static RequestScratch stage_request(CudaRequest *data, size_t missedPackedBytes, size_t missedRawBytes) {
-  cudaStream_t stream = data->stream;
+  cudaStream_t stream = staging_stream(data->stream);
   const int nb = data->numBucketsPlusOne - 1;
   const size_t sList = (size_t)data->numInteractions * sizeof(ILCell);
   const size_t sMark = (size_t)(nb + 1) * sizeof(int), sStart = (size_t)nb * sizeof(int);
@@ -366,8 +453,11 @@ static void cell_list_request(CudaRequest *data, Gather g) {
   const size_t nMissed = (g == G_MISSED) ? data->sMissed / sizeof(CudaMultipoleMoments) : 0;
   RequestScratch s = stage_request(data, nMissed * sizeof(PackedCell), (g == G_MISSED) ? data->sMissed : 0);
   const PackedCell *cells = (const PackedCell *)(g == G_LOCAL ? data->d_localMoments : data->d_remoteMoments);
-  if (g == G_MISSED) { /* moments travel with the request (HostCUDA.cu:296-342) */
-    cudaChk(cudaMemcpyAsync(s.missedRaw, data->missedNodes, data->sMissed, cudaMemcpyHostToDevice, stream));
+  if (g == G_MISSED) /* moments travel with the request (HostCUDA.cu:296-342) */
+    cudaChk(cudaMemcpyAsync(s.missedRaw, data->missedNodes, data->sMissed, cudaMemcpyHostToDevice,
+                            staging_stream(stream)));
+  staging_handoff(stream);
+  if (g == G_MISSED) {
     repack_cells(s.missedRaw, (PackedCell *)s.missedPacked, (int)nMissed, stream);
     cells = (const PackedCell *)s.missedPacked;
   }
@@ -389,8 +479,10 @@ static void part_list_request(CudaRequest *data, Gather g, const CompactPartData
   const size_t nExtra = sExtra / sizeof(CompactPartData);
   RequestScratch s = stage_request(data, nExtra * sizeof(PackedPart), sExtra);
   const PackedPart *src = (const PackedPart *)(g == G_LOCAL ? data->d_localParts : data->d_remoteParts);
+  if (g == G_MISSED)
+    cudaChk(cudaMemcpyAsync(s.missedRaw, h_extra, sExtra, cudaMemcpyHostToDevice, staging_stream(stream)));
+  staging_handoff(stream);
   if (g == G_MISSED) {
-    cudaChk(cudaMemcpyAsync(s.missedRaw, h_extra, sExtra, cudaMemcpyHostToDevice, stream));
     repack_parts(s.missedRaw, (PackedPart *)s.missedPacked, (int)nExtra, stream);
     src = (const PackedPart *)s.missedPacked;
   }
@@ -474,9 +566,11 @@ void EwaldHost(CompactPartData *d_localParts, VariablePartData *d_localVars, Ewa
   const int n = h_idata->cachedData->n;
   int *d_markers = nullptr;
   if (largephase && n > 0) {
-    d_markers = (int *)pool_alloc((size_t)n * sizeof(int), stream);
+    cudaStream_t st = staging_stream(stream);
+    d_markers = (int *)pool_alloc((size_t)n * sizeof(int), st);
     cudaChk(cudaMemcpyAsync(d_markers, h_idata->EwaldMarkers, (size_t)n * sizeof(int),
-                            cudaMemcpyHostToDevice, stream));
+                            cudaMemcpyHostToDevice, st));
+    staging_handoff(stream);
   }
   if (!largephase || d_markers)
     launch_ewald((const PackedPart *)d_localParts, d_localVars, d_markers, h_idata->EwaldRange[0],
@@ -505,7 +599,10 @@ void *cb200_stream_create(void) {
   cudaChk(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   return (void *)s;
 }
-void cb200_stream_destroy(void *stream) { cudaChk(cudaStreamDestroy((cudaStream_t)stream)); }
+void cb200_stream_destroy(void *stream) {
+  drop_companion((cudaStream_t)stream);
+  cudaChk(cudaStreamDestroy((cudaStream_t)stream));
+}
 void cb200_stream_synchronize(void *stream) { cudaChk(cudaStreamSynchronize((cudaStream_t)stream)); }
 void cb200_device_synchronize(void) { cudaChk(cudaDeviceSynchronize()); }
 void cb200_set_device(int ordinal) { cudaChk(cudaSetDevice(ordinal)); }

@@ -20,7 +20,7 @@ def hc():
     return HostCUDA(double=False, device=0)
 
 
-def oracle_forces(wl, np_real=np.float32, ewald_inner=1.1e-2):
+def oracle_forces(wl, np_real=np.float32, ewald_inner=1.2e-3):
     """double-precision CPU answer on the inputs as the device sees them (rounded to cudatype)"""
     parts = np.ascontiguousarray(wl["parts"].astype(np_real).astype(np.float64))
     mom = np.ascontiguousarray(wl["moments"].astype(np_real).astype(np.float64))
@@ -34,20 +34,24 @@ def oracle_forces(wl, np_real=np.float32, ewald_inner=1.1e-2):
     if ew:
         r = lambda a: np.asarray(a, dtype=np_real).astype(np.float64)
         orc.ewald(parts, ew.get("active"), r(ew["root"]), r(ew["momc"]), float(np_real(ew["L"])), ew["fEwCut"],
-                  ew["nReps"], int(np.ceil(ew["fEwCut"])), ew.get("fInner2coef", ewald_inner), r(ew["ewt"]), v)
+                  ew["nReps"], int(np.ceil(ew["fEwCut"])), ewald_inner, r(ew["ewt"]), v)   # the CPU path's series radius (Ewald.cpp:119)
     return v
 
 
-def compare(got, want, median_tol=MEDIAN_TOL, max_tol=MAX_TOL, pot_tol=POT_TOL):
+def compare(got, want, median_tol=MEDIAN_TOL, max_tol=MAX_TOL, pot_tol=POT_TOL, floor_frac=0.0):
+    """floor_frac: the worst-particle test divides by max(|a|, floor_frac * rms|a|) -- in a periodic
+    box the net force on some particles nearly cancels and |da|/|a| there measures the
+    cancellation, not the kernel.  The median test always uses |a| itself."""
     got = np.asarray(got, dtype=np.float64)
     amag = np.sqrt((want[:, :3] ** 2).sum(1))
     live = amag > 0
     da = np.sqrt(((got[:, :3] - want[:, :3]) ** 2).sum(1))
     rel = da[live] / amag[live]
+    rel_floor = da[live] / np.maximum(amag[live], floor_frac * np.sqrt((amag ** 2).mean()))
     assert np.all(np.isfinite(got))
     assert np.array_equal(got[~live, :3], want[~live, :3])      # untouched particles stay exactly zero
     assert np.median(rel) <= median_tol, f"median |da|/|a| = {np.median(rel):.3g}"
-    assert rel.max() <= max_tol, f"max |da|/|a| = {rel.max():.3g}"
+    assert rel_floor.max() <= max_tol, f"max |da|/|a| = {rel_floor.max():.3g}"
     pl = np.abs(want[:, 3]) > 0
     prel = np.abs(got[pl, 3] - want[pl, 3]) / np.abs(want[pl, 3])
     assert np.median(prel) <= pot_tol, f"median |dpot|/|pot| = {np.median(prel):.3g}"
@@ -153,7 +157,7 @@ def test_tree_workloads_match_oracle(hc, name, n):
     finally:
         step.free()
     # Ewald's erfc/exp chain in float costs a little more than the list kernels
-    compare(got, oracle_forces_tree(wl), median_tol=5e-6, max_tol=1e-3, pot_tol=2e-5)
+    compare(got, oracle_forces_tree(wl), median_tol=5e-6, max_tol=3e-4, pot_tol=2e-5, floor_frac=0.1)
 
 
 def test_resident_path_equals_abi_path(hc):

@@ -34,7 +34,8 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(HERE, "liboracle.so")
-        if not os.path.exists(so):
+        src = os.path.join(HERE, "gravity_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
             build()
         L = C.CDLL(so)
         d, i, vp = C.c_double, C.c_int, C.c_void_p
@@ -61,6 +62,7 @@ def lib():
         L.orc_open_criterion_node.argtypes = [dp, i, dp, dp, dp, dp, i, d, d]
         L.orc_open_criterion_node.restype = i
         L.orc_num_threads.restype = i
+        L.orc_set_num_threads.argtypes = [i]
         _LIB = L
     return _LIB
 

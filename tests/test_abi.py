@@ -1,0 +1,84 @@
+"""The drop-in boundary without a GPU: the library loads, exports every symbol the headers
+declare (C ABI) and the 17 C++-linkage entry points under exactly the mangled names the
+reference's own HostCUDA.cu produces (HostCUDA.h:99-126, EwaldCUDA.h:59-62, CudaFunctions.h:7-8)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from changa_b200 import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# nm -D of the reference's HostCUDA.cu compiled unmodified (oracle/_ref/libhostcuda_ref.so), host entry points
+REFERENCE_MANGLED = [
+    "_Z24allocatePinnedHostMemoryPPvm",
+    "_Z20freePinnedHostMemoryPv",
+    "_Z28DataManagerTransferLocalTreePvmS_mS_mPS_S0_S0_P11CUstream_stiS_",
+    "_Z30DataManagerTransferRemoteChunkPvmS_mPS_S0_P11CUstream_stS_",
+    "_Z24TransferParticleVarsBackP16VariablePartDatamPvP11CUstream_stS1_",
+    "_Z34TreePieceCellListDataTransferLocalP12_CudaRequest",
+    "_Z35TreePieceCellListDataTransferRemoteP12_CudaRequest",
+    "_Z41TreePieceCellListDataTransferRemoteResumeP12_CudaRequest",
+    "_Z34TreePiecePartListDataTransferLocalP12_CudaRequest",
+    "_Z44TreePiecePartListDataTransferLocalSmallPhaseP12_CudaRequestP15CompactPartDatai",
+    "_Z35TreePiecePartListDataTransferRemoteP12_CudaRequest",
+    "_Z41TreePiecePartListDataTransferRemoteResumeP12_CudaRequest",
+    "_Z26TreePieceDataTransferBasicP12_CudaRequestP11_CudaDevPtr",
+    "_Z33TreePieceDataTransferBasicCleanupP11_CudaDevPtr",
+    "_Z20EwaldHostMemorySetupP9EwaldDataiii",
+    "_Z19EwaldHostMemoryFreeP9EwaldDatai",
+    "_Z9EwaldHostP15CompactPartDataP16VariablePartDataP9EwaldDataP11CUstream_stPvii",
+]
+
+
+def exported(path):
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+
+
+@pytest.mark.parametrize("double", [False, True])
+def test_library_loads_and_exports_the_c_abi(double):
+    L = lib.load(double)
+    missing = [s for s in lib.C_ABI_SYMBOLS if not hasattr(L, s)]
+    assert not missing, missing
+    assert L.cb200_real_bytes() == (8 if double else 4)
+    assert L.cb200_abi_version() >= 1
+    assert b"sm_100a" in L.cb200_build_info()
+
+
+def test_header_declarations_are_all_exported():
+    """every cb200_* function include/changa_b200_api.h declares is in C_ABI_SYMBOLS and in the .so"""
+    hdr = open(os.path.join(ROOT, "include", "changa_b200_api.h")).read()
+    declared = set(re.findall(r"\b(cb200_[A-Za-z0-9_]+)\s*\(", hdr)) - {"cb200_callback_fn"}
+    syms = exported(lib.library_path(False))
+    assert declared <= syms, declared - syms
+    assert declared == set(lib.C_ABI_SYMBOLS), declared ^ set(lib.C_ABI_SYMBOLS)
+
+
+def test_cxx_entry_points_have_the_reference_mangled_names():
+    syms = exported(lib.library_path(False))
+    missing = [m for m in REFERENCE_MANGLED if m not in syms]
+    assert not missing, missing
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhostcuda_ref.so")),
+                    reason="oracle/_ref not built")
+def test_every_host_export_of_the_reference_build_is_matched():
+    ref = exported(os.path.join(ROOT, "oracle", "_ref", "libhostcuda_ref.so"))
+    ours = exported(lib.library_path(False))
+    host = {s for s in ref if s.startswith("_Z") and "device_stub" not in s
+            and not re.search(r"hapi|nodeGravityComputation|particleGravityComputation|EwaldKernel|ZeroVars|gpuLocalTreeWalk", s)}
+    assert host == set(REFERENCE_MANGLED), host ^ set(REFERENCE_MANGLED)
+    assert host <= ours
+
+
+def test_partition_buckets_host_side():
+    import numpy as np
+    cost = np.random.default_rng(0).uniform(1, 10, 1000)
+    for ranks in (1, 2, 4, 8):
+        cuts = lib.partition_buckets(cost, ranks)
+        assert cuts[0] == 0 and cuts[-1] == 1000 and np.all(np.diff(cuts) > 0)
+        loads = np.add.reduceat(cost, cuts[:-1])
+        assert loads.max() / loads.mean() < 1.02

@@ -172,11 +172,10 @@ class ResidentStep:
             parts = np.ascontiguousarray(wl["parts"], dtype=f32)
             mom = np.ascontiguousarray(wl["moments"], dtype=f32)
             if world > 1:  # every rank owns an equal, padded slice of both arrays; one all-gather each
-                self.pc, self.mc = -(-self.n // world), -(-self.nn // world)
-                pp = np.zeros((self.pc * world, 5), dtype=f32); pp[: self.n] = parts
-                mm = np.zeros((self.mc * world, 27), dtype=f32); mm[: self.nn] = mom
-                self.my_parts = up(pp[rank * self.pc:(rank + 1) * self.pc])
-                self.my_mom = up(mm[rank * self.mc:(rank + 1) * self.mc])
+                from changa_b200.multigpu import shard_rows
+                mine_p, self.pc = shard_rows(parts, rank, world)
+                mine_m, self.mc = shard_rows(mom, rank, world)
+                self.my_parts, self.my_mom = up(mine_p), up(mine_m)
                 self.raw_parts = torch.zeros((self.pc * world, 5), dtype=torch.float32, device=dev)
                 self.raw_mom = torch.zeros((self.mc * world, 27), dtype=torch.float32, device=dev)
             else:
@@ -210,8 +209,9 @@ class ResidentStep:
     def step(self):
         L, s = self.hc.L, self.stream
         if self.world > 1:
-            self.dist.all_gather_into_tensor(self.raw_parts, self.my_parts)
-            self.dist.all_gather_into_tensor(self.raw_mom, self.my_mom)
+            from changa_b200.multigpu import gather_rows
+            gather_rows(self.dist, self.torch, self.my_parts, self.world, out=self.raw_parts)
+            gather_rows(self.dist, self.torch, self.my_mom, self.world, out=self.raw_mom)
         L.cb200_pack_moments_device(self.raw_mom.data_ptr(), self.pk_mom.data_ptr(), self.nmk, s)
         L.cb200_pack_particles_device(self.raw_parts.data_ptr(), self.pk_parts.data_ptr(), self.npk, s)
         L.cb200_zero_vars_device(self.vars.data_ptr(), self.n, s)

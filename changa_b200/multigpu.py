@@ -1,0 +1,31 @@
+"""Host logic of the multi-GPU force step: one process per GPU, buckets cut into
+contiguous SFC ranges, particle and moment records replicated with one all-gather each per step.
+Backend-agnostic (`torch.distributed`: nccl on the GPUs, gloo in the CPU tests)."""
+import numpy as np
+
+
+def shard_rows(a, rank, world):
+    """equal, zero-padded row slices of a 2-D array: what each rank contributes to the all-gather.
+    Returns (my_rows, rows_per_rank)."""
+    a = np.ascontiguousarray(a)
+    chunk = -(-a.shape[0] // world)
+    padded = np.zeros((chunk * world,) + a.shape[1:], dtype=a.dtype)
+    padded[: a.shape[0]] = a
+    return padded[rank * chunk:(rank + 1) * chunk].copy(), chunk
+
+
+def gather_rows(dist, torch, mine, world, out=None):
+    """one all_gather_into_tensor; `mine` is this rank's (chunk, cols) tensor"""
+    if out is None:
+        out = torch.empty((mine.shape[0] * world,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(out, mine)
+    return out
+
+
+def bucket_cuts_by_particles(bucket_sizes, world):
+    """contiguous bucket ranges holding (nearly) equal particle counts; never splits a bucket"""
+    csum = np.cumsum(bucket_sizes)
+    n = int(csum[-1])
+    cuts = np.searchsorted(csum, np.arange(1, world) * n / world, side="left") + 1
+    cuts = np.concatenate([[0], np.minimum(cuts, len(bucket_sizes)), [len(bucket_sizes)]])
+    return np.maximum.accumulate(cuts).astype(np.int64)

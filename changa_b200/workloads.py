@@ -231,8 +231,8 @@ def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_ran
     rng_b = None
     if bucket_range_of is not None:
         rank, world = bucket_range_of
-        cuts = np.searchsorted(np.cumsum(t.bucket_sizes), np.arange(1, world) * t.n / world, side="left") + 1
-        cuts = np.concatenate([[0], cuts, [t.num_buckets]])
+        from .multigpu import bucket_cuts_by_particles
+        cuts = bucket_cuts_by_particles(t.bucket_sizes, world)
         rng_b = (int(cuts[rank]), int(cuts[rank + 1]))
     wl = tree_workload(None, None, None, theta=cfg["theta"], n_replicas=cfg["n_replicas"], period=1.0,
                        ewald={} if cfg["ewald"] else None, bucket_range=rng_b, tree=t,

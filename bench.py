@@ -216,6 +216,8 @@ class ResidentStep:
         L.cb200_pack_particles_device(self.raw_parts.data_ptr(), self.pk_parts.data_ptr(), self.npk, s)
         L.cb200_zero_vars_device(self.vars.data_ptr(), self.n, s)
         P, V, M = self.pk_parts.data_ptr(), self.vars.data_ptr(), self.pk_mom.data_ptr()
+        if self.ew is not None:  # same order as ForceStep.run: Ewald needs only the particles
+            L.cb200_ewald_device(P, V, self.ew_markers.data_ptr(), self.ew_n, self.ew.cachedData, self.ew.ewt, s)
         if "cell" in self.lists:
             il, m, st, sz, nb, mx = self.lists["cell"]
             L.cb200_cell_list_device_ex(P, V, M, il.data_ptr(), m.data_ptr(), st.data_ptr(), sz.data_ptr(), nb,
@@ -228,8 +230,6 @@ class ResidentStep:
             il, m, st, sz, nb, mx = self.lists["softcell"]
             L.cb200_part_list_device_ex(P, V, self.soft_src.data_ptr(), il.data_ptr(), m.data_ptr(), st.data_ptr(),
                                         sz.data_ptr(), nb, self.fperiod, mx, s)
-        if self.ew is not None:
-            L.cb200_ewald_device(P, V, self.ew_markers.data_ptr(), self.ew_n, self.ew.cachedData, self.ew.ewt, s)
 
     def timed(self, steps, warmup):
         torch = self.torch

@@ -785,6 +785,169 @@ part_list_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restr
   }
 }
 
+#ifndef CUDA_USE_DOUBLE
+/* ---------------------------------------- particle-particle, packed f32x2 math */
+/* Same idea as cell_list_x2_kernel: the lane keeps ONE source particle and meets
+ * TWO targets per instruction.  The unsoftened branch (r >= soft_s + soft_t for
+ * both targets, by far the common case) is 17 packed FP instructions + 2 MUFU.RSQ
+ * per two pairs; a pair that needs the spline falls back to the scalar pp_pair
+ * for both halves (gravity.h:147-182). */
+struct TargetSoftPair { f32x2 x, y, z, m, soft; float pad[2]; }; /* 48 bytes */
+
+__device__ __forceinline__ void pp_pair2(float sx, float sy, float sz, float sm, float ssoft,
+                                         const TargetSoftPair &p, f32x2 &ax, f32x2 &ay, f32x2 &az,
+                                         f32x2 &pot, float &idt0, float &idt1) {
+  const f32x2 rx = sub2(bc2(sx), p.x), ry = sub2(bc2(sy), p.y), rz = sub2(bc2(sz), p.z);
+  const f32x2 rsq = fma2(rz, rz, fma2(ry, ry, mul2(rx, rx)));
+  const f32x2 twoh = add2(p.soft, bc2(ssoft));
+  float q0, q1, h0, h1;
+  unpk2(rsq, q0, q1);
+  unpk2(mul2(twoh, twoh), h0, h1);
+  if (q0 >= h0 && q1 >= h1) { /* both Newtonian; rsq > 0 is implied unless both softenings are 0 */
+    float d0 = rsqrt_dev(q0), d1 = rsqrt_dev(q1);
+    d0 = (q0 != 0.0f) ? d0 : 0.0f;
+    d1 = (q1 != 0.0f) ? d1 : 0.0f;
+    const f32x2 d = pk2(d0, d1);
+    const f32x2 b = mul2(mul2(d, d), d);
+    const f32x2 bm = mul2s(sm, b);
+    ax = fma2(rx, bm, ax);
+    ay = fma2(ry, bm, ay);
+    az = fma2(rz, bm, az);
+    pot = fma2(bc2(-sm), d, pot);
+    float i0, i1;
+    unpk2(mul2(add2(p.m, bc2(sm)), b), i0, i1);
+    idt0 = fmaxf(idt0, i0);
+    idt1 = fmaxf(idt1, i1);
+  } else { /* at least one softened pair: the scalar spline for both halves */
+    float x0, x1, y0, y1, z0, z1, m0, m1, s0, s1;
+    unpk2(p.x, x0, x1); unpk2(p.y, y0, y1); unpk2(p.z, z0, z1); unpk2(p.m, m0, m1); unpk2(p.soft, s0, s1);
+    float a0, a1, b0, b1, c0, c1, e0, e1;
+    unpk2(ax, a0, a1); unpk2(ay, b0, b1); unpk2(az, c0, c1); unpk2(pot, e0, e1);
+    const real4 t0 = {x0, y0, z0, m0}, t1 = {x1, y1, z1, m1};
+    pp_pair(sx, sy, sz, sm, ssoft, t0, s0, a0, b0, c0, e0, idt0);
+    pp_pair(sx, sy, sz, sm, ssoft, t1, s1, a1, b1, c1, e1, idt1);
+    ax = pk2(a0, a1); ay = pk2(b0, b1); az = pk2(c0, c1); pot = pk2(e0, e1);
+  }
+}
+
+template <int PB>
+constexpr size_t part_list_x2_smem_bytes() {
+  return (size_t)kListWarps * (5 * PB * 32 * sizeof(float) + (PB / 2) * sizeof(TargetSoftPair));
+}
+
+template <int PB, int MINB>
+__global__ void __launch_bounds__(kListWarps * 32, MINB)
+part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
+                    const PackedPart *__restrict__ sources, const ILCell *__restrict__ list,
+                    const int *__restrict__ markers, const int *__restrict__ starts,
+                    const int *__restrict__ sizes, int nBuckets, float fperiod,
+                    unsigned int *__restrict__ nextBucket) {
+  static_assert(PB % 2 == 0 && 5 * PB <= 64, "two reduction rows per lane at most");
+  constexpr int NP = PB / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *red = reinterpret_cast<float *>(smem_raw) + (size_t)warp * (5 * PB * 32);
+  TargetSoftPair *sp = reinterpret_cast<TargetSoftPair *>(smem_raw + (size_t)kListWarps * 5 * PB * 32 * sizeof(float)) + warp * NP;
+  const ILCell none = {-1, 0};
+
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = (int)atomicAdd(nextBucket, 1u);
+    k = __shfl_sync(kFull, k, 0);
+    if (k >= nBuckets) break;
+    const BucketMeta m = load_bucket_meta(markers, starts, sizes, k);
+    if (m.len <= 0) continue;
+    const ILCell *__restrict__ mylist = list + m.begin;
+    const int len = m.len, ntiles = (len + 31) >> 5;
+
+    for (int p0 = 0; p0 < m.count; p0 += PB) {
+      const int np = min(PB, m.count - p0);
+      const int npairs = (np + 1) >> 1;
+      __syncwarp();
+      if (lane < 2 * npairs) {
+        const PackedPart *q = parts + m.first + p0 + min(lane, np - 1);
+        const float4 v = *reinterpret_cast<const float4 *>(q);
+        float *dst = reinterpret_cast<float *>(sp + (lane >> 1)) + (lane & 1);
+        dst[0] = v.x; dst[2] = v.y; dst[4] = v.z; dst[6] = v.w; dst[8] = q->soft;
+      }
+      __syncwarp();
+
+      f32x2 ax[NP], ay[NP], az[NP], pot[NP];
+      float idt[PB];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) { ax[j] = ay[j] = az[j] = pot[j] = 0ull; idt[2 * j] = idt[2 * j + 1] = 0.0f; }
+
+      /* source rows one tile ahead in registers, list entries two ahead */
+      ILCell cur = none, nxt = none;
+      if (lane < len) cur = mylist[lane];
+      if (32 + lane < len) nxt = mylist[32 + lane];
+      float4 s_pos = {0, 0, 0, 0};
+      float s_soft = 0;
+      if (cur.index >= 0) {
+        const PackedPart *q = sources + cur.index;
+        s_pos = *reinterpret_cast<const float4 *>(q);
+        s_soft = q->soft;
+      }
+      for (int t = 0; t < ntiles; ++t) {
+        float4 n_pos = {0, 0, 0, 0};
+        float n_soft = 0;
+        if (nxt.index >= 0) {
+          const PackedPart *q = sources + nxt.index;
+          n_pos = *reinterpret_cast<const float4 *>(q);
+          n_soft = q->soft;
+        }
+        ILCell nn = none;
+        if ((t + 2) * 32 + lane < len) nn = mylist[(t + 2) * 32 + lane];
+        if (cur.index >= 0) {
+          const float sx = fmaf(float(replica_x(cur.offsetID)), fperiod, s_pos.x);
+          const float sy = fmaf(float(replica_y(cur.offsetID)), fperiod, s_pos.y);
+          const float sz = fmaf(float(replica_z(cur.offsetID)), fperiod, s_pos.z);
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            if (j < npairs) {
+              const TargetSoftPair p = sp[j];
+              pp_pair2(sx, sy, sz, s_pos.w, s_soft, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
+            }
+          }
+        }
+        cur = nxt; nxt = nn;
+        s_pos = n_pos; s_soft = n_soft;
+      }
+
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        if (j < npairs) {
+          float a0, a1, b0, b1, c0, c1, e0, e1;
+          unpk2(ax[j], a0, a1); unpk2(ay[j], b0, b1); unpk2(az[j], c0, c1); unpk2(pot[j], e0, e1);
+          float *r0 = red + (size_t)(2 * j) * 5 * 32 + lane;
+          r0[0] = a0; r0[32] = b0; r0[64] = c0; r0[96] = e0; r0[128] = idt[2 * j];
+          r0[160] = a1; r0[192] = b1; r0[224] = c1; r0[256] = e1; r0[288] = idt[2 * j + 1];
+        }
+      }
+      __syncwarp();
+      float *out = reinterpret_cast<float *>(vars + m.first + p0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = lane + 32 * h;
+        if (v < 5 * np) {
+          const float *row = red + v * 32;
+          const bool isMax = (v % 5) == 4;
+          float acc = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = row[(i + lane) & 31];
+            acc = isMax ? fmaxf(acc, x) : acc + x;
+          }
+          out[v] = isMax ? fmaxf(out[v], acc) : out[v] + acc;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+#endif /* !CUDA_USE_DOUBLE */
+
 /* ------------------------------------------------------------------ Ewald */
 struct EwaldParams {
   EwaldReadOnlyData ro;

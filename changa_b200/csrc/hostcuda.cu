@@ -242,6 +242,19 @@ static void launch_part_list(const PackedPart *parts, VariablePartData *vars, co
   cudaChk(cudaPeekAtLastError());
 }
 
+#ifndef CUDA_USE_DOUBLE
+template <int PB, int MINB>
+static void launch_part_list_x2(const PackedPart *parts, VariablePartData *vars, const PackedPart *sources,
+                                const ILCell *list, const int *markers, const int *starts,
+                                const int *sizes, int nBuckets, real fperiod, unsigned *counter,
+                                cudaStream_t stream) {
+  static int ctas = resident_ctas(part_list_x2_kernel<PB, MINB>, part_list_x2_smem_bytes<PB>());
+  part_list_x2_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, part_list_x2_smem_bytes<PB>(), stream>>>(
+      parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter);
+  cudaChk(cudaPeekAtLastError());
+}
+#endif
+
 /* maxBucket picks the register tile: targets per pass */
 static void dispatch_cell_list(int maxBucket, const PackedPart *parts, VariablePartData *vars,
                                const PackedCell *cells, const ILCell *list, const int *markers,
@@ -284,12 +297,19 @@ static void dispatch_part_list(int maxBucket, const PackedPart *parts, VariableP
   (void)maxBucket;
   launch_part_list<8, 2>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
 #else
-  if (maxBucket <= 8)
-    launch_part_list<8, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-  else if (maxBucket <= 12)
-    launch_part_list<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-  else
-    launch_part_list<16, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  static const bool scalar = getenv("CB200_PP_SCALAR") != nullptr; /* A/B switch: the pre-FFMA2 kernel */
+  if (scalar) {
+    if (maxBucket <= 8)
+      launch_part_list<8, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    else if (maxBucket <= 12)
+      launch_part_list<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    else
+      launch_part_list<16, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  } else if (maxBucket <= 8) {
+    launch_part_list_x2<8, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  } else {
+    launch_part_list_x2<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  }
 #endif
 }
 

@@ -322,34 +322,44 @@ class ForceStep:
     def d2h_bytes(self):
         return self.vars_out.nbytes
 
+    def _requests(self):
+        """CudaRequests of the step, built once (a TreePiece builds them in C++ as its lists fill up);
+        only the device handles change from step to step"""
+        if getattr(self, "_reqs", None) is None:
+            hc, reqs, k = self.hc, [], 0
+            for staged, call, node, extra in (
+                    (self.cell, hc.TreePieceCellListDataTransferLocal, True, None),
+                    (self.part, hc.TreePiecePartListDataTransferLocal, False, None),
+                    (self.soft, hc.TreePiecePartListDataTransferLocalSmallPhase, False, self.soft_src)):
+                if not staged:
+                    continue
+                for pl, pm, ps, pz, n in staged.chunks:
+                    st = self.streams[k % len(self.streams)]
+                    k += 1
+                    req = hc.make_request(st, None, None, None, pl.array, pm.array, ps.array, pz.array,
+                                          self.fperiod, node=node)
+                    reqs.append((req, call, extra))
+            self._reqs = reqs
+        return self._reqs
+
     def run(self, sync=True):
-        """enqueue the whole step; returns the (pinned) result array after the copy-back"""
+        """enqueue the whole step; returns the (pinned) result array after the copy-back.
+        Order on the stream: upload, Ewald (needs only the particles, so its kernel runs while the
+        first lists are still crossing PCIe), cell lists, particle lists, softened cells, copy back."""
         hc = self.hc
         s0 = self.streams[0]
         dm, dp, dv = hc.DataManagerTransferLocalTree(self.moments.array, self.parts.array, self.vars_in.array,
                                                      s0, self.np_)
         if len(self.streams) > 1:
             hc.stream_synchronize(s0)  # DataManager waits for the upload callback before the walks start
-        k = 0
-        for staged, call, node in ((self.cell, hc.TreePieceCellListDataTransferLocal, True),
-                                   (self.part, hc.TreePiecePartListDataTransferLocal, False)):
-            if not staged:
-                continue
-            for pl, pm, ps, pz, n in staged.chunks:
-                st = self.streams[k % len(self.streams)]
-                k += 1
-                req = hc.make_request(st, dm, dp, dv, pl.array, pm.array, ps.array, pz.array, self.fperiod,
-                                      node=node)
-                call(req)
-        if self.soft:
-            for pl, pm, ps, pz, n in self.soft.chunks:
-                st = self.streams[k % len(self.streams)]
-                k += 1
-                req = hc.make_request(st, dm, dp, dv, pl.array, pm.array, ps.array, pz.array, self.fperiod,
-                                      node=False)
-                hc.TreePiecePartListDataTransferLocalSmallPhase(req, self.soft_src.array)
         if self.ewald:
-            hc.EwaldHost(dp, dv, self.ewald, self.streams[k % len(self.streams)])
+            hc.EwaldHost(dp, dv, self.ewald, s0)
+        for req, call, extra in self._requests():
+            req.d_localMoments, req.d_localParts, req.d_localVars = dm, dp, dv
+            if extra is not None:
+                call(req, extra.array)
+            else:
+                call(req)
         if len(self.streams) > 1:
             for st in self.streams[1:]:
                 hc.stream_synchronize(st)

@@ -479,7 +479,7 @@ __device__ __forceinline__ BucketMeta load_bucket_meta(const int *__restrict__ m
   return m;
 }
 
-template <int PB, int MINB, bool DUAL>
+template <int PB, int MINB>
 __global__ void __launch_bounds__(kListWarps * 32, MINB)
 cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
                     const PackedCell *__restrict__ cells, const ILCell *__restrict__ list,
@@ -576,20 +576,6 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
           const float ccx = fmaf(float(replica_x(cur.offsetID)), fperiod, c[PK_CX]);
           const float ccy = fmaf(float(replica_y(cur.offsetID)), fperiod, c[PK_CY]);
           const float ccz = fmaf(float(replica_z(cur.offsetID)), fperiod, c[PK_CZ]);
-          if (DUAL) { /* two target pairs per straight-line block: twice the independent FMA chains */
-#pragma unroll
-            for (int j = 0; j < NP; j += 2) {
-              if (j + 1 < NP && j + 1 < npairs) {
-                const TargetPair pa = sp[j], pb = sp[j + 1];
-                pc_pair2(c, ccx, ccy, ccz, pa, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
-                pc_pair2(c, ccx, ccy, ccz, pb, ax[j + 1], ay[j + 1], az[j + 1], pot[j + 1], idt[2 * j + 2],
-                         idt[2 * j + 3]);
-              } else if (j < npairs) {
-                const TargetPair pa = sp[j];
-                pc_pair2(c, ccx, ccy, ccz, pa, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
-              }
-            }
-          } else {
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
               if (j < npairs) {
@@ -597,7 +583,6 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
                 pc_pair2(c, ccx, ccy, ccz, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
               }
             }
-          }
         }
         __syncwarp();
         cur = nxt;
@@ -803,7 +788,8 @@ __device__ __forceinline__ void pp_pair2(float sx, float sy, float sz, float sm,
   float q0, q1, h0, h1;
   unpk2(rsq, q0, q1);
   unpk2(mul2(twoh, twoh), h0, h1);
-  if (q0 >= h0 && q1 >= h1) { /* both Newtonian; rsq > 0 is implied unless both softenings are 0 */
+  /* Newtonian, or exactly coincident (self pair: contributes nothing, d = 0 below) */
+  if ((q0 >= h0 || q0 == 0.0f) && (q1 >= h1 || q1 == 0.0f)) {
     float d0 = rsqrt_dev(q0), d1 = rsqrt_dev(q1);
     d0 = (q0 != 0.0f) ? d0 : 0.0f;
     d1 = (q1 != 0.0f) ? d1 : 0.0f;
@@ -849,26 +835,60 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
   float *red = reinterpret_cast<float *>(smem_raw) + (size_t)warp * (5 * PB * 32);
   TargetSoftPair *sp = reinterpret_cast<TargetSoftPair *>(smem_raw + (size_t)kListWarps * 5 * PB * 32 * sizeof(float)) + warp * NP;
   const ILCell none = {-1, 0};
-
-  for (;;) {
+  auto grab = [&]() {
     int k = 0;
     if (lane == 0) k = (int)atomicAdd(nextBucket, 1u);
-    k = __shfl_sync(kFull, k, 0);
-    if (k >= nBuckets) break;
-    const BucketMeta m = load_bucket_meta(markers, starts, sizes, k);
-    if (m.len <= 0) continue;
+    return __shfl_sync(kFull, k, 0);
+  };
+  auto load_source = [&](const ILCell &e, float4 &pos, float &soft) {
+    pos = make_float4(0.f, 0.f, 0.f, 0.f);
+    soft = 0.f;
+    if (e.index >= 0) {
+      const PackedPart *q = sources + e.index;
+      pos = *reinterpret_cast<const float4 *>(q);
+      soft = q->soft;
+    }
+  };
+
+  /* one bucket ahead, as in cell_list_x2_kernel: markers of bucket k+1 are loaded while k
+   * runs; its first two list tiles, its first source rows and its targets are requested
+   * during the last tile of k */
+  int k = grab();
+  BucketMeta m = {0, 0, 0, 0};
+  if (k < nBuckets) m = load_bucket_meta(markers, starts, sizes, k);
+  bool havePre = false;
+  ILCell pre0 = none, pre1 = none;
+  float4 preq = {0.f, 0.f, 0.f, 0.f}, pres = {0.f, 0.f, 0.f, 0.f};
+  float preqSoft = 0.f, presSoft = 0.f;
+
+  while (k < nBuckets) {
+    const int kn = grab();
+    BucketMeta mn = {0, 0, 0, 0};
+    if (kn < nBuckets) mn = load_bucket_meta(markers, starts, sizes, kn);
+    bool nextPre = false;
+    ILCell npre0 = none, npre1 = none;
+    float4 npreq = {0.f, 0.f, 0.f, 0.f}, npres = {0.f, 0.f, 0.f, 0.f};
+    float npreqSoft = 0.f, npresSoft = 0.f;
+
     const ILCell *__restrict__ mylist = list + m.begin;
     const int len = m.len, ntiles = (len + 31) >> 5;
 
-    for (int p0 = 0; p0 < m.count; p0 += PB) {
+    for (int p0 = 0; p0 < m.count && len > 0; p0 += PB) {
       const int np = min(PB, m.count - p0);
       const int npairs = (np + 1) >> 1;
+      const bool lastPass = p0 + PB >= m.count;
+      const bool usePre = havePre && p0 == 0;
       __syncwarp();
       if (lane < 2 * npairs) {
-        const PackedPart *q = parts + m.first + p0 + min(lane, np - 1);
-        const float4 v = *reinterpret_cast<const float4 *>(q);
+        float4 v = preq;
+        float vs = preqSoft;
+        if (!usePre) {
+          const PackedPart *q = parts + m.first + p0 + min(lane, np - 1);
+          v = *reinterpret_cast<const float4 *>(q);
+          vs = q->soft;
+        }
         float *dst = reinterpret_cast<float *>(sp + (lane >> 1)) + (lane & 1);
-        dst[0] = v.x; dst[2] = v.y; dst[4] = v.z; dst[6] = v.w; dst[8] = q->soft;
+        dst[0] = v.x; dst[2] = v.y; dst[4] = v.z; dst[6] = v.w; dst[8] = vs;
       }
       __syncwarp();
 
@@ -879,25 +899,33 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
 
       /* source rows one tile ahead in registers, list entries two ahead */
       ILCell cur = none, nxt = none;
-      if (lane < len) cur = mylist[lane];
-      if (32 + lane < len) nxt = mylist[32 + lane];
-      float4 s_pos = {0, 0, 0, 0};
-      float s_soft = 0;
-      if (cur.index >= 0) {
-        const PackedPart *q = sources + cur.index;
-        s_pos = *reinterpret_cast<const float4 *>(q);
-        s_soft = q->soft;
+      float4 s_pos;
+      float s_soft;
+      if (usePre) {
+        cur = pre0; nxt = pre1; s_pos = pres; s_soft = presSoft;
+      } else {
+        if (lane < len) cur = mylist[lane];
+        if (32 + lane < len) nxt = mylist[32 + lane];
+        load_source(cur, s_pos, s_soft);
       }
       for (int t = 0; t < ntiles; ++t) {
-        float4 n_pos = {0, 0, 0, 0};
-        float n_soft = 0;
-        if (nxt.index >= 0) {
-          const PackedPart *q = sources + nxt.index;
-          n_pos = *reinterpret_cast<const float4 *>(q);
-          n_soft = q->soft;
-        }
+        float4 n_pos;
+        float n_soft;
+        load_source(nxt, n_pos, n_soft);
         ILCell nn = none;
         if ((t + 2) * 32 + lane < len) nn = mylist[(t + 2) * 32 + lane];
+        if (lastPass && t == ntiles - 1 && mn.len > 0) {
+          const ILCell *nl = list + mn.begin;
+          if (lane < mn.len) npre0 = nl[lane];
+          if (32 + lane < mn.len) npre1 = nl[32 + lane];
+          const int npn = min(PB, mn.count);
+          if (lane < 2 * ((npn + 1) >> 1)) {
+            const PackedPart *q = parts + mn.first + min(lane, npn - 1);
+            npreq = *reinterpret_cast<const float4 *>(q);
+            npreqSoft = q->soft;
+          }
+          nextPre = true;
+        }
         if (cur.index >= 0) {
           const float sx = fmaf(float(replica_x(cur.offsetID)), fperiod, s_pos.x);
           const float sy = fmaf(float(replica_y(cur.offsetID)), fperiod, s_pos.y);
@@ -910,6 +938,7 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
             }
           }
         }
+        if (nextPre && lastPass && t == ntiles - 1) load_source(npre0, npres, npresSoft); /* after the math: its index has landed */
         cur = nxt; nxt = nn;
         s_pos = n_pos; s_soft = n_soft;
       }
@@ -944,6 +973,8 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
       }
       __syncwarp();
     }
+    k = kn; m = mn;
+    havePre = nextPre; pre0 = npre0; pre1 = npre1; preq = npreq; preqSoft = npreqSoft; pres = npres; presSoft = npresSoft;
   }
 }
 #endif /* !CUDA_USE_DOUBLE */

@@ -219,13 +219,13 @@ static void launch_cell_list(const PackedPart *parts, VariablePartData *vars, co
 }
 
 #ifndef CUDA_USE_DOUBLE
-template <int PB, int MINB, bool DUAL>
+template <int PB, int MINB>
 static void launch_cell_list_x2(const PackedPart *parts, VariablePartData *vars, const PackedCell *cells,
                                 const ILCell *list, const int *markers, const int *starts,
                                 const int *sizes, int nBuckets, real fperiod, unsigned *counter,
                                 cudaStream_t stream) {
-  static int ctas = resident_ctas(cell_list_x2_kernel<PB, MINB, DUAL>, cell_list_x2_smem_bytes<PB>());
-  cell_list_x2_kernel<PB, MINB, DUAL><<<list_grid(nBuckets, ctas), kListWarps * 32, cell_list_x2_smem_bytes<PB>(), stream>>>(
+  static int ctas = resident_ctas(cell_list_x2_kernel<PB, MINB>, cell_list_x2_smem_bytes<PB>());
+  cell_list_x2_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, cell_list_x2_smem_bytes<PB>(), stream>>>(
       parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter);
   cudaChk(cudaPeekAtLastError());
 }
@@ -275,15 +275,9 @@ static void dispatch_cell_list(int maxBucket, const PackedPart *parts, VariableP
     else
       launch_cell_list<16, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   } else if (maxBucket <= 8) {
-    launch_cell_list_x2<8, 3, false>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    launch_cell_list_x2<8, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   } else {
-    static const int variant = getenv("CB200_PC_VARIANT") ? atoi(getenv("CB200_PC_VARIANT")) : 0; /* tuning switch */
-    if (variant == 1)
-      launch_cell_list_x2<12, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-    else if (variant == 2)
-      launch_cell_list_x2<12, 4, false>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-    else
-      launch_cell_list_x2<12, 3, false>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    launch_cell_list_x2<12, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   }
 #endif
 }
@@ -308,7 +302,11 @@ static void dispatch_part_list(int maxBucket, const PackedPart *parts, VariableP
   } else if (maxBucket <= 8) {
     launch_part_list_x2<8, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   } else {
-    launch_part_list_x2<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    static const int variant = getenv("CB200_PP_VARIANT") ? atoi(getenv("CB200_PP_VARIANT")) : 0; /* tuning switch */
+    if (variant == 1)
+      launch_part_list_x2<12, 3>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    else
+      launch_part_list_x2<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   }
 #endif
 }

@@ -32,6 +32,8 @@
 #include "../../include/changa_b200_api.h"
 #include "gravity_kernels.cuh"
 #include "moments_build.cuh"
+#include "walk_kernels.cuh"
+#include <cub/device/device_scan.cuh>
 
 #ifdef CB200_WITH_CHARM_HAPI
 #include "hapi.h"
@@ -723,6 +725,9 @@ void cb200_pack_particles_device(const void *d_raw, void *d_packed, int n, void 
 void cb200_zero_vars_device(void *d_vars, int n, void *stream) {
   if (n > 0) cudaChk(cudaMemsetAsync(d_vars, 0, (size_t)n * sizeof(VariablePartData), (cudaStream_t)stream));
 }
+void cb200_copy_device(void *dst, const void *src, size_t bytes, void *stream) {
+  if (bytes) cudaChk(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+}
 size_t cb200_packed_moment_bytes(void) { return sizeof(PackedCell); }
 size_t cb200_packed_particle_bytes(void) { return sizeof(PackedPart); }
 
@@ -768,6 +773,106 @@ void cb200_build_moments(const double *d_pos_xyz, const double *d_mass, const do
     g_launches.fetch_add(1);
   }
   pool_free(work, s);
+}
+
+/* ---- interaction lists on the device ---- */
+void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h_levelStart,
+                       const int *d_child0, const int *d_child1, const int *d_parent,
+                       const int *d_firstPart, const int *d_lastPart, const int *d_bucketFirst,
+                       const int *d_bucketCount, const int *d_bucketNode, const double *d_boxlo_xyz,
+                       const double *d_boxhi_xyz, const double *d_moments_f64, double theta, int nReplicas,
+                       double period, int bucketLo, int bucketHi, cb200_lists *out, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  memset(out, 0, sizeof *out);
+  out->numBuckets = numBuckets;
+  if (numNodes <= 0 || numBuckets <= 0) return;
+  const int sms = device_info().sms;
+  WalkTree t;
+  t.numNodes = numNodes; t.numBuckets = numBuckets;
+  t.child0 = d_child0; t.child1 = d_child1; t.parent = d_parent; t.first = d_firstPart; t.last = d_lastPart;
+  t.bucketFirst = d_bucketFirst; t.bucketCount = d_bucketCount; t.bucketNode = d_bucketNode;
+  t.boxlo = d_boxlo_xyz; t.boxhi = d_boxhi_xyz; t.mom = d_moments_f64;
+  WalkParams p;
+  p.theta = theta; p.thetaMono = theta * theta * theta * theta; /* TreePiece.cpp:5036 */
+  p.period = period; p.nReplicas = nReplicas;
+  p.bucketLo = bucketLo < 0 ? 0 : bucketLo;
+  p.bucketHi = bucketHi > numBuckets ? numBuckets : bucketHi;
+
+  /* per-node list slices come from three pools sized from the tree (host walk: ~110 cell,
+   * ~45 undecided, ~12 bucket entries per node); the error flag reports an overflow */
+  WalkPools pools;
+  pools.capC = (unsigned long long)numNodes * 256 + (1u << 16);
+  pools.capU = (unsigned long long)numNodes * 128 + (1u << 16);
+  pools.capL = (unsigned long long)numNodes * 64 + (1u << 16);
+  pools.clist = (WalkEntry *)pool_alloc(pools.capC * sizeof(WalkEntry), s);
+  pools.lplist = (WalkEntry *)pool_alloc(pools.capL * sizeof(WalkEntry), s);
+  pools.undlist = (WalkEntry *)pool_alloc(pools.capU * sizeof(WalkEntry), s);
+  char *ctl = (char *)pool_alloc(256, s);
+  cudaChk(cudaMemsetAsync(ctl, 0, 256, s));
+  pools.used = (unsigned long long *)ctl;
+  pools.error = (int *)(ctl + 64);
+  NodeLists *lists = (NodeLists *)pool_alloc((size_t)numNodes * sizeof(NodeLists), s);
+  const int walkCtas = sms;
+  WalkEntry *scratch = (WalkEntry *)pool_alloc((size_t)walkCtas * kWalkWarps * 4 * kWalkCap * sizeof(WalkEntry), s);
+  for (int lvl = 0; lvl < numLevels; ++lvl) {
+    const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
+    if (n <= 0) continue;
+    const int need = (n + kWalkWarps - 1) / kWalkWarps;
+    walk_level_kernel<<<need < walkCtas ? need : walkCtas, kWalkWarps * 32, 0, s>>>(t, p, lo, n, lists, pools, scratch);
+    cudaChk(cudaPeekAtLastError());
+    g_launches.fetch_add(1);
+  }
+
+  /* per-bucket sizes -> markers */
+  const size_t nb1 = (size_t)numBuckets + 1;
+  int *counts = (int *)pool_alloc(3 * nb1 * sizeof(int), s);
+  cudaChk(cudaMemsetAsync(counts, 0, 3 * nb1 * sizeof(int), s));
+  out->d_cellMarkers = (int *)pool_alloc(nb1 * sizeof(int), s);
+  out->d_softMarkers = (int *)pool_alloc(nb1 * sizeof(int), s);
+  out->d_partMarkers = (int *)pool_alloc(nb1 * sizeof(int), s);
+  out->d_starts = (int *)pool_alloc(nb1 * sizeof(int), s);
+  out->d_sizes = (int *)pool_alloc(nb1 * sizeof(int), s);
+  const int emitGrid = (numBuckets + kWalkWarps - 1) / kWalkWarps;
+  emit_count_kernel<<<emitGrid, kWalkWarps * 32, 0, s>>>(t, p, lists, pools, counts, counts + nb1, counts + 2 * nb1,
+                                                       out->d_starts, out->d_sizes);
+  cudaChk(cudaPeekAtLastError());
+  size_t tmpBytes = 0;
+  cudaChk(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts, out->d_cellMarkers, (int)nb1, s));
+  void *tmp = pool_alloc(tmpBytes, s);
+  cudaChk(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, counts, out->d_cellMarkers, (int)nb1, s));
+  cudaChk(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, counts + nb1, out->d_softMarkers, (int)nb1, s));
+  cudaChk(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, counts + 2 * nb1, out->d_partMarkers, (int)nb1, s));
+  g_launches.fetch_add(4);
+  int totals[4] = {0, 0, 0, 0};
+  cudaChk(cudaMemcpyAsync(&totals[0], out->d_cellMarkers + numBuckets, sizeof(int), cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaMemcpyAsync(&totals[1], out->d_softMarkers + numBuckets, sizeof(int), cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaMemcpyAsync(&totals[2], out->d_partMarkers + numBuckets, sizeof(int), cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaMemcpyAsync(&totals[3], pools.error, sizeof(int), cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaStreamSynchronize(s)); /* the list sizes decide the allocations below */
+  out->nCell = totals[0]; out->nSoft = totals[1]; out->nPart = totals[2]; out->error = totals[3];
+  if (!out->error) {
+    out->d_cell = (ILCell *)pool_alloc((size_t)(totals[0] > 0 ? totals[0] : 1) * sizeof(ILCell), s);
+    out->d_soft = (ILCell *)pool_alloc((size_t)(totals[1] > 0 ? totals[1] : 1) * sizeof(ILCell), s);
+    out->d_part = (ILCell *)pool_alloc((size_t)(totals[2] > 0 ? totals[2] : 1) * sizeof(ILCell), s);
+    emit_fill_kernel<<<emitGrid, kWalkWarps * 32, 0, s>>>(t, p, lists, pools, out->d_cellMarkers, out->d_softMarkers,
+                                                        out->d_partMarkers, out->d_cell, out->d_soft, out->d_part);
+    cudaChk(cudaPeekAtLastError());
+    out->d_nodeParticles = pool_alloc((size_t)numNodes * sizeof(PackedPart), s);
+    nodes_as_particles_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(d_moments_f64, (PackedPart *)out->d_nodeParticles,
+                                                                    numNodes);
+    cudaChk(cudaPeekAtLastError());
+    g_launches.fetch_add(3);
+  }
+  pool_free(tmp, s); pool_free(counts, s); pool_free(scratch, s); pool_free(lists, s); pool_free(ctl, s);
+  pool_free(pools.clist, s); pool_free(pools.lplist, s); pool_free(pools.undlist, s);
+}
+
+void cb200_lists_free(cb200_lists *l, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  pool_free(l->d_cell, s); pool_free(l->d_soft, s); pool_free(l->d_part, s);
+  pool_free(l->d_cellMarkers, s); pool_free(l->d_softMarkers, s); pool_free(l->d_partMarkers, s);
+  pool_free(l->d_starts, s); pool_free(l->d_sizes, s); pool_free(l->d_nodeParticles, s);
+  memset(l, 0, sizeof *l);
 }
 
 /* ---- bucket partitioner: contiguous SFC ranges of equal cost ---- */

@@ -210,6 +210,7 @@ struct Arena {
   std::vector<int> part; /* ILPart triples */
   std::vector<int> soft; /* ILCell pairs: node index, offsetID */
   long long opened = 0, tested = 0;
+  long long visited = 0, maxChk = 0, maxC = 0, maxL = 0, maxU = 0, sumC = 0, sumL = 0, sumU = 0;
 };
 
 struct Walk {
@@ -357,6 +358,11 @@ struct Walk {
       const OffsetNode e = chk[head];
       process(e.node, reencode_offset(target, e.offsetID), my, L, chk, A);
     }
+    A.visited++;
+    A.maxChk = std::max<long long>(A.maxChk, (long long)chk.size());
+    A.maxC = std::max<long long>(A.maxC, (long long)L.clist.size()); A.sumC += L.clist.size();
+    A.maxL = std::max<long long>(A.maxL, (long long)L.lplist.size()); A.sumL += L.lplist.size();
+    A.maxU = std::max<long long>(A.maxU, (long long)L.undlist.size()); A.sumU += L.undlist.size();
     std::vector<OffsetNode>().swap(chk);
     if (!L.undlist.empty()) {
       const int ch[2] = {t.child0[my], t.child1[my]};
@@ -380,6 +386,7 @@ struct Lists {
   std::vector<int> cell, part, soft;
   std::vector<long long> cellMark, partMark, softMark;
   long long opened = 0, tested = 0;
+  long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 }  // namespace
@@ -459,6 +466,15 @@ void cb200h_tree_export(void *h, int *order, double *parts, double *moments, int
   }
 }
 
+/* per node: parent, first bucket beneath, buckets beneath (inputs of the device walk) */
+void cb200h_tree_export_links(void *h, int *parent, int *bucketFirst, int *bucketCount) {
+  Tree *t = (Tree *)h;
+  const size_t nn = t->numNodes();
+  if (parent) memcpy(parent, t->parent.data(), sizeof(int) * nn);
+  if (bucketFirst) memcpy(bucketFirst, t->bucketFirst.data(), sizeof(int) * nn);
+  if (bucketCount) memcpy(bucketCount, t->bucketCount.data(), sizeof(int) * nn);
+}
+
 /* Walk buckets [bucketLo, bucketHi) (a rank's SFC range; the whole tree is the
  * source).  bucketActive: one byte per bucket of the tree, or NULL = all active. */
 void *cb200h_walk(void *h, double theta, int nReplicas, double period, const unsigned char *bucketActive,
@@ -516,11 +532,19 @@ void *cb200h_walk(void *h, double theta, int nReplicas, double period, const uns
     if (s.nPart) memcpy(&L->part[3 * (size_t)L->partMark[b]], &A.part[s.part], sizeof(int) * 3 * s.nPart);
     if (s.nSoft) memcpy(&L->soft[2 * (size_t)L->softMark[b]], &A.soft[s.soft], sizeof(int) * 2 * s.nSoft);
   }
-  for (const Arena &A : w.arenas) { L->opened += A.opened; L->tested += A.tested; }
+  for (const Arena &A : w.arenas) {
+    L->opened += A.opened; L->tested += A.tested;
+    L->stats[0] += A.visited; L->stats[1] = std::max(L->stats[1], A.maxChk); L->stats[2] = std::max(L->stats[2], A.maxC);
+    L->stats[3] = std::max(L->stats[3], A.maxL); L->stats[4] = std::max(L->stats[4], A.maxU);
+    L->stats[5] += A.sumC; L->stats[6] += A.sumL; L->stats[7] += A.sumU;
+  }
   return L;
 }
 
 void cb200h_lists_free(void *h) { delete (Lists *)h; }
+
+/* visited local nodes, max checklist / clist / lplist / undlist length of one node, summed lengths */
+void cb200h_lists_stats(void *h, long long *out) { memcpy(out, ((Lists *)h)->stats, sizeof(long long) * 8); }
 
 /* out: cells, part buckets, softened cells, expanded particle entries, MAC tests, opened */
 void cb200h_lists_sizes(void *h, long long *out) {
@@ -566,6 +590,72 @@ void cb200h_expand_part_list(const int *part, const long long *partMark, int num
       for (int k = 0; k < num; ++k, ++o) { expanded[2 * o] = start + k; expanded[2 * o + 1] = off; }
     }
   }
+}
+
+/* Ewald set-up of one step (TreePiece::EwaldInit, Ewald.cpp:285-375), C twin of
+ * changa_b200/ewald_tables.py: complete root moments (MomcData order, 32 values) and the h-loop
+ * table rows {hx, hy, hz, hCfac, hSfac}.  With T2, T3, T4 the complete moment tensors and h an
+ * integer wave vector: hCfac = -(g0 M + g2 T2:hh/2 + g4 T4::hhhh/24), hSfac = -(g3 T3:.hhh/6),
+ * g_k = g0 (2 pi/L)^k with signs (+,+,-,-,+,+).  Returns the number of rows (<= cap written). */
+int cb200h_ewald_tables(const double *root, double L, double dEwhCut, double *momc, double *ewt, int cap) {
+  /* index of component (a,b[,c[,d]]) with a<=b<=c<=d in x<y<z among the stored reduced ones, or -1 */
+  static const char *names2[] = {"xx", "xy", "xz", "yy", "yz"};
+  static const char *names3[] = {"xxx", "xyy", "xxy", "yyy", "xxz", "yyz", "xyz"};
+  static const char *names4[] = {"xxxx", "xyyy", "xxxy", "yyyy", "xxxz", "yyyz", "xxyy", "xxyz", "xyyz"};
+  auto key = [](const int *idx, int n) { int c[3] = {0, 0, 0}; for (int i = 0; i < n; ++i) c[idx[i]]++; return c[0] * 25 + c[1] * 5 + c[2]; };
+  auto keyOf = [](const char *nm) { int c[3] = {0, 0, 0}; for (const char *p = nm; *p; ++p) c[*p - 'x']++; return c[0] * 25 + c[1] * 5 + c[2]; };
+  double comp[125];
+  bool have[125] = {false};
+  const double r = root[0];
+  for (int i = 0; i < 5; ++i) { comp[keyOf(names2[i])] = root[6 + i] * r * r; have[keyOf(names2[i])] = true; }
+  for (int i = 0; i < 7; ++i) { comp[keyOf(names3[i])] = root[11 + i] * r * r * r; have[keyOf(names3[i])] = true; }
+  for (int i = 0; i < 9; ++i) { comp[keyOf(names4[i])] = root[18 + i] * r * r * r * r; have[keyOf(names4[i])] = true; }
+  /* trace-free completion: T[..zz] = -(T[..xx] + T[..yy]), fewest z first */
+  for (int order = 2; order <= 4; ++order)
+    for (int nz = 2; nz <= order; ++nz)
+      for (int nx = 0; nx <= order - nz; ++nx) {
+        const int ny = order - nz - nx, k = nx * 25 + ny * 5 + nz;
+        if (have[k]) continue;
+        comp[k] = -(comp[(nx + 2) * 25 + ny * 5 + (nz - 2)] + comp[nx * 25 + (ny + 2) * 5 + (nz - 2)]);
+        have[k] = true;
+      }
+  static const char *momcNames[] = {"xx", "yy", "xy", "xz", "yz", "xxx", "xyy", "xxy", "yyy", "xxz", "yyz", "xyz",
+                                    "xxxx", "xyyy", "xxxy", "yyyy", "xxxz", "yyyz", "xxyy", "xxyz", "xyyz", "zz",
+                                    "xzz", "yzz", "zzz", "xxzz", "xyzz", "xzzz", "yyzz", "yzzz", "zzzz"};
+  const double M = root[2];
+  momc[0] = M;
+  for (int i = 0; i < 31; ++i) momc[1 + i] = comp[keyOf(momcNames[i])];
+  const int hreps = (int)std::ceil(dEwhCut);
+  const double alpha = 2.0 / L, k4 = M_PI * M_PI / (alpha * alpha * L * L), c = 2.0 * M_PI / L;
+  int n = 0;
+  for (int hx = -hreps; hx <= hreps; ++hx)
+    for (int hy = -hreps; hy <= hreps; ++hy)
+      for (int hz = -hreps; hz <= hreps; ++hz) {
+        const int h2 = hx * hx + hy * hy + hz * hz;
+        if (h2 == 0 || h2 > dEwhCut * dEwhCut) continue;
+        const double h[3] = {(double)hx, (double)hy, (double)hz};
+        double q2 = 0, q3 = 0, q4 = 0;
+        int idx[4];
+        for (idx[0] = 0; idx[0] < 3; ++idx[0])
+          for (idx[1] = 0; idx[1] < 3; ++idx[1]) {
+            q2 += comp[key(idx, 2)] * h[idx[0]] * h[idx[1]];
+            for (idx[2] = 0; idx[2] < 3; ++idx[2]) {
+              q3 += comp[key(idx, 3)] * h[idx[0]] * h[idx[1]] * h[idx[2]];
+              for (idx[3] = 0; idx[3] < 3; ++idx[3])
+                q4 += comp[key(idx, 4)] * h[idx[0]] * h[idx[1]] * h[idx[2]] * h[idx[3]];
+            }
+          }
+        const double g0 = std::exp(-k4 * h2) / (M_PI * h2 * L);
+        const double g2 = -c * c * g0, g3 = -c * c * c * g0, g4 = c * c * c * c * g0;
+        if (n < cap) {
+          double *row = ewt + 5 * (size_t)n;
+          row[0] = c * hx; row[1] = c * hy; row[2] = c * hz;
+          row[3] = -(g0 * M + g2 * q2 / 2.0 + g4 * q4 / 24.0);
+          row[4] = -(g3 * q3 / 6.0);
+        }
+        ++n;
+      }
+  return n;
 }
 
 int cb200h_num_threads(void) {

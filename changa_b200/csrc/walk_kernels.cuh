@@ -1,0 +1,367 @@
+/* walk_kernels.cuh -- interaction-list generation on the device.
+ *
+ * Emits, per bucket, exactly the ILCell / ILPart / softened-cell lists that
+ * ChaNGa's host walk produces (LocalTargetWalk::dft, TreeWalk.cpp:308-397;
+ * ListCompute::doWork, Compute.cpp:690-884; stateReady, Compute.cpp:1608-1863)
+ * -- same entries, same order, same offsetID bits -- so the 8-byte-per-entry
+ * lists never cross PCIe.  The specification is csrc/treewalk.cpp (host, bit-
+ * exact against the sequential oracle); the device version is the same walk
+ * organised for a GPU:
+ *
+ *   walk_level_kernel   level-synchronous over the LOCAL tree: one warp owns
+ *                       one local node, starts from its parent's undecided
+ *                       list (the 27 root replicas for the root), and drains a
+ *                       FIFO checklist 32 entries at a time.  Processing an
+ *                       entry depends only on (source node, local node), so a
+ *                       batch evaluated in parallel and appended in lane order
+ *                       (ballot + popc compaction) reproduces the sequential
+ *                       order exactly.  Outputs: clist, lplist, undlist of the
+ *                       node, copied into exactly-sized slices of a pool.
+ *   emit_count/fill     one warp per bucket: concatenates the per-node lists
+ *                       along the path root -> bucket, level by level, cells
+ *                       (minus the ones openSoftening sends to the softened
+ *                       list) and then particle buckets expanded per particle
+ *                       (GenericList<ILPart>::serialize, Compute.cpp:1174-1187).
+ *
+ * All geometry in double, like the host walk (gravity.h:251-260, 652-723).
+ */
+#ifndef CB200_WALK_KERNELS_CUH
+#define CB200_WALK_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include "device_layout.cuh"
+
+namespace cb200 {
+
+constexpr int kWalkCap = 2048;          /* entries per node list / checklist (host walk: max ~640) */
+constexpr int kWalkWarps = 4;           /* warps per CTA */
+constexpr int kWalkOffsetMask = 0x1ff << 22;
+constexpr int kWalkBucketMask = (1 << 22) - 1;
+
+struct WalkEntry { int node; int offsetID; };
+
+/* moments arrive as 27 doubles per node in CudaMultipoleMoments order */
+struct WalkTree {
+  int numNodes, numBuckets;
+  const int *child0, *child1, *first, *last, *bucketFirst, *bucketCount, *parent;
+  const double *boxlo, *boxhi, *mom;
+  const int *bucketNode;
+};
+
+struct WalkParams {
+  double theta, thetaMono, period;
+  int nReplicas, bucketLo, bucketHi;
+};
+
+/* per-node results: slices of the three pools */
+struct NodeLists {
+  int cOff, cLen, lOff, lLen, uOff, uLen;
+  int visited, pad;
+};
+
+struct WalkPools {
+  WalkEntry *clist, *lplist, *undlist;
+  unsigned long long capC, capL, capU;  /* entries per pool */
+  unsigned long long *used;             /* [3] bump counters */
+  int *error;                           /* != 0: a capacity was exceeded */
+};
+
+__device__ __forceinline__ bool walk_box_sphere(const double *lo, const double *hi, const double *c, double r) {
+  double dsq = 0.0, delta;
+  const double rsq = r * r;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if ((delta = lo[d] - c[d]) > 0) dsq += delta * delta;
+    else if ((delta = c[d] - hi[d]) > 0) dsq += delta * delta;
+    if (rsq < dsq) return false;
+  }
+  return dsq <= rsq;
+}
+__device__ __forceinline__ bool walk_box_inside_sphere(const double *lo, const double *hi, const double *c, double r) {
+  double s = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double a = fabs(lo[d] - c[d]), b = fabs(hi[d] - c[d]);
+    const double w = a > b ? a : b;
+    s += w * w;
+  }
+  return s <= r * r;
+}
+__device__ __forceinline__ void walk_shifted_cm(const double *m, int offsetID, double period, double *c) {
+  c[0] = m[3] + (((offsetID >> 22) & 7) - 3) * period;
+  c[1] = m[4] + (((offsetID >> 25) & 7) - 3) * period;
+  c[2] = m[5] + (((offsetID >> 28) & 7) - 3) * period;
+}
+/* gravity.h:251-260 */
+__device__ __forceinline__ bool walk_open_softening(const double *m, const double *c, const double *mm,
+                                                    const double *mylo, const double *myhi) {
+  const double rs = 2.0 * m[1], rm = 2.0 * mm[1];
+  const double dx = mm[3] - c[0], dy = mm[4] - c[1], dz = mm[5] - c[2];
+  if (dx * dx + dy * dy + dz * dz <= (rs + rm) * (rs + rm)) return true;
+  return walk_box_sphere(mylo, myhi, c, rs);
+}
+/* gravity.h:652-723: 1 open, -1 undecided, 0 accept */
+__device__ __forceinline__ int walk_open_criterion(const WalkTree &t, const WalkParams &p, int node, int offsetID,
+                                                   int my, bool myIsBucket) {
+  if (t.last[node] - t.first[node] + 1 <= 6) return 1;
+  const double *m = t.mom + (size_t)node * 27;
+  const double geom = 2.0 / sqrt(3.0);
+  double radius = geom * m[0] / p.theta;
+  if (radius < m[0]) radius = m[0];
+  double c[3];
+  walk_shifted_cm(m, offsetID, p.period, c);
+  const double *lo = t.boxlo + 3 * (size_t)my, *hi = t.boxhi + 3 * (size_t)my;
+  if (walk_box_sphere(lo, hi, c, radius)) {
+    if (myIsBucket) return 1;
+    return walk_box_inside_sphere(lo, hi, c, radius) ? 1 : -1;
+  }
+  if (!walk_open_softening(m, c, t.mom + (size_t)my * 27, lo, hi)) return 0;
+  radius = geom * m[0] / p.thetaMono;
+  return walk_box_sphere(lo, hi, c, radius) ? 1 : 0;
+}
+
+/* active buckets of a node under the [bucketLo, bucketHi) restriction */
+__device__ __forceinline__ bool walk_node_active(const WalkTree &t, const WalkParams &p, int node, int &firstActive) {
+  const int b0 = t.bucketFirst[node], b1 = b0 + t.bucketCount[node];
+  const int lo = b0 > p.bucketLo ? b0 : p.bucketLo, hi = b1 < p.bucketHi ? b1 : p.bucketHi;
+  firstActive = lo;
+  return lo < hi;
+}
+
+/* ordered append of the lanes whose flag is set */
+__device__ __forceinline__ void walk_append(WalkEntry *dst, int &count, bool flag, WalkEntry e, int lane, int cap,
+                                            int *error) {
+  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+  const int pos = count + __popc(ballot & ((1u << lane) - 1));
+  if (flag) {
+    if (pos < cap) dst[pos] = e;
+    else *error = 1;
+  }
+  count += __popc(ballot);
+}
+
+/* One level of the local tree: nodes [lo, lo+n).  scratch: per warp 4 x kWalkCap entries
+ * (checklist, clist, lplist, undlist). */
+__global__ void __launch_bounds__(kWalkWarps * 32)
+walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict__ lists, WalkPools pools,
+                  WalkEntry *__restrict__ scratch) {
+  const int lane = threadIdx.x & 31;
+  const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int totalWarps = (gridDim.x * blockDim.x) >> 5;
+  WalkEntry *chk = scratch + (size_t)warpGlobal * 4 * kWalkCap;
+  WalkEntry *cl = chk + kWalkCap, *lp = cl + kWalkCap, *und = lp + kWalkCap;
+
+  for (int w = warpGlobal; w < n; w += totalWarps) {
+    const int my = lo + w;
+    NodeLists out = {0, 0, 0, 0, 0, 0, 0, 0};
+    int target = 0;
+    bool go = walk_node_active(t, p, my, target);
+    const int par = t.parent[my];
+    if (go && par >= 0) go = lists[par].visited && lists[par].uLen > 0; /* descend only under a non-empty undecided list */
+    if (!go) {
+      if (lane == 0) lists[my] = out;
+      continue;
+    }
+    target &= kWalkBucketMask;
+    const bool myIsBucket = t.child0[my] < 0 && t.child1[my] < 0;
+    int head = 0, tail = 0, nc = 0, nl = 0, nu = 0;
+    /* initial checklist: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757) */
+    if (par < 0) {
+      const int side = 2 * p.nReplicas + 1, total = side * side * side;
+      for (int i = lane; i < total; i += 32) {
+        const int x = i / (side * side) - p.nReplicas, y = (i / side) % side - p.nReplicas, z = i % side - p.nReplicas;
+        if (i < kWalkCap) chk[i] = {0, (((x + 3) | ((y + 3) << 3) | ((z + 3) << 6)) << 22)};
+      }
+      tail = total;
+    } else {
+      const NodeLists pl = lists[par];
+      for (int i = lane; i < pl.uLen; i += 32) chk[i] = pools.undlist[pl.uOff + i];
+      tail = pl.uLen;
+    }
+    if (tail > kWalkCap) { if (lane == 0) *pools.error = 1; tail = kWalkCap; }
+    __syncwarp();
+
+    while (head < tail) {
+      const int i = head + lane;
+      const bool have = i < tail;
+      WalkEntry e = {0, 0};
+      int open = 0;
+      bool srcBucket = false;
+      int c0 = -1, c1 = -1;
+      if (have) {
+        e = chk[i & (kWalkCap - 1)];
+        e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
+        open = walk_open_criterion(t, p, e.node, e.offsetID, my, myIsBucket);
+        c0 = t.child0[e.node]; c1 = t.child1[e.node];
+        srcBucket = c0 < 0 && c1 < 0;
+      }
+      /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */
+      const bool toC = have && open == 0;
+      const bool toL = have && open != 0 && srcBucket;
+      const bool expand = have && open != 0 && !srcBucket && (open == 1 || myIsBucket);
+      const bool toU = have && open != 0 && !srcBucket && !expand;
+      walk_append(cl, nc, toC, e, lane, kWalkCap, pools.error);
+      walk_append(lp, nl, toL, e, lane, kWalkCap, pools.error);
+      walk_append(und, nu, toU, e, lane, kWalkCap, pools.error);
+      /* children in order 0, 1 behind everything already queued */
+      const int kids = expand ? (c0 >= 0) + (c1 >= 0) : 0;
+      int incl = kids;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int totalKids = __shfl_sync(0xffffffffu, incl, 31);
+      const int batch = min(32, tail - head);
+      if (tail - head - batch + totalKids > kWalkCap) { if (lane == 0) *pools.error = 1; break; }
+      int pos = tail + incl - kids;
+      if (expand) {
+        if (c0 >= 0) chk[(pos++) & (kWalkCap - 1)] = {c0, e.offsetID};
+        if (c1 >= 0) chk[pos & (kWalkCap - 1)] = {c1, e.offsetID};
+      }
+      head += batch;
+      tail += totalKids;
+      __syncwarp();
+    }
+
+    /* exact-size slices of the pools */
+    unsigned long long oc = 0, ol = 0, ou = 0;
+    if (lane == 0) {
+      oc = atomicAdd(pools.used + 0, (unsigned long long)nc);
+      ol = atomicAdd(pools.used + 1, (unsigned long long)nl);
+      ou = atomicAdd(pools.used + 2, (unsigned long long)nu);
+      if (oc + nc > pools.capC || ol + nl > pools.capL || ou + nu > pools.capU) { *pools.error = 2; nc = nl = nu = 0; }
+    }
+    oc = __shfl_sync(0xffffffffu, oc, 0); ol = __shfl_sync(0xffffffffu, ol, 0); ou = __shfl_sync(0xffffffffu, ou, 0);
+    nc = __shfl_sync(0xffffffffu, nc, 0); nl = __shfl_sync(0xffffffffu, nl, 0); nu = __shfl_sync(0xffffffffu, nu, 0);
+    for (int i = lane; i < nc; i += 32) pools.clist[oc + i] = cl[i];
+    for (int i = lane; i < nl; i += 32) pools.lplist[ol + i] = lp[i];
+    for (int i = lane; i < nu; i += 32) pools.undlist[ou + i] = und[i];
+    out.cOff = (int)oc; out.cLen = nc; out.lOff = (int)ol; out.lLen = nl; out.uOff = (int)ou; out.uLen = nu;
+    out.visited = 1;
+    if (lane == 0) lists[my] = out;
+    __syncwarp();
+  }
+}
+
+/* path root -> deepest visited ancestor-or-self of the bucket's node; returns its length */
+__device__ __forceinline__ int walk_path(const WalkTree &t, const NodeLists *lists, int bucketNode, int *path) {
+  int chain[64], n = 0;
+  for (int v = bucketNode; v >= 0 && n < 64; v = t.parent[v]) chain[n++] = v;
+  int len = 0;
+  for (int k = n - 1; k >= 0; --k) { /* root first; stop below the lowest node */
+    if (!lists[chain[k]].visited) break;
+    path[len++] = chain[k];
+  }
+  return len;
+}
+
+/* counts[b] = {cells, softened cells, expanded particle entries} of bucket b (0 outside the range) */
+__global__ void __launch_bounds__(kWalkWarps * 32)
+emit_count_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, WalkPools pools,
+                  int *__restrict__ nCell, int *__restrict__ nSoft, int *__restrict__ nPart,
+                  int *__restrict__ starts, int *__restrict__ sizes) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= t.numBuckets) return;
+  int cells = 0, soft = 0, part = 0;
+  if (b >= p.bucketLo && b < p.bucketHi) {
+    const int bn = t.bucketNode[b];
+    int path[64];
+    const int plen = walk_path(t, lists, bn, path);
+    const double *mm = t.mom + (size_t)bn * 27, *lo = t.boxlo + 3 * (size_t)bn, *hi = t.boxhi + 3 * (size_t)bn;
+    for (int k = 0; k < plen; ++k) {
+      const NodeLists nl = lists[path[k]];
+      for (int i = lane; i < nl.cLen; i += 32) {
+        const WalkEntry e = pools.clist[nl.cOff + i];
+        const double *m = t.mom + (size_t)e.node * 27;
+        double c[3];
+        walk_shifted_cm(m, e.offsetID, p.period, c);
+        if (walk_open_softening(m, c, mm, lo, hi)) ++soft; else ++cells;
+      }
+      for (int i = lane; i < nl.lLen; i += 32) {
+        const int src = pools.lplist[nl.lOff + i].node;
+        part += t.last[src] - t.first[src] + 1;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cells += __shfl_xor_sync(0xffffffffu, cells, o);
+      soft += __shfl_xor_sync(0xffffffffu, soft, o);
+      part += __shfl_xor_sync(0xffffffffu, part, o);
+    }
+  }
+  if (lane == 0) {
+    nCell[b] = cells; nSoft[b] = soft; nPart[b] = part;
+    const int bn = t.bucketNode[b];
+    starts[b] = t.first[bn]; sizes[b] = t.last[bn] - t.first[bn] + 1;
+  }
+}
+
+/* markers are exclusive prefix sums of the counts (numBuckets + 1 entries each) */
+__global__ void __launch_bounds__(kWalkWarps * 32)
+emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, WalkPools pools,
+                 const int *__restrict__ cellMark, const int *__restrict__ softMark, const int *__restrict__ partMark,
+                 ILCell *__restrict__ cellOut, ILCell *__restrict__ softOut, ILCell *__restrict__ partOut) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= t.numBuckets || b < p.bucketLo || b >= p.bucketHi) return;
+  const int bn = t.bucketNode[b];
+  int path[64];
+  const int plen = walk_path(t, lists, bn, path);
+  const double *mm = t.mom + (size_t)bn * 27, *lo = t.boxlo + 3 * (size_t)bn, *hi = t.boxhi + 3 * (size_t)bn;
+  int wc = cellMark[b], ws = softMark[b], wp = partMark[b];
+  for (int k = 0; k < plen; ++k) { /* cells, level 0 .. maxlevel (Compute.cpp:1653-1743) */
+    const NodeLists nl = lists[path[k]];
+    for (int i0 = 0; i0 < nl.cLen; i0 += 32) {
+      const int i = i0 + lane;
+      const bool have = i < nl.cLen;
+      WalkEntry e = {0, 0};
+      bool isSoft = false;
+      if (have) {
+        e = pools.clist[nl.cOff + i];
+        const double *m = t.mom + (size_t)e.node * 27;
+        double c[3];
+        walk_shifted_cm(m, e.offsetID, p.period, c);
+        isSoft = walk_open_softening(m, c, mm, lo, hi);
+      }
+      const unsigned bs = __ballot_sync(0xffffffffu, have && isSoft), bc = __ballot_sync(0xffffffffu, have && !isSoft);
+      const unsigned below = (1u << lane) - 1;
+      if (have) {
+        ILCell o;
+        o.index = e.node; o.offsetID = e.offsetID;
+        if (isSoft) softOut[ws + __popc(bs & below)] = o;
+        else cellOut[wc + __popc(bc & below)] = o;
+      }
+      ws += __popc(bs);
+      wc += __popc(bc);
+    }
+  }
+  for (int k = 0; k < plen; ++k) { /* particle buckets, expanded per particle (Compute.cpp:1823-1863, 1174-1187) */
+    const NodeLists nl = lists[path[k]];
+    for (int i = 0; i < nl.lLen; ++i) {
+      const WalkEntry e = pools.lplist[nl.lOff + i];
+      const int f = t.first[e.node], cnt = t.last[e.node] - f + 1;
+      for (int j = lane; j < cnt; j += 32) {
+        ILCell o;
+        o.index = f + j; o.offsetID = e.offsetID & kWalkOffsetMask; /* encodeOffset(0, x, y, z) */
+        partOut[wp + j] = o;
+      }
+      wp += cnt;
+    }
+  }
+}
+
+/* softened cells as ad-hoc source particles: every node as {cm, M | soft} */
+__global__ void nodes_as_particles_kernel(const double *__restrict__ mom, PackedPart *__restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *m = mom + (size_t)i * 27;
+  PackedPart q;
+  q.x = (real)m[3]; q.y = (real)m[4]; q.z = (real)m[5]; q.mass = (real)m[2];
+  q.soft = (real)m[1]; q.pad0 = q.pad1 = q.pad2 = 0;
+  out[i] = q;
+}
+
+}  // namespace cb200
+#endif

@@ -1,0 +1,120 @@
+"""The force step with the interaction lists built on the GPU: the host hands
+over the sorted particles and the tree topology; moments (cb200_build_moments), lists
+(cb200_walk_device) and forces are all computed on the device, so per step only
+~90 bytes per particle cross PCIe instead of the 8-byte-per-entry lists (~500 bytes per particle
+at theta = 0.7).  torch is used for device buffers and H2D/D2H copies only."""
+import ctypes as C
+
+import numpy as np
+
+
+class DeviceTreeStep:
+    def __init__(self, hc, tree, theta=0.7, n_replicas=0, period=1.0, ewald=None, bucket_range=None):
+        """tree: changa_b200.tree.Tree (host-built topology).  ewald: None | dict(dEwCut, dEwhCut)."""
+        import torch
+        self.torch, self.hc, self.t = torch, hc, tree
+        self.theta, self.nrep, self.period = float(theta), int(n_replicas), float(period)
+        self.ewald = ewald
+        self.range = bucket_range or (0, tree.num_buckets)
+        self.ext = torch.cuda.Stream()          # torch owns it: its allocators record events on it at teardown
+        self.stream = self.ext.cuda_stream
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        t = tree
+        # what the host must provide every step (pinned, as TreePiece / DataManager would hold it)
+        self.h = {
+            "pos": pin(t.parts[:, 2:5]), "mass": pin(t.parts[:, 0]), "soft": pin(t.parts[:, 1]),
+            "child0": pin(t.child0), "child1": pin(t.child1), "parent": pin(t.parent),
+            "first": pin(t.first), "last": pin(t.last), "bfirst": pin(t.bucket_first), "bcount": pin(t.bucket_count),
+            "bnode": pin(t.bucket_node), "geolo": pin(t.geolo), "geohi": pin(t.geohi),
+            "boxlo": pin(t.boxlo), "boxhi": pin(t.boxhi),
+            "parts32": pin(t.parts.astype(np.float32)),
+        }
+        self.level_start = np.ascontiguousarray(t.level_start, dtype=np.int32)
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.h.values())
+        self.out = torch.zeros((t.n, 5), dtype=torch.float32).pin_memory()
+        self.d2h_bytes = self.out.numel() * 4
+        self.lists_info = None
+
+    def run(self, keep_lists=False):
+        torch, hc, t, L = self.torch, self.hc, self.t, self.hc.L
+        s = self.stream
+        with torch.cuda.stream(self.ext):
+            d = {k: v.to("cuda", non_blocking=True) for k, v in self.h.items()}
+            nn, nb, n = t.num_nodes, t.num_buckets, t.n
+            mom32 = torch.empty((nn, 27), dtype=torch.float32, device="cuda")
+            mom64 = torch.empty((nn, 27), dtype=torch.float64, device="cuda")
+            L.cb200_build_moments(d["pos"].data_ptr(), d["mass"].data_ptr(), d["soft"].data_ptr(), n,
+                                  d["child0"].data_ptr(), d["child1"].data_ptr(), d["first"].data_ptr(),
+                                  d["last"].data_ptr(), d["geolo"].data_ptr(), d["geohi"].data_ptr(),
+                                  d["boxlo"].data_ptr(), d["boxhi"].data_ptr(), self.level_start.ctypes.data,
+                                  t.num_levels, nn, mom32.data_ptr(), mom64.data_ptr(), s)
+            lists = hc.T.Lists()
+            L.cb200_walk_device(nn, nb, t.num_levels, self.level_start.ctypes.data, d["child0"].data_ptr(),
+                                d["child1"].data_ptr(), d["parent"].data_ptr(), d["first"].data_ptr(),
+                                d["last"].data_ptr(), d["bfirst"].data_ptr(), d["bcount"].data_ptr(),
+                                d["bnode"].data_ptr(), d["boxlo"].data_ptr(), d["boxhi"].data_ptr(),
+                                mom64.data_ptr(), self.theta, self.nrep, self.period, self.range[0], self.range[1],
+                                C.byref(lists), s)
+            if lists.error:
+                raise RuntimeError(f"device walk: per-node capacity exceeded (error {lists.error})")
+            pk_parts = torch.empty(n * L.cb200_packed_particle_bytes(), dtype=torch.uint8, device="cuda")
+            pk_mom = torch.empty(nn * L.cb200_packed_moment_bytes(), dtype=torch.uint8, device="cuda")
+            L.cb200_pack_particles_device(d["parts32"].data_ptr(), pk_parts.data_ptr(), n, s)
+            L.cb200_pack_moments_device(mom32.data_ptr(), pk_mom.data_ptr(), nn, s)
+            vars_ = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+            P, V, M = pk_parts.data_ptr(), vars_.data_ptr(), pk_mom.data_ptr()
+            fper = self.period if (self.nrep or self.ewald is not None) else 0.0
+            if self.ewald is not None:
+                self._ewald(mom64, P, V, s)
+            mx = int(t.bucket_sizes.max())
+            L.cb200_cell_list_device_ex(P, V, M, lists.d_cell, lists.d_cellMarkers, lists.d_starts, lists.d_sizes,
+                                        nb, fper, mx, s)
+            L.cb200_part_list_device_ex(P, V, P, lists.d_part, lists.d_partMarkers, lists.d_starts, lists.d_sizes,
+                                        nb, fper, mx, s)
+            if lists.nSoft:
+                L.cb200_part_list_device_ex(P, V, lists.d_nodeParticles, lists.d_soft, lists.d_softMarkers,
+                                            lists.d_starts, lists.d_sizes, nb, fper, mx, s)
+            self.out.copy_(vars_, non_blocking=True)
+            self.lists_info = {"nCell": int(lists.nCell), "nSoft": int(lists.nSoft), "nPart": int(lists.nPart)}
+            if keep_lists:
+                self.kept = self._download(lists, nb)
+            L.cb200_lists_free(C.byref(lists), s)
+            hc.stream_synchronize(s)
+        return self.out.numpy()
+
+    def _ewald(self, mom64, P, V, s):
+        """root moments come back (27 doubles), the h-table is built on the host (EwaldInit, Ewald.cpp:285-375)"""
+        from .tree import ewald_tables_fast as ewald_tables
+        hc, t = self.hc, self.t
+        self.hc.stream_synchronize(s)
+        root = mom64[0].cpu().numpy()
+        momc, ewt = ewald_tables(root, self.period, self.ewald.get("dEwhCut", 2.8))
+        b0, b1 = self.range
+        first, last = int(t.bucket_starts[b0]), int(t.bucket_starts[b1 - 1] + t.bucket_sizes[b1 - 1] - 1)
+        if getattr(self, "_ew", None) is None:
+            self._ew = hc.EwaldHostMemorySetup(1, len(ewt), 0)
+        hc.fill_ewald(self._ew, root, momc, ewt, self.period, float(self.ewald.get("dEwCut", 2.6)), self.nrep,
+                      active=None, first=first, last=last)
+        # small-phase form: a contiguous particle range, no marker array
+        hc.L.cb200_EwaldHost(P, V, C.byref(self._ew), s, None, 0, 0)
+
+    def _download(self, lists, nb):
+        torch = self.torch
+        def arr(ptr, n, cols):
+            if n == 0:
+                return np.zeros((0, cols) if cols > 1 else (0,), dtype=np.int32)
+            buf = torch.empty(n * cols, dtype=torch.int32, device="cuda")
+            self.hc.L.cb200_copy_device(buf.data_ptr(), ptr, n * cols * 4, self.stream)
+            self.hc.stream_synchronize(self.stream)
+            a = buf.cpu().numpy()
+            return a.reshape(n, cols) if cols > 1 else a
+        return {"cell": arr(lists.d_cell, int(lists.nCell), 2), "soft": arr(lists.d_soft, int(lists.nSoft), 2),
+                "part": arr(lists.d_part, int(lists.nPart), 2), "cell_mark": arr(lists.d_cellMarkers, nb + 1, 1),
+                "soft_mark": arr(lists.d_softMarkers, nb + 1, 1), "part_mark": arr(lists.d_partMarkers, nb + 1, 1),
+                "starts": arr(lists.d_starts, nb, 1), "sizes": arr(lists.d_sizes, nb, 1)}
+
+    def free(self):
+        if getattr(self, "_ew", None) is not None:
+            self.hc.EwaldHostMemoryFree(self._ew, 0)
+            self._ew = None
+        self.h = self.out = None

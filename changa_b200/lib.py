@@ -71,8 +71,17 @@ def make_types(double=False):
         _fields_ = [("d_list", C.c_void_p), ("d_bucketMarkers", C.c_void_p),
                     ("d_bucketStarts", C.c_void_p), ("d_bucketSizes", C.c_void_p)]
 
+    class Lists(C.Structure):
+        _fields_ = [("d_cell", C.c_void_p), ("d_soft", C.c_void_p), ("d_part", C.c_void_p),
+                    ("d_cellMarkers", C.c_void_p), ("d_softMarkers", C.c_void_p), ("d_partMarkers", C.c_void_p),
+                    ("d_starts", C.c_void_p), ("d_sizes", C.c_void_p), ("d_nodeParticles", C.c_void_p),
+                    ("nCell", C.c_longlong), ("nSoft", C.c_longlong), ("nPart", C.c_longlong),
+                    ("numBuckets", C.c_int), ("error", C.c_int)]
+
     class T:
         pass
+
+    T.Lists = Lists
 
     T.real = real
     T.np_real = np.float64 if double else np.float32
@@ -101,9 +110,9 @@ C_ABI_SYMBOLS = [
     "cb200_cell_list_device", "cb200_part_list_device", "cb200_cell_list_device_ex",
     "cb200_part_list_device_ex", "cb200_ewald_device",
     "cb200_packed_moment_bytes", "cb200_packed_particle_bytes",
-    "cb200_pack_moments_device", "cb200_pack_particles_device", "cb200_zero_vars_device",
+    "cb200_pack_moments_device", "cb200_pack_particles_device", "cb200_zero_vars_device", "cb200_copy_device",
     "cb200_timing_enable", "cb200_timing_reset", "cb200_timing_read", "cb200_kernel_launches",
-    "cb200_build_moments", "cb200_partition_buckets",
+    "cb200_build_moments", "cb200_partition_buckets", "cb200_walk_device", "cb200_lists_free",
 ]
 
 CALLBACK_FN = C.CFUNCTYPE(None, C.c_void_p)
@@ -160,11 +169,15 @@ def load(double=False):
     L.cb200_pack_moments_device.argtypes = [vp, vp, i, vp]
     L.cb200_pack_particles_device.argtypes = [vp, vp, i, vp]
     L.cb200_zero_vars_device.argtypes = [vp, i, vp]
+    L.cb200_copy_device.argtypes = [vp, vp, sz, vp]
     L.cb200_timing_enable.argtypes = [i]
     L.cb200_timing_read.argtypes = [C.POINTER(C.c_double * 6)]
     L.cb200_kernel_launches.restype = C.c_longlong
     L.cb200_build_moments.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp]
     L.cb200_partition_buckets.argtypes = [vp, i, i, vp]
+    L.cb200_walk_device.argtypes = [i, i, i, vp] + [vp] * 11 + [C.c_double, i, C.c_double, i, i,
+                                                                 C.POINTER(T.Lists), vp]
+    L.cb200_lists_free.argtypes = [C.POINTER(T.Lists), vp]
     L.types = T
     L.path = path
     _LIBS[double] = L

@@ -27,13 +27,17 @@ def lib():
         L.cb200h_tree_free.argtypes = [vp]
         L.cb200h_tree_sizes.argtypes = [vp, vp]
         L.cb200h_tree_export.argtypes = [vp] * 16
+        L.cb200h_tree_export_links.argtypes = [vp, vp, vp, vp]
         L.cb200h_walk.restype = vp
         L.cb200h_walk.argtypes = [vp, d, i, d, vp, i, i]
         L.cb200h_lists_free.argtypes = [vp]
         L.cb200h_lists_sizes.argtypes = [vp, vp]
+        L.cb200h_lists_stats.argtypes = [vp, vp]
         L.cb200h_lists_export.argtypes = [vp] * 7
         L.cb200h_expand_part_list.argtypes = [vp, vp, i, vp, vp]
         L.cb200h_num_threads.restype = i
+        L.cb200h_ewald_tables.restype = i
+        L.cb200h_ewald_tables.argtypes = [vp, d, d, vp, vp, i]
         _LIB = L
     return _LIB
 
@@ -75,6 +79,10 @@ class Tree:
                              _p(self.geolo), _p(self.geohi), _p(self.boxlo), _p(self.boxhi),
                              _p(self.bucket_node), _p(self.bucket_starts), _p(self.bucket_sizes))
 
+        self.parent = np.zeros(nn, dtype=np.int32)
+        self.bucket_first, self.bucket_count = np.zeros(nn, dtype=np.int32), np.zeros(nn, dtype=np.int32)
+        L.cb200h_tree_export_links(self.h, _p(self.parent), _p(self.bucket_first), _p(self.bucket_count))
+
     def walk(self, theta=0.7, n_replicas=0, period=1.0, bucket_active=None, bucket_range=None):
         """Interaction lists of the active buckets in bucket_range (default: all).
         Returns a dict:
@@ -99,6 +107,10 @@ class Tree:
             "soft": np.zeros((int(sz[2]), 2), dtype=np.int32), "soft_mark": np.zeros(nb + 1, dtype=np.int64),
             "expanded_part_entries": int(sz[3]), "mac_tests": int(sz[4]), "mac_opened": int(sz[5]),
         }
+        st = np.zeros(8, dtype=np.int64)
+        L.cb200h_lists_stats(h, _p(st))
+        out["node_stats"] = dict(zip(("visited", "max_chk", "max_clist", "max_lplist", "max_undlist",
+                                      "sum_clist", "sum_lplist", "sum_undlist"), (int(x) for x in st)))
         L.cb200h_lists_export(h, _p(out["cell"]), _p(out["cell_mark"]), _p(out["part"]), _p(out["part_mark"]),
                               _p(out["soft"]), _p(out["soft_mark"]))
         L.cb200h_lists_free(h)
@@ -126,6 +138,15 @@ class Tree:
             self.free()
         except Exception:
             pass
+
+
+def ewald_tables_fast(root_cell, L, dEwhCut=2.8):
+    """C twin of changa_b200.ewald_tables.ewald_tables (microseconds instead of a millisecond)"""
+    root = np.ascontiguousarray(root_cell, dtype=np.float64)
+    momc = np.zeros(32)
+    ewt = np.zeros((512, 5))
+    n = lib().cb200h_ewald_tables(_p(root), float(L), float(dEwhCut), _p(momc), _p(ewt), 512)
+    return momc, np.ascontiguousarray(ewt[:n])
 
 
 def serialize(ilist, mark, starts, sizes):

@@ -164,6 +164,8 @@ size_t cb200_packed_moment_bytes(void);   /* bytes per cell row      */
 size_t cb200_packed_particle_bytes(void); /* bytes per particle row  */
 void cb200_pack_moments_device(const void *d_raw, void *d_packed, int n, void *stream);
 void cb200_pack_particles_device(const void *d_raw, void *d_packed, int n, void *stream);
+/* stream-ordered copy between any two of {device, pinned host} (cudaMemcpyDefault) */
+void cb200_copy_device(void *dst, const void *src, size_t bytes, void *stream);
 /* what ZeroVars does (HostCUDA.cu:2195-2205): clear n VariablePartData rows */
 void cb200_zero_vars_device(void *d_vars, int n, void *stream);
 
@@ -193,6 +195,35 @@ void cb200_build_moments(const double *d_pos_xyz, const double *d_mass,
                          const int *h_levelStart, int numLevels, int numNodes,
                          void *d_moments_out, double *d_moments_f64_out,
                          void *stream);
+
+/* --- new: interaction lists built on the device ----------------- */
+/* The double walk of TreeWalk.cpp:308-397 / Compute.cpp:690-884,1608-1863 on the
+ * GPU: per bucket exactly the entries, order and offsetID bits of ChaNGa's host
+ * walk, already in the layout the *_device_ex entry points consume, so the lists
+ * never cross PCIe.  Tree arrays are DEVICE pointers, nodes in breadth-first
+ * (nodeArrayIndex) order, child -1 = absent; h_levelStart is a HOST array of
+ * numLevels+1 node offsets; d_moments_f64 = 27 doubles per node as written by
+ * cb200_build_moments; boxes are the tight bounding boxes.  Only buckets
+ * [bucketLo, bucketHi) get lists (a rank's SFC share; the whole tree is the source).
+ * Every array of the result lives in the stream-ordered pool; release it with
+ * cb200_lists_free.  error != 0: a per-node capacity was exceeded (nothing usable). */
+typedef struct cb200_lists {
+  ILCell *d_cell, *d_soft, *d_part; /* cells | softened cells (index = node) | particles, expanded */
+  int *d_cellMarkers, *d_softMarkers, *d_partMarkers; /* numBuckets+1 each; empty lists outside the range */
+  int *d_starts, *d_sizes;          /* first target particle / particle count of every bucket */
+  void *d_nodeParticles;            /* every node as a packed source particle {cm, M | soft}: sources of d_soft */
+  long long nCell, nSoft, nPart;
+  int numBuckets;
+  int error;
+} cb200_lists;
+void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h_levelStart,
+                       const int *d_child0, const int *d_child1, const int *d_parent,
+                       const int *d_firstPart, const int *d_lastPart,
+                       const int *d_bucketFirst, const int *d_bucketCount, const int *d_bucketNode,
+                       const double *d_boxlo_xyz, const double *d_boxhi_xyz, const double *d_moments_f64,
+                       double theta, int nReplicas, double period, int bucketLo, int bucketHi,
+                       cb200_lists *out, void *stream);
+void cb200_lists_free(cb200_lists *lists, void *stream);
 
 /* --- new: per-GPU bucket partitioner --------------------------- */
 /* Cuts numBuckets SFC-ordered buckets into nRanks contiguous ranges of equal

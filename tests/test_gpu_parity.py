@@ -342,3 +342,66 @@ def test_against_the_reference_cuda_kernels(hc):
     assert np.median(diff) < 1e-5 and np.median(err_ref) < 1e-4          # the two GPU paths agree
     assert np.median(err_ours) <= 2 * np.median(err_ref) + 1e-7          # and ours is no further from the CPU answer
     np.testing.assert_allclose(got[:, 4], ref[:, 4], rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------
+# interaction lists built on the device
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n,nrep", [("cube300", 14 ** 3, 1), ("king", 6000, 0)])
+def test_device_walk_lists_are_bit_exact(hc, name, n, nrep):
+    """cb200_walk_device emits, per bucket, exactly the host walk's entries in its order
+    (which tests/test_tree_walk.py ties to the sequential reference-style walk)"""
+    from changa_b200.workloads import config_workload
+    from changa_b200.device_step import DeviceTreeStep
+    wl = config_workload(name, n=n, gen_kwargs=dict(rs=1.0) if name == "king" else None)
+    t = wl["tree"]
+    host = t.walk(theta=0.7, n_replicas=nrep, period=1.0)
+    ex, em = t.expand_part_list(host["part"], host["part_mark"])
+    step = DeviceTreeStep(hc, t, theta=0.7, n_replicas=nrep, period=1.0, ewald=None)
+    try:
+        step.run(keep_lists=True)
+        dev = step.kept
+    finally:
+        step.free()
+    assert np.array_equal(dev["cell_mark"], host["cell_mark"].astype(np.int32))
+    assert np.array_equal(dev["part_mark"], em.astype(np.int32))
+    assert np.array_equal(dev["soft_mark"], host["soft_mark"].astype(np.int32))
+    assert np.array_equal(dev["cell"], host["cell"])
+    assert np.array_equal(dev["part"], ex)
+    assert np.array_equal(dev["soft"], host["soft"])
+    assert np.array_equal(dev["starts"], t.bucket_starts) and np.array_equal(dev["sizes"], t.bucket_sizes)
+    if name == "king":
+        assert len(host["soft"]) > 0
+
+
+def test_device_tree_step_matches_oracle(hc):
+    """whole step from the sorted particles + topology: device moments, device lists, forces, Ewald"""
+    from changa_b200.workloads import config_workload
+    from changa_b200.device_step import DeviceTreeStep
+    wl = config_workload("cube300", n=16 ** 3)
+    step = DeviceTreeStep(hc, wl["tree"], theta=0.7, n_replicas=1, period=1.0, ewald={})
+    try:
+        got = step.run().copy()
+    finally:
+        step.free()
+    compare(got, oracle_forces_tree(wl), median_tol=5e-6, max_tol=3e-4, pot_tol=2e-5, floor_frac=0.1)
+
+
+def test_device_walk_bucket_range(hc):
+    """a rank's bucket range gets the same entries as in the full walk (replica code and index;
+    the low offsetID bits name the walk target, which depends on the range start)"""
+    from changa_b200.workloads import config_workload
+    from changa_b200.device_step import DeviceTreeStep
+    wl = config_workload("cube300", n=12 ** 3)
+    t = wl["tree"]
+    nb = t.num_buckets
+    b0, b1 = nb // 3, 2 * nb // 3
+    host = t.walk(theta=0.7, n_replicas=1, period=1.0, bucket_range=(b0, b1))
+    step = DeviceTreeStep(hc, t, theta=0.7, n_replicas=1, period=1.0, bucket_range=(b0, b1))
+    try:
+        step.run(keep_lists=True)
+        dev = step.kept
+    finally:
+        step.free()
+    assert np.array_equal(dev["cell_mark"], host["cell_mark"].astype(np.int32))
+    assert np.array_equal(dev["cell"], host["cell"])

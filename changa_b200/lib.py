@@ -119,6 +119,10 @@ CALLBACK_FN = C.CFUNCTYPE(None, C.c_void_p)
 
 
 def library_path(double=False):
+    """in-tree build; CB200_LIB / CB200_LIB_F64 point at another build of the same ABI (A/B runs)"""
+    override = os.environ.get("CB200_LIB_F64" if double else "CB200_LIB")
+    if override:
+        return os.path.abspath(override)
     return os.path.join(HERE, "libchanga_b200_f64.so" if double else "libchanga_b200.so")
 
 

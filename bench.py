@@ -65,6 +65,17 @@ def measured_peaks():
             out["hbm_source"] = "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
+    # DRAM bytes of one p-c launch on the default workload, from the committed `ncu --set full`
+    # capture of this same command (tools/ncu_summary.py); null when no capture is committed
+    out["pc_traffic"], out["pc_traffic_source"] = None, None
+    import glob
+    caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_cell_list_x2.json")))
+    if caps:
+        try:
+            out["pc_traffic"] = float(json.load(open(caps[-1]))["dram_bytes"])
+            out["pc_traffic_source"] = os.path.relpath(caps[-1], ROOT)
+        except Exception:
+            pass
     return out
 
 
@@ -395,7 +406,8 @@ def main():
                         "ewald_real_terms_per_particle": ew_real / max(ew_n, 1), "note": "rank 0, CUDA events around each launch"},
             "roofline": {"bound": "fp32_fma", "kernel": "cell_list_kernel (p-c hexadecapole)", "achieved": pc_tflops,
                          "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": pc_tflops / peaks["fp32_tflops"],
-                         "traffic": None, "flop_per_pair": FLOP_PC, "achieved_ref170": pc_tflops * FLOP_PC_REF / FLOP_PC,
+                         "traffic": peaks["pc_traffic"] if args.workload == "cube300" and not args.n and world == 1 else None,
+                         "traffic_source": peaks["pc_traffic_source"], "flop_per_pair": FLOP_PC, "achieved_ref170": pc_tflops * FLOP_PC_REF / FLOP_PC,
                          "peak_source": peaks["fp32_source"],
                          "hbm": {"algorithmic_bytes": pc_bytes, "achieved_gbs": pc_bytes / (pc_ms * 1e-3) / 1e9 if pc_ms else None,
                                  "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["hbm_source"]}},

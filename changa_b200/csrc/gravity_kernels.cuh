@@ -666,6 +666,22 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
           const float ccx = fmaf(float(replica_x(cur.offsetID)), fperiod, c[PK_CX]);
           const float ccy = fmaf(float(replica_y(cur.offsetID)), fperiod, c[PK_CY]);
           const float ccz = fmaf(float(replica_z(cur.offsetID)), fperiod, c[PK_CZ]);
+#ifdef CB200_V_DOUBLE
+          /* two pair evaluations per basic block: the dependent head of one (displacement ->
+           * rsqrt -> scaled displacement) overlaps the FMA-dense tail of the other */
+#pragma unroll
+          for (int j = 0; j < NP; j += 2) {
+            if (j + 1 < npairs) {
+              const TargetPair pa = lds_target_pair(tgtAddr + j * 32);
+              const TargetPair pb = lds_target_pair(tgtAddr + (j + 1) * 32);
+              pc_pair2(c, ccx, ccy, ccz, pa, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
+              pc_pair2(c, ccx, ccy, ccz, pb, ax[j + 1], ay[j + 1], az[j + 1], pot[j + 1], idt[2 * j + 2], idt[2 * j + 3]);
+            } else if (j < npairs) {
+              const TargetPair p = lds_target_pair(tgtAddr + j * 32);
+              pc_pair2(c, ccx, ccy, ccz, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
+            }
+          }
+#else
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
             if (j < npairs) {
@@ -673,6 +689,7 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
               pc_pair2(c, ccx, ccy, ccz, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
             }
           }
+#endif
         }
         __syncwarp();
         cur = nxt;

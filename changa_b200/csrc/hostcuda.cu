@@ -812,7 +812,12 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
   pools.used = (unsigned long long *)ctl;
   pools.error = (int *)(ctl + 64);
   NodeLists *lists = (NodeLists *)pool_alloc((size_t)numNodes * sizeof(NodeLists), s);
-  const int walkCtas = sms;
+  WalkNodeRec *rec = (WalkNodeRec *)pool_alloc((size_t)numNodes * sizeof(WalkNodeRec), s);
+  walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, rec);
+  cudaChk(cudaPeekAtLastError());
+  g_launches.fetch_add(1);
+  t.rec = rec;
+  const int walkCtas = sms * 8; /* 64 registers: 32 resident warps per SM; the walk is latency-bound */
   WalkEntry *scratch = (WalkEntry *)pool_alloc((size_t)walkCtas * kWalkWarps * 4 * kWalkCap * sizeof(WalkEntry), s);
   for (int lvl = 0; lvl < numLevels; ++lvl) {
     const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
@@ -864,6 +869,7 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
     g_launches.fetch_add(3);
   }
   pool_free(tmp, s); pool_free(counts, s); pool_free(scratch, s); pool_free(lists, s); pool_free(ctl, s);
+  pool_free(rec, s);
   pool_free(pools.clist, s); pool_free(pools.lplist, s); pool_free(pools.undlist, s);
 }
 

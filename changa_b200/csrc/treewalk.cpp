@@ -658,6 +658,13 @@ int cb200h_ewald_tables(const double *root, double L, double dEwhCut, double *mo
   return n;
 }
 
+/* testdata/ppartt.c:34-65: srand(seed); x, y, z = xmin + rand()/RAND_MAX (xmax - xmin) per
+ * particle, in that order (glibc rand(): the recipe is only reproducible with it) */
+void cb200h_uniform_box(int seed, long long n, double xmin, double xmax, double *pos) {
+  srand((unsigned)seed);
+  for (long long i = 0; i < 3 * n; ++i) pos[i] = xmin + (double)rand() / (double)RAND_MAX * (xmax - xmin);
+}
+
 int cb200h_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -40,13 +40,34 @@ constexpr int kWalkBucketMask = (1 << 22) - 1;
 
 struct WalkEntry { int node; int offsetID; };
 
+/* what one opening test reads of a SOURCE node, gathered into one 64-byte record (two
+ * sectors) instead of five scattered arrays: the walk is a stream of dependent gathers */
+struct __align__(16) WalkNodeRec {
+  double cx, cy, cz, radius, soft;
+  int child0, child1, first, last;
+  double pad;
+};
+static_assert(sizeof(WalkNodeRec) == 64, "WalkNodeRec");
+
 /* moments arrive as 27 doubles per node in CudaMultipoleMoments order */
 struct WalkTree {
   int numNodes, numBuckets;
   const int *child0, *child1, *first, *last, *bucketFirst, *bucketCount, *parent;
   const double *boxlo, *boxhi, *mom;
   const int *bucketNode;
+  const WalkNodeRec *rec;
 };
+
+__global__ void walk_pack_nodes_kernel(WalkTree t, WalkNodeRec *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.numNodes) return;
+  const double *m = t.mom + (size_t)i * 27;
+  WalkNodeRec r;
+  r.radius = m[0]; r.soft = m[1]; r.cx = m[3]; r.cy = m[4]; r.cz = m[5];
+  r.child0 = t.child0[i]; r.child1 = t.child1[i]; r.first = t.first[i]; r.last = t.last[i];
+  r.pad = 0.0;
+  out[i] = r;
+}
 
 struct WalkParams {
   double theta, thetaMono, period;
@@ -87,36 +108,35 @@ __device__ __forceinline__ bool walk_box_inside_sphere(const double *lo, const d
   }
   return s <= r * r;
 }
-__device__ __forceinline__ void walk_shifted_cm(const double *m, int offsetID, double period, double *c) {
-  c[0] = m[3] + (((offsetID >> 22) & 7) - 3) * period;
-  c[1] = m[4] + (((offsetID >> 25) & 7) - 3) * period;
-  c[2] = m[5] + (((offsetID >> 28) & 7) - 3) * period;
+__device__ __forceinline__ void walk_shifted_cm(const WalkNodeRec &m, int offsetID, double period, double *c) {
+  c[0] = m.cx + (((offsetID >> 22) & 7) - 3) * period;
+  c[1] = m.cy + (((offsetID >> 25) & 7) - 3) * period;
+  c[2] = m.cz + (((offsetID >> 28) & 7) - 3) * period;
 }
-/* gravity.h:251-260 */
-__device__ __forceinline__ bool walk_open_softening(const double *m, const double *c, const double *mm,
+/* gravity.h:251-260; mm: the local node */
+__device__ __forceinline__ bool walk_open_softening(const WalkNodeRec &m, const double *c, const WalkNodeRec &mm,
                                                     const double *mylo, const double *myhi) {
-  const double rs = 2.0 * m[1], rm = 2.0 * mm[1];
-  const double dx = mm[3] - c[0], dy = mm[4] - c[1], dz = mm[5] - c[2];
+  const double rs = 2.0 * m.soft, rm = 2.0 * mm.soft;
+  const double dx = mm.cx - c[0], dy = mm.cy - c[1], dz = mm.cz - c[2];
   if (dx * dx + dy * dy + dz * dz <= (rs + rm) * (rs + rm)) return true;
   return walk_box_sphere(mylo, myhi, c, rs);
 }
 /* gravity.h:652-723: 1 open, -1 undecided, 0 accept */
-__device__ __forceinline__ int walk_open_criterion(const WalkTree &t, const WalkParams &p, int node, int offsetID,
-                                                   int my, bool myIsBucket) {
-  if (t.last[node] - t.first[node] + 1 <= 6) return 1;
-  const double *m = t.mom + (size_t)node * 27;
+__device__ __forceinline__ int walk_open_criterion(const WalkParams &p, const WalkNodeRec &m, int offsetID,
+                                                   const WalkNodeRec &mine, const double *lo, const double *hi,
+                                                   bool myIsBucket) {
+  if (m.last - m.first + 1 <= 6) return 1;
   const double geom = 2.0 / sqrt(3.0);
-  double radius = geom * m[0] / p.theta;
-  if (radius < m[0]) radius = m[0];
+  double radius = geom * m.radius / p.theta;
+  if (radius < m.radius) radius = m.radius;
   double c[3];
   walk_shifted_cm(m, offsetID, p.period, c);
-  const double *lo = t.boxlo + 3 * (size_t)my, *hi = t.boxhi + 3 * (size_t)my;
   if (walk_box_sphere(lo, hi, c, radius)) {
     if (myIsBucket) return 1;
     return walk_box_inside_sphere(lo, hi, c, radius) ? 1 : -1;
   }
-  if (!walk_open_softening(m, c, t.mom + (size_t)my * 27, lo, hi)) return 0;
-  radius = geom * m[0] / p.thetaMono;
+  if (!walk_open_softening(m, c, mine, lo, hi)) return 0;
+  radius = geom * m.radius / p.thetaMono;
   return walk_box_sphere(lo, hi, c, radius) ? 1 : 0;
 }
 
@@ -163,7 +183,11 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       continue;
     }
     target &= kWalkBucketMask;
-    const bool myIsBucket = t.child0[my] < 0 && t.child1[my] < 0;
+    const WalkNodeRec mine = t.rec[my];
+    const bool myIsBucket = mine.child0 < 0 && mine.child1 < 0;
+    double mylo[3], myhi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { mylo[d] = t.boxlo[3 * (size_t)my + d]; myhi[d] = t.boxhi[3 * (size_t)my + d]; }
     int head = 0, tail = 0, nc = 0, nl = 0, nu = 0;
     /* initial checklist: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757) */
     if (par < 0) {
@@ -191,8 +215,9 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       if (have) {
         e = chk[i & (kWalkCap - 1)];
         e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
-        open = walk_open_criterion(t, p, e.node, e.offsetID, my, myIsBucket);
-        c0 = t.child0[e.node]; c1 = t.child1[e.node];
+        const WalkNodeRec src = t.rec[e.node];
+        open = walk_open_criterion(p, src, e.offsetID, mine, mylo, myhi, myIsBucket);
+        c0 = src.child0; c1 = src.child1;
         srcBucket = c0 < 0 && c1 < 0;
       }
       /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */
@@ -269,19 +294,20 @@ emit_count_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists,
     const int bn = t.bucketNode[b];
     int path[64];
     const int plen = walk_path(t, lists, bn, path);
-    const double *mm = t.mom + (size_t)bn * 27, *lo = t.boxlo + 3 * (size_t)bn, *hi = t.boxhi + 3 * (size_t)bn;
+    const WalkNodeRec mm = t.rec[bn];
+    const double *lo = t.boxlo + 3 * (size_t)bn, *hi = t.boxhi + 3 * (size_t)bn;
     for (int k = 0; k < plen; ++k) {
       const NodeLists nl = lists[path[k]];
       for (int i = lane; i < nl.cLen; i += 32) {
         const WalkEntry e = pools.clist[nl.cOff + i];
-        const double *m = t.mom + (size_t)e.node * 27;
+        const WalkNodeRec m = t.rec[e.node];
         double c[3];
         walk_shifted_cm(m, e.offsetID, p.period, c);
         if (walk_open_softening(m, c, mm, lo, hi)) ++soft; else ++cells;
       }
       for (int i = lane; i < nl.lLen; i += 32) {
-        const int src = pools.lplist[nl.lOff + i].node;
-        part += t.last[src] - t.first[src] + 1;
+        const WalkNodeRec src = t.rec[pools.lplist[nl.lOff + i].node];
+        part += src.last - src.first + 1;
       }
     }
 #pragma unroll
@@ -309,7 +335,8 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
   const int bn = t.bucketNode[b];
   int path[64];
   const int plen = walk_path(t, lists, bn, path);
-  const double *mm = t.mom + (size_t)bn * 27, *lo = t.boxlo + 3 * (size_t)bn, *hi = t.boxhi + 3 * (size_t)bn;
+  const WalkNodeRec mm = t.rec[bn];
+  const double *lo = t.boxlo + 3 * (size_t)bn, *hi = t.boxhi + 3 * (size_t)bn;
   int wc = cellMark[b], ws = softMark[b], wp = partMark[b];
   for (int k = 0; k < plen; ++k) { /* cells, level 0 .. maxlevel (Compute.cpp:1653-1743) */
     const NodeLists nl = lists[path[k]];
@@ -320,7 +347,7 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
       bool isSoft = false;
       if (have) {
         e = pools.clist[nl.cOff + i];
-        const double *m = t.mom + (size_t)e.node * 27;
+        const WalkNodeRec m = t.rec[e.node];
         double c[3];
         walk_shifted_cm(m, e.offsetID, p.period, c);
         isSoft = walk_open_softening(m, c, mm, lo, hi);

@@ -35,11 +35,23 @@ class DeviceTreeStep:
         self.d2h_bytes = self.out.numel() * 4
         self.lists_info = None
 
-    def run(self, keep_lists=False):
+    def run(self, keep_lists=False, phases=None):
+        """phases: optional dict filled with the milliseconds of each phase (CUDA events on the
+        step's stream: h2d, moments, walk, pack, ewald, forces, d2h)"""
         torch, hc, t, L = self.torch, self.hc, self.t, self.hc.L
         s = self.stream
+        marks = []
+
+        def mark(name):
+            if phases is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(self.ext)
+                marks.append((name, e))
+
         with torch.cuda.stream(self.ext):
+            mark("start")
             d = {k: v.to("cuda", non_blocking=True) for k, v in self.h.items()}
+            mark("h2d")
             nn, nb, n = t.num_nodes, t.num_buckets, t.n
             mom32 = torch.empty((nn, 27), dtype=torch.float32, device="cuda")
             mom64 = torch.empty((nn, 27), dtype=torch.float64, device="cuda")
@@ -48,6 +60,7 @@ class DeviceTreeStep:
                                   d["last"].data_ptr(), d["geolo"].data_ptr(), d["geohi"].data_ptr(),
                                   d["boxlo"].data_ptr(), d["boxhi"].data_ptr(), self.level_start.ctypes.data,
                                   t.num_levels, nn, mom32.data_ptr(), mom64.data_ptr(), s)
+            mark("moments")
             lists = hc.T.Lists()
             L.cb200_walk_device(nn, nb, t.num_levels, self.level_start.ctypes.data, d["child0"].data_ptr(),
                                 d["child1"].data_ptr(), d["parent"].data_ptr(), d["first"].data_ptr(),
@@ -55,6 +68,7 @@ class DeviceTreeStep:
                                 d["bnode"].data_ptr(), d["boxlo"].data_ptr(), d["boxhi"].data_ptr(),
                                 mom64.data_ptr(), self.theta, self.nrep, self.period, self.range[0], self.range[1],
                                 C.byref(lists), s)
+            mark("walk")
             if lists.error:
                 raise RuntimeError(f"device walk: per-node capacity exceeded (error {lists.error})")
             pk_parts = torch.empty(n * L.cb200_packed_particle_bytes(), dtype=torch.uint8, device="cuda")
@@ -64,8 +78,10 @@ class DeviceTreeStep:
             vars_ = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
             P, V, M = pk_parts.data_ptr(), vars_.data_ptr(), pk_mom.data_ptr()
             fper = self.period if (self.nrep or self.ewald is not None) else 0.0
+            mark("pack")
             if self.ewald is not None:
                 self._ewald(mom64, P, V, s)
+            mark("ewald")
             mx = int(t.bucket_sizes.max())
             L.cb200_cell_list_device_ex(P, V, M, lists.d_cell, lists.d_cellMarkers, lists.d_starts, lists.d_sizes,
                                         nb, fper, mx, s)
@@ -74,12 +90,17 @@ class DeviceTreeStep:
             if lists.nSoft:
                 L.cb200_part_list_device_ex(P, V, lists.d_nodeParticles, lists.d_soft, lists.d_softMarkers,
                                             lists.d_starts, lists.d_sizes, nb, fper, mx, s)
+            mark("forces")
             self.out.copy_(vars_, non_blocking=True)
+            mark("d2h")
             self.lists_info = {"nCell": int(lists.nCell), "nSoft": int(lists.nSoft), "nPart": int(lists.nPart)}
             if keep_lists:
                 self.kept = self._download(lists, nb)
             L.cb200_lists_free(C.byref(lists), s)
             hc.stream_synchronize(s)
+        if phases is not None:
+            for (_, a), (name, b) in zip(marks, marks[1:]):
+                phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
         return self.out.numpy()
 
     def _ewald(self, mom64, P, V, s):

@@ -110,13 +110,11 @@ def uniform_box(n, seed=1, xmin=-0.5, xmax=0.5):
     srand(seed); x,y,z = xmin + rand()/RAND_MAX*(xmax-xmin) per particle in that order;
     m = 1/N; eps = N^(-1/3) (xmax-xmin)/20.  Returns (pos, mass, soft)."""
     import ctypes
-    libc = ctypes.CDLL("libc.so.6")
-    libc.srand(int(seed))
-    libc.rand.restype = ctypes.c_int
-    rand_max = 2147483647.0
-    rand = libc.rand
-    r = np.fromiter((rand() for _ in range(3 * n)), dtype=np.float64, count=3 * n)
-    pos = xmin + r.reshape(n, 3) / rand_max * (xmax - xmin)
+    from .tree import lib
+    pos = np.zeros((n, 3))
+    f = lib().cb200h_uniform_box
+    f.argtypes = [ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    f(int(seed), int(n), float(xmin), float(xmax), pos.ctypes.data)
     mass = np.full(n, 1.0 / n)
     soft = np.full(n, n ** (-1.0 / 3.0) * (xmax - xmin) / 20.0)
     return pos, mass, soft

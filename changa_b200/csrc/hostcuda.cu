@@ -813,7 +813,8 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
   pools.error = (int *)(ctl + 64);
   NodeLists *lists = (NodeLists *)pool_alloc((size_t)numNodes * sizeof(NodeLists), s);
   WalkNodeRec *rec = (WalkNodeRec *)pool_alloc((size_t)numNodes * sizeof(WalkNodeRec), s);
-  walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, rec);
+  t.softMaxBits = (const unsigned long long *)(ctl + 128); /* ctl is zeroed above */
+  walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, rec, (unsigned long long *)(ctl + 128));
   cudaChk(cudaPeekAtLastError());
   g_launches.fetch_add(1);
   t.rec = rec;

@@ -56,10 +56,23 @@ struct WalkTree {
   const double *boxlo, *boxhi, *mom;
   const int *bucketNode;
   const WalkNodeRec *rec;
+  const unsigned long long *softMaxBits; /* max over nodes of `soft`, as the bits of a non-negative double */
 };
 
-__global__ void walk_pack_nodes_kernel(WalkTree t, WalkNodeRec *__restrict__ out) {
+constexpr int kWalkMaybeSoft = 1 << 31; /* clist entries only: some bucket below the owner MAY see this cell softened */
+
+__global__ void walk_pack_nodes_kernel(WalkTree t, WalkNodeRec *__restrict__ out, unsigned long long *softMaxBits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double soft = 0.0;
+  if (i < t.numNodes) soft = fmax(t.mom[(size_t)i * 27 + 1], 0.0);
+  /* non-negative doubles order like their bit patterns */
+  unsigned long long b = (unsigned long long)__double_as_longlong(soft);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long v = __shfl_xor_sync(0xffffffffu, b, o);
+    b = v > b ? v : b;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(softMaxBits, b);
   if (i >= t.numNodes) return;
   const double *m = t.mom + (size_t)i * 27;
   WalkNodeRec r;
@@ -188,6 +201,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     double mylo[3], myhi[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) { mylo[d] = t.boxlo[3 * (size_t)my + d]; myhi[d] = t.boxhi[3 * (size_t)my + d]; }
+    const double rmMax = 2.0 * __longlong_as_double((long long)*t.softMaxBits);
     int head = 0, tail = 0, nc = 0, nl = 0, nu = 0;
     /* initial checklist: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757) */
     if (par < 0) {
@@ -219,6 +233,15 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
         open = walk_open_criterion(p, src, e.offsetID, mine, mylo, myhi, myIsBucket);
         c0 = src.child0; c1 = src.child1;
         srcBucket = c0 < 0 && c1 < 0;
+        if (open == 0) {
+          /* openSoftening (gravity.h:251-260) is decided per BUCKET at emit time.  Every bucket
+           * below this node has its box and centre of mass inside this node's box, so when the
+           * cell's softening sphere, grown by the largest bucket softening, misses the box no
+           * bucket can see the cell softened: emit then skips the test and the 64-byte gather */
+          double c[3];
+          walk_shifted_cm(src, e.offsetID, p.period, c);
+          if (walk_box_sphere(mylo, myhi, c, 2.0 * src.soft + rmMax)) e.offsetID |= kWalkMaybeSoft;
+        }
       }
       /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */
       const bool toC = have && open == 0;
@@ -300,10 +323,14 @@ emit_count_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists,
       const NodeLists nl = lists[path[k]];
       for (int i = lane; i < nl.cLen; i += 32) {
         const WalkEntry e = pools.clist[nl.cOff + i];
-        const WalkNodeRec m = t.rec[e.node];
-        double c[3];
-        walk_shifted_cm(m, e.offsetID, p.period, c);
-        if (walk_open_softening(m, c, mm, lo, hi)) ++soft; else ++cells;
+        bool isSoft = false;
+        if (e.offsetID & kWalkMaybeSoft) {
+          const WalkNodeRec m = t.rec[e.node];
+          double c[3];
+          walk_shifted_cm(m, e.offsetID, p.period, c);
+          isSoft = walk_open_softening(m, c, mm, lo, hi);
+        }
+        if (isSoft) ++soft; else ++cells;
       }
       for (int i = lane; i < nl.lLen; i += 32) {
         const WalkNodeRec src = t.rec[pools.lplist[nl.lOff + i].node];
@@ -347,10 +374,13 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
       bool isSoft = false;
       if (have) {
         e = pools.clist[nl.cOff + i];
-        const WalkNodeRec m = t.rec[e.node];
-        double c[3];
-        walk_shifted_cm(m, e.offsetID, p.period, c);
-        isSoft = walk_open_softening(m, c, mm, lo, hi);
+        if (e.offsetID & kWalkMaybeSoft) {
+          const WalkNodeRec m = t.rec[e.node];
+          double c[3];
+          walk_shifted_cm(m, e.offsetID, p.period, c);
+          isSoft = walk_open_softening(m, c, mm, lo, hi);
+          e.offsetID &= ~kWalkMaybeSoft;
+        }
       }
       const unsigned bs = __ballot_sync(0xffffffffu, have && isSoft), bc = __ballot_sync(0xffffffffu, have && !isSoft);
       const unsigned below = (1u << lane) - 1;

@@ -267,6 +267,42 @@ class ResidentStep:
         return sum(a.elapsed_time(b) for a, b in evs)  # ms over exactly `steps` steps
 
 
+def large_box_step(hc, n, steps=3):
+    """The same force step on a box that fills the GPU (uniform, SURVEY 8d recipe C3 at a size one
+    default run can afford), with the interaction lists built ON the device: upload particles +
+    tree topology, device moments, device double walk, p-c / p-p / Ewald, download.  Reported next
+    to the headline numbers: kernel rates without the launch-ramp and tail of the 110k-particle box."""
+    from changa_b200.device_step import DeviceTreeStep
+    from changa_b200.tree import Tree
+    from changa_b200.workloads import uniform_box
+    pos, mass, soft = uniform_box(n, seed=1)
+    tree = Tree(pos, mass, soft, max_bucket=12)
+    st = DeviceTreeStep(hc, tree, theta=0.7, n_replicas=1, period=1.0, ewald={"dEwCut": 2.6, "dEwhCut": 2.8})
+    st.run(keep_lists=True)  # warm-up; the markers give the pair counts
+    k, bs = st.kept, tree.bucket_sizes.astype(np.int64)
+    pc = int((np.diff(k["cell_mark"].astype(np.int64)) * bs).sum())
+    pp = int((np.diff(k["part_mark"].astype(np.int64)) * bs).sum() + (np.diff(k["soft_mark"].astype(np.int64)) * bs).sum())
+    st.kept = None
+    hc.timing(True)
+    phases = {}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st.run(phases=phases)
+    wall = (time.perf_counter() - t0) / steps
+    taps = hc.timing_read()
+    hc.timing(False)
+    st.free()
+    tree.free()
+    pc_ms = taps["cell_ms"] / max(taps["cell_launches"], 1)
+    return {"workload": f"uniform(N={n},theta=0.7,nReplicas=1,bucket=12), lists built on the device",
+            "ms_per_step": wall * 1e3, "steps": steps, "interactions_per_s": (pc + pp) / wall,
+            "pc_pairs": pc, "pp_pairs": pp, "phases_ms": {a: round(b / steps, 3) for a, b in phases.items()},
+            "pc_ms": pc_ms, "pc_tflops": pc * FLOP_PC / (pc_ms * 1e-3) / 1e12,
+            "pp_ms": taps["part_ms"] / steps, "ewald_ms": taps["ewald_ms"] / max(taps["ewald_launches"], 1),
+            "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": st.d2h_bytes,
+            "timing": "wall clock around DeviceTreeStep.run(); phases and kernels by CUDA events on its stream"}
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port (kind "port": gravity.h / Ewald.cpp need Charm++ and do not
     compile here) with all host threads; rank 0 only."""
@@ -306,6 +342,8 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="particles per GPU (default: the config's own size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 50)")
+    ap.add_argument("--large-n", type=int, default=1 << 22,
+                    help="particles of the extra device-built-lists box at N=1 (0: skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -364,6 +402,12 @@ def main():
     h2d, d2h = fs.h2d_bytes, fs.d2h_bytes
     fs.free()
 
+    large = None
+    if world == 1 and args.large_n > 0:
+        try:
+            large = large_box_step(hc, args.large_n)
+        except Exception as e:  # extra information: never takes the headline line down
+            large = {"error": repr(e)}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- aggregate over ranks ------------------------------------------------------------
@@ -417,6 +461,10 @@ def main():
             "gpu_launches": int(g_launch),
             "clocks": clocks,
         }
+        if large is not None:
+            if "pc_tflops" in large:
+                large["pc_frac_of_fp32_peak"] = large["pc_tflops"] / peaks["fp32_tflops"]
+            line["large_box"] = large
         if world == 1 and not args.no_cpu_baseline:
             try:
                 dt, threads = cpu_force_step(wl, repeats=2)

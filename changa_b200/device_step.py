@@ -49,12 +49,20 @@ class DeviceTreeStep:
                 marks.append((name, e))
 
         with torch.cuda.stream(self.ext):
-            mark("start")
-            d = {k: v.to("cuda", non_blocking=True) for k, v in self.h.items()}
-            mark("h2d")
             nn, nb, n = t.num_nodes, t.num_buckets, t.n
-            mom32 = torch.empty((nn, 27), dtype=torch.float32, device="cuda")
-            mom64 = torch.empty((nn, 27), dtype=torch.float64, device="cuda")
+            if getattr(self, "dev", None) is None:  # device buffers live as long as the step object
+                self.dev = {k: torch.empty_like(v, device="cuda") for k, v in self.h.items()}
+                self.dev["mom32"] = torch.empty((nn, 27), dtype=torch.float32, device="cuda")
+                self.dev["mom64"] = torch.empty((nn, 27), dtype=torch.float64, device="cuda")
+                self.dev["pk_parts"] = torch.empty(n * L.cb200_packed_particle_bytes(), dtype=torch.uint8, device="cuda")
+                self.dev["pk_mom"] = torch.empty(nn * L.cb200_packed_moment_bytes(), dtype=torch.uint8, device="cuda")
+                self.dev["vars"] = torch.empty((n, 5), dtype=torch.float32, device="cuda")
+            d = self.dev
+            mark("start")
+            for k, v in self.h.items():
+                d[k].copy_(v, non_blocking=True)
+            mark("h2d")
+            mom32, mom64 = d["mom32"], d["mom64"]
             L.cb200_build_moments(d["pos"].data_ptr(), d["mass"].data_ptr(), d["soft"].data_ptr(), n,
                                   d["child0"].data_ptr(), d["child1"].data_ptr(), d["first"].data_ptr(),
                                   d["last"].data_ptr(), d["geolo"].data_ptr(), d["geohi"].data_ptr(),
@@ -71,11 +79,10 @@ class DeviceTreeStep:
             mark("walk")
             if lists.error:
                 raise RuntimeError(f"device walk: per-node capacity exceeded (error {lists.error})")
-            pk_parts = torch.empty(n * L.cb200_packed_particle_bytes(), dtype=torch.uint8, device="cuda")
-            pk_mom = torch.empty(nn * L.cb200_packed_moment_bytes(), dtype=torch.uint8, device="cuda")
+            pk_parts, pk_mom, vars_ = d["pk_parts"], d["pk_mom"], d["vars"]
             L.cb200_pack_particles_device(d["parts32"].data_ptr(), pk_parts.data_ptr(), n, s)
             L.cb200_pack_moments_device(mom32.data_ptr(), pk_mom.data_ptr(), nn, s)
-            vars_ = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+            L.cb200_zero_vars_device(vars_.data_ptr(), n, s)
             P, V, M = pk_parts.data_ptr(), vars_.data_ptr(), pk_mom.data_ptr()
             fper = self.period if (self.nrep or self.ewald is not None) else 0.0
             mark("pack")
@@ -138,4 +145,4 @@ class DeviceTreeStep:
         if getattr(self, "_ew", None) is not None:
             self.hc.EwaldHostMemoryFree(self._ew, 0)
             self._ew = None
-        self.h = self.out = None
+        self.h = self.out = self.dev = None

@@ -269,38 +269,38 @@ class ResidentStep:
 
 def large_box_step(hc, n, steps=3):
     """The same force step on a box that fills the GPU (uniform, SURVEY 8d recipe C3 at a size one
-    default run can afford), with the interaction lists built ON the device: upload particles +
-    tree topology, device moments, device double walk, p-c / p-p / Ewald, download.  Reported next
-    to the headline numbers: kernel rates without the launch-ramp and tail of the 110k-particle box."""
-    from changa_b200.device_step import DeviceTreeStep
-    from changa_b200.tree import Tree
+    default run can afford), from UNSORTED host particles: upload 40 B/particle, then keys, sort,
+    tree, moments, double walk, p-c / p-p / Ewald all on the device, accelerations back in the
+    caller's order (changa_b200.device_step.RawParticleStep).  Reported next to the headline
+    numbers: kernel rates without the launch ramp and tail of the 110k-particle box."""
+    from changa_b200.device_step import RawParticleStep
     from changa_b200.workloads import uniform_box
     pos, mass, soft = uniform_box(n, seed=1)
-    tree = Tree(pos, mass, soft, max_bucket=12)
-    st = DeviceTreeStep(hc, tree, theta=0.7, n_replicas=1, period=1.0, ewald={"dEwCut": 2.6, "dEwhCut": 2.8})
-    st.run(keep_lists=True)  # warm-up; the markers give the pair counts
-    k, bs = st.kept, tree.bucket_sizes.astype(np.int64)
-    pc = int((np.diff(k["cell_mark"].astype(np.int64)) * bs).sum())
-    pp = int((np.diff(k["part_mark"].astype(np.int64)) * bs).sum() + (np.diff(k["soft_mark"].astype(np.int64)) * bs).sum())
-    st.kept = None
+    st = RawParticleStep(hc, pos, mass, soft, theta=0.7, n_replicas=1, period=1.0,
+                         ewald={"dEwCut": 2.6, "dEwhCut": 2.8}, max_bucket=12)
+    st.run(count_pairs=True)  # warm-up (pool growth); the markers give the pair counts
+    info = dict(st.info)
+    pc, pp = info["pc_pairs"], info["pp_pairs"]
     hc.timing(True)
     phases = {}
     t0 = time.perf_counter()
     for _ in range(steps):
-        st.run(phases=phases)
+        out = st.run(phases=phases)
     wall = (time.perf_counter() - t0) / steps
+    finite = bool(np.isfinite(out).all())
     taps = hc.timing_read()
     hc.timing(False)
+    h2d, d2h = st.h2d_bytes, st.d2h_bytes
     st.free()
-    tree.free()
     pc_ms = taps["cell_ms"] / max(taps["cell_launches"], 1)
-    return {"workload": f"uniform(N={n},theta=0.7,nReplicas=1,bucket=12), lists built on the device",
+    return {"workload": f"uniform(N={n},theta=0.7,nReplicas=1,bucket=12), tree and lists built on the device",
             "ms_per_step": wall * 1e3, "steps": steps, "interactions_per_s": (pc + pp) / wall,
-            "pc_pairs": pc, "pp_pairs": pp, "phases_ms": {a: round(b / steps, 3) for a, b in phases.items()},
+            "nodes": info["nodes"], "buckets": info["buckets"], "pc_pairs": pc, "pp_pairs": pp,
+            "phases_ms": {a: round(b / steps, 3) for a, b in phases.items()},
             "pc_ms": pc_ms, "pc_tflops": pc * FLOP_PC / (pc_ms * 1e-3) / 1e12,
             "pp_ms": taps["part_ms"] / steps, "ewald_ms": taps["ewald_ms"] / max(taps["ewald_launches"], 1),
-            "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": st.d2h_bytes,
-            "timing": "wall clock around DeviceTreeStep.run(); phases and kernels by CUDA events on its stream"}
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "finite": finite,
+            "timing": "wall clock around RawParticleStep.run(); phases and kernels by CUDA events on its stream"}
 
 
 def run_reference(args, rank, world):

@@ -33,7 +33,9 @@
 #include "gravity_kernels.cuh"
 #include "moments_build.cuh"
 #include "walk_kernels.cuh"
+#include "tree_kernels.cuh"
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #ifdef CB200_WITH_CHARM_HAPI
 #include "hapi.h"
@@ -773,6 +775,133 @@ void cb200_build_moments(const double *d_pos_xyz, const double *d_mass, const do
     g_launches.fetch_add(1);
   }
   pool_free(work, s);
+}
+
+/* ---- tree topology on the device ---- */
+void cb200_build_tree(const double *d_pos_xyz, const double *d_mass, const double *d_soft, int n, int maxBucket,
+                      const double *rootlo, const double *roothi, cb200_tree *out, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  memset(out, 0, sizeof *out);
+  out->numParticles = n;
+  if (n <= 0) return;
+  TreeBox box;
+  for (int d = 0; d < 3; ++d) { box.lo[d] = rootlo[d]; box.inv[d] = 1.0 / (roothi[d] - rootlo[d]); }
+  const int tb = 256;
+  /* keys, stable sort by key (ties keep the caller's order), sorted particle arrays */
+  unsigned long long *keysIn = (unsigned long long *)pool_alloc((size_t)n * 8, s);
+  unsigned long long *keys = (unsigned long long *)pool_alloc((size_t)n * 8, s);
+  int *idxIn = (int *)pool_alloc((size_t)n * 4, s);
+  out->d_order = (int *)pool_alloc((size_t)n * 4, s);
+  tree_keys_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(d_pos_xyz, n, box, keysIn, idxIn);
+  cudaChk(cudaPeekAtLastError());
+  size_t tmpBytes = 0;
+  cudaChk(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keysIn, keys, idxIn, out->d_order, n, 0, kTreeKeyBits, s));
+  void *tmp = pool_alloc(tmpBytes, s);
+  cudaChk(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keys, idxIn, out->d_order, n, 0, kTreeKeyBits, s));
+  pool_free(tmp, s); pool_free(keysIn, s); pool_free(idxIn, s);
+  out->d_pos = (double *)pool_alloc((size_t)n * 24, s);
+  out->d_mass = (double *)pool_alloc((size_t)n * 8, s);
+  out->d_soft = (double *)pool_alloc((size_t)n * 8, s);
+  out->d_packedParts = pool_alloc((size_t)n * sizeof(PackedPart), s);
+  tree_gather_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(d_pos_xyz, d_mass, d_soft, out->d_order, n, out->d_pos,
+                                                      out->d_mass, out->d_soft, (PackedPart *)out->d_packedParts);
+  cudaChk(cudaPeekAtLastError());
+  g_launches.fetch_add(5);
+
+  /* nodes, level by level; capacity: a node holds at least one particle, chains of single
+   * children are the only way past ~n/3 nodes */
+  const int cap = n + n / 2 + 4096;
+  TreeArrays t;
+  t.child0 = out->d_child0 = (int *)pool_alloc((size_t)cap * 4, s);
+  t.child1 = out->d_child1 = (int *)pool_alloc((size_t)cap * 4, s);
+  t.parent = out->d_parent = (int *)pool_alloc((size_t)cap * 4, s);
+  t.first = out->d_first = (int *)pool_alloc((size_t)cap * 4, s);
+  t.last = out->d_last = (int *)pool_alloc((size_t)cap * 4, s);
+  t.geolo = out->d_geolo = (double *)pool_alloc((size_t)cap * 24, s);
+  t.geohi = out->d_geohi = (double *)pool_alloc((size_t)cap * 24, s);
+  int *err = (int *)pool_alloc(4, s);
+  cudaChk(cudaMemsetAsync(err, 0, 4, s));
+  tree_root_kernel<<<1, 1, 0, s>>>(t, n, box, roothi[0], roothi[1], roothi[2]);
+  int *split = (int *)pool_alloc((size_t)(n + 1) * 4, s); /* a level has at most n nodes */
+  int *nkids = (int *)pool_alloc((size_t)(n + 1) * 4, s);
+  int *slot = (int *)pool_alloc((size_t)(n + 1) * 4, s);
+  size_t scanBytes = 0;
+  cudaChk(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, nkids, slot, n + 1, s));
+  void *scanTmp = pool_alloc(scanBytes, s);
+  int lo = 0, hi = 1, level = 0;
+  out->levelStart[0] = 0;
+  while (lo < hi && level < kTreeMaxLevels) {
+    const int cnt = hi - lo;
+    out->levelStart[level + 1] = hi;
+    tree_split_kernel<<<(cnt + 1 + tb - 1) / tb, tb, 0, s>>>(t, keys, lo, cnt, level, maxBucket, split, nkids);
+    cudaChk(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, nkids, slot, cnt + 1, s));
+    int total = 0;
+    cudaChk(cudaMemcpyAsync(&total, slot + cnt, 4, cudaMemcpyDeviceToHost, s));
+    cudaChk(cudaStreamSynchronize(s)); /* the size of the next level decides the next launch */
+    g_launches.fetch_add(2);
+    if (total > 0) {
+      if (hi + total > cap) { out->error = 1; break; }
+      tree_emit_kernel<<<(cnt + tb - 1) / tb, tb, 0, s>>>(t, lo, cnt, level, split, slot, hi, cap, err);
+      cudaChk(cudaPeekAtLastError());
+      g_launches.fetch_add(1);
+    }
+    lo = hi;
+    hi += total;
+    ++level;
+  }
+  out->numLevels = level;
+  out->numNodes = hi;
+  const int nn = hi;
+
+  /* buckets in particle order; first bucket / bucket count of every node */
+  int *flag = (int *)pool_alloc((size_t)(n + 1) * 4, s);
+  int *rank = (int *)pool_alloc((size_t)(n + 1) * 4, s);
+  int *leafAt = (int *)pool_alloc((size_t)n * 4, s);
+  cudaChk(cudaMemsetAsync(flag, 0, (size_t)(n + 1) * 4, s));
+  tree_leaf_flags_kernel<<<(nn + tb - 1) / tb, tb, 0, s>>>(t, nn, flag, leafAt);
+  cudaChk(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, flag, rank, n + 1, s));
+  int nb = 0;
+  cudaChk(cudaMemcpyAsync(&nb, rank + n, 4, cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaStreamSynchronize(s));
+  out->numBuckets = nb;
+  out->d_bucketNode = (int *)pool_alloc((size_t)nb * 4, s);
+  out->d_bucketStarts = (int *)pool_alloc((size_t)nb * 4, s);
+  out->d_bucketSizes = (int *)pool_alloc((size_t)nb * 4, s);
+  out->d_bucketFirst = (int *)pool_alloc((size_t)nn * 4, s);
+  out->d_bucketCount = (int *)pool_alloc((size_t)nn * 4, s);
+  const int m = nn > n ? nn : n;
+  tree_buckets_kernel<<<(m + tb - 1) / tb, tb, 0, s>>>(t, nn, n, flag, rank, leafAt, out->d_bucketNode,
+                                                     out->d_bucketFirst, out->d_bucketCount, out->d_bucketStarts,
+                                                     out->d_bucketSizes);
+  cudaChk(cudaPeekAtLastError());
+  /* tight bounding boxes, bottom-up */
+  out->d_boxlo = (double *)pool_alloc((size_t)nn * 24, s);
+  out->d_boxhi = (double *)pool_alloc((size_t)nn * 24, s);
+  for (int lvl = out->numLevels - 1; lvl >= 0; --lvl) {
+    const int l0 = out->levelStart[lvl], cnt = out->levelStart[lvl + 1] - l0;
+    if (cnt <= 0) continue;
+    tree_boxes_level_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(t, out->d_pos, l0, cnt, out->d_boxlo, out->d_boxhi);
+    cudaChk(cudaPeekAtLastError());
+    g_launches.fetch_add(1);
+  }
+  g_launches.fetch_add(3);
+  int herr = 0;
+  cudaChk(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaStreamSynchronize(s));
+  if (herr) out->error = herr;
+  pool_free(flag, s); pool_free(rank, s); pool_free(leafAt, s); pool_free(scanTmp, s);
+  pool_free(split, s); pool_free(nkids, s); pool_free(slot, s); pool_free(err, s); pool_free(keys, s);
+}
+
+void cb200_tree_free(cb200_tree *t, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  pool_free(t->d_pos, s); pool_free(t->d_mass, s); pool_free(t->d_soft, s); pool_free(t->d_packedParts, s);
+  pool_free(t->d_order, s); pool_free(t->d_child0, s); pool_free(t->d_child1, s); pool_free(t->d_parent, s);
+  pool_free(t->d_first, s); pool_free(t->d_last, s); pool_free(t->d_geolo, s); pool_free(t->d_geohi, s);
+  pool_free(t->d_boxlo, s); pool_free(t->d_boxhi, s); pool_free(t->d_bucketNode, s);
+  pool_free(t->d_bucketFirst, s); pool_free(t->d_bucketCount, s); pool_free(t->d_bucketStarts, s);
+  pool_free(t->d_bucketSizes, s);
+  memset(t, 0, sizeof *t);
 }
 
 /* ---- interaction lists on the device ---- */

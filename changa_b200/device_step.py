@@ -146,3 +146,165 @@ class DeviceTreeStep:
             self.hc.EwaldHostMemoryFree(self._ew, 0)
             self._ew = None
         self.h = self.out = self.dev = None
+
+
+class RawParticleStep:
+    """The whole force step from UNSORTED particles (SURVEY f1 + f2): per step the host hands over
+    positions, masses and softenings (40 bytes per particle) and gets accelerations back in its
+    own particle order; keys, sort, tree topology, boxes, moments, interaction lists, forces and
+    the Ewald sum all run on the device (cb200_build_tree, cb200_build_moments,
+    cb200_walk_device, cb200_*_list_device_ex, cb200_EwaldHost)."""
+
+    def __init__(self, hc, pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, ewald=None, max_bucket=12,
+                 root_lo=(-0.5, -0.5, -0.5), root_hi=(0.5, 0.5, 0.5)):
+        import torch
+        self.torch, self.hc = torch, hc
+        self.theta, self.nrep, self.period = float(theta), int(n_replicas), float(period)
+        self.ewald, self.max_bucket = ewald, int(max_bucket)
+        self.lo = np.ascontiguousarray(root_lo, dtype=np.float64)
+        self.hi = np.ascontiguousarray(root_hi, dtype=np.float64)
+        self.ext = torch.cuda.Stream()
+        self.stream = self.ext.cuda_stream
+        n = len(pos)
+        self.n = n
+        pin = lambda a: torch.from_numpy(np.array(a, dtype=np.float64, order="C")).pin_memory()
+        self.h = {"pos": pin(pos), "mass": pin(np.broadcast_to(mass, (n,))), "soft": pin(np.broadcast_to(soft, (n,)))}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.h.values())
+        self.out = torch.zeros((n, 5), dtype=torch.float32).pin_memory()
+        self.d2h_bytes = self.out.numel() * 4
+        self.dev = None
+        self.info = None
+        self._ew = None
+
+    def run(self, phases=None, keep_tree=False, count_pairs=False):
+        """count_pairs: also leave {pc_pairs, pp_pairs} (sum over buckets of list length x bucket
+        size, as Compute.cpp:1643-1651 counts interactions) in self.info"""
+        torch, hc, L, s, n = self.torch, self.hc, self.hc.L, self.stream, self.n
+        marks = []
+
+        def mark(name):
+            if phases is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(self.ext)
+                marks.append((name, e))
+
+        with torch.cuda.stream(self.ext):
+            if self.dev is None:
+                self.dev = {k: torch.empty_like(v, device="cuda") for k, v in self.h.items()}
+                self.dev["vars"] = torch.empty((n, 5), dtype=torch.float32, device="cuda")
+                self.dev["out"] = torch.empty((n, 5), dtype=torch.float32, device="cuda")
+            d = self.dev
+            mark("start")
+            for k, v in self.h.items():
+                d[k].copy_(v, non_blocking=True)
+            mark("h2d")
+            tr = hc.T.DevTree()
+            L.cb200_build_tree(d["pos"].data_ptr(), d["mass"].data_ptr(), d["soft"].data_ptr(), n, self.max_bucket,
+                               self.lo.ctypes.data, self.hi.ctypes.data, C.byref(tr), s)
+            if tr.error:
+                raise RuntimeError("device tree build: node capacity exceeded")
+            mark("tree")
+            nn, nb = tr.numNodes, tr.numBuckets
+            key = (nn,)
+            if d.get("key") != key:  # node-sized buffers follow the tree
+                d["mom32"] = torch.empty((nn, 27), dtype=torch.float32, device="cuda")
+                d["mom64"] = torch.empty((nn, 27), dtype=torch.float64, device="cuda")
+                d["pk_mom"] = torch.empty(nn * L.cb200_packed_moment_bytes(), dtype=torch.uint8, device="cuda")
+                d["key"] = key
+            mom32, mom64 = d["mom32"], d["mom64"]
+            lvl = C.addressof(tr) + hc.T.DevTree.levelStart.offset
+            L.cb200_build_moments(tr.d_pos, tr.d_mass, tr.d_soft, n, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last,
+                                  tr.d_geolo, tr.d_geohi, tr.d_boxlo, tr.d_boxhi, lvl, tr.numLevels, nn,
+                                  mom32.data_ptr(), mom64.data_ptr(), s)
+            mark("moments")
+            lists = hc.T.Lists()
+            L.cb200_walk_device(nn, nb, tr.numLevels, lvl, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first,
+                                tr.d_last, tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo,
+                                tr.d_boxhi, mom64.data_ptr(), self.theta, self.nrep, self.period, 0, nb,
+                                C.byref(lists), s)
+            if lists.error:
+                raise RuntimeError(f"device walk: per-node capacity exceeded (error {lists.error})")
+            mark("walk")
+            L.cb200_pack_moments_device(mom32.data_ptr(), d["pk_mom"].data_ptr(), nn, s)
+            vars_ = d["vars"]
+            L.cb200_zero_vars_device(vars_.data_ptr(), n, s)
+            P, V, M = tr.d_packedParts, vars_.data_ptr(), d["pk_mom"].data_ptr()
+            fper = self.period if (self.nrep or self.ewald is not None) else 0.0
+            mark("pack")
+            if self.ewald is not None:
+                from .tree import ewald_tables_fast as ewald_tables
+                hc.stream_synchronize(s)
+                root = mom64[0].cpu().numpy()
+                momc, ewt = ewald_tables(root, self.period, self.ewald.get("dEwhCut", 2.8))
+                if self._ew is None:
+                    self._ew = hc.EwaldHostMemorySetup(1, len(ewt), 0)
+                hc.fill_ewald(self._ew, root, momc, ewt, self.period, float(self.ewald.get("dEwCut", 2.6)), self.nrep,
+                              active=None, first=0, last=n - 1)
+                L.cb200_EwaldHost(P, V, C.byref(self._ew), s, None, 0, 0)
+            mark("ewald")
+            mx = self.max_bucket
+            L.cb200_cell_list_device_ex(P, V, M, lists.d_cell, lists.d_cellMarkers, lists.d_starts, lists.d_sizes,
+                                        nb, fper, mx, s)
+            L.cb200_part_list_device_ex(P, V, P, lists.d_part, lists.d_partMarkers, lists.d_starts, lists.d_sizes,
+                                        nb, fper, mx, s)
+            if lists.nSoft:
+                L.cb200_part_list_device_ex(P, V, lists.d_nodeParticles, lists.d_soft, lists.d_softMarkers,
+                                            lists.d_starts, lists.d_sizes, nb, fper, mx, s)
+            mark("forces")
+            # back to the caller's particle order: out[order[i]] = vars[i]
+            order = torch.empty(n, dtype=torch.int32, device="cuda")
+            L.cb200_copy_device(order.data_ptr(), tr.d_order, n * 4, s)
+            d["out"].index_copy_(0, order.long(), vars_)
+            self.out.copy_(d["out"], non_blocking=True)
+            mark("d2h")
+            self.info = {"nodes": nn, "buckets": nb, "levels": tr.numLevels, "nCell": int(lists.nCell),
+                         "nSoft": int(lists.nSoft), "nPart": int(lists.nPart)}
+            if keep_tree:
+                self.kept_tree = self._download_tree(tr)
+            if count_pairs:
+                def dev_i32(ptr, count):
+                    t = torch.empty(count, dtype=torch.int32, device="cuda")
+                    L.cb200_copy_device(t.data_ptr(), ptr, count * 4, s)
+                    return t.long()
+                sizes = dev_i32(lists.d_sizes, nb)
+                pairs = [int((torch.diff(dev_i32(m, nb + 1)) * sizes).sum().item())
+                         for m in (lists.d_cellMarkers, lists.d_partMarkers, lists.d_softMarkers)]
+                self.info.update(pc_pairs=pairs[0], pp_pairs=pairs[1] + pairs[2])
+            L.cb200_lists_free(C.byref(lists), s)
+            L.cb200_tree_free(C.byref(tr), s)
+            hc.stream_synchronize(s)
+        if phases is not None:
+            for (_, a), (name, b) in zip(marks, marks[1:]):
+                phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
+        return self.out.numpy()
+
+    def _download_tree(self, tr):
+        torch, L, s = self.torch, self.hc.L, self.stream
+
+        def arr(ptr, count, dtype):
+            t = torch.empty(count, dtype=dtype, device="cuda")
+            if count:
+                L.cb200_copy_device(t.data_ptr(), ptr, count * t.element_size(), s)
+            self.hc.stream_synchronize(s)
+            return t.cpu().numpy()
+        n, nn, nb = tr.numParticles, tr.numNodes, tr.numBuckets
+        i32, f64 = torch.int32, torch.float64
+        out = {"order": arr(tr.d_order, n, i32), "pos": arr(tr.d_pos, 3 * n, f64).reshape(n, 3),
+               "mass": arr(tr.d_mass, n, f64), "soft": arr(tr.d_soft, n, f64),
+               "level_start": np.array(tr.levelStart[:tr.numLevels + 1], dtype=np.int32)}
+        for name, ptr in (("child0", tr.d_child0), ("child1", tr.d_child1), ("parent", tr.d_parent),
+                          ("first", tr.d_first), ("last", tr.d_last), ("bucket_first", tr.d_bucketFirst),
+                          ("bucket_count", tr.d_bucketCount)):
+            out[name] = arr(ptr, nn, i32)
+        for name, ptr in (("geolo", tr.d_geolo), ("geohi", tr.d_geohi), ("boxlo", tr.d_boxlo), ("boxhi", tr.d_boxhi)):
+            out[name] = arr(ptr, 3 * nn, f64).reshape(nn, 3)
+        for name, ptr in (("bucket_node", tr.d_bucketNode), ("bucket_starts", tr.d_bucketStarts),
+                          ("bucket_sizes", tr.d_bucketSizes)):
+            out[name] = arr(ptr, nb, i32)
+        return out
+
+    def free(self):
+        if self._ew is not None:
+            self.hc.EwaldHostMemoryFree(self._ew, 0)
+            self._ew = None
+        self.h = self.out = self.dev = None

@@ -78,10 +78,19 @@ def make_types(double=False):
                     ("nCell", C.c_longlong), ("nSoft", C.c_longlong), ("nPart", C.c_longlong),
                     ("numBuckets", C.c_int), ("error", C.c_int)]
 
+    class DevTree(C.Structure):
+        _fields_ = [(n, C.c_void_p) for n in (
+            "d_pos", "d_mass", "d_soft", "d_packedParts", "d_order", "d_child0", "d_child1", "d_parent",
+            "d_first", "d_last", "d_geolo", "d_geohi", "d_boxlo", "d_boxhi", "d_bucketNode",
+            "d_bucketFirst", "d_bucketCount", "d_bucketStarts", "d_bucketSizes")] + [
+            ("numParticles", C.c_int), ("numNodes", C.c_int), ("numBuckets", C.c_int), ("numLevels", C.c_int),
+            ("levelStart", C.c_int * 66), ("error", C.c_int)]
+
     class T:
         pass
 
     T.Lists = Lists
+    T.DevTree = DevTree
 
     T.real = real
     T.np_real = np.float64 if double else np.float32
@@ -113,6 +122,7 @@ C_ABI_SYMBOLS = [
     "cb200_pack_moments_device", "cb200_pack_particles_device", "cb200_zero_vars_device", "cb200_copy_device",
     "cb200_timing_enable", "cb200_timing_reset", "cb200_timing_read", "cb200_kernel_launches",
     "cb200_build_moments", "cb200_partition_buckets", "cb200_walk_device", "cb200_lists_free",
+    "cb200_build_tree", "cb200_tree_free",
 ]
 
 CALLBACK_FN = C.CFUNCTYPE(None, C.c_void_p)
@@ -182,6 +192,8 @@ def load(double=False):
     L.cb200_walk_device.argtypes = [i, i, i, vp] + [vp] * 11 + [C.c_double, i, C.c_double, i, i,
                                                                  C.POINTER(T.Lists), vp]
     L.cb200_lists_free.argtypes = [C.POINTER(T.Lists), vp]
+    L.cb200_build_tree.argtypes = [vp, vp, vp, i, i, vp, vp, C.POINTER(T.DevTree), vp]
+    L.cb200_tree_free.argtypes = [C.POINTER(T.DevTree), vp]
     L.types = T
     L.path = path
     _LIBS[double] = L

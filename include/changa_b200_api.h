@@ -196,6 +196,32 @@ void cb200_build_moments(const double *d_pos_xyz, const double *d_mass,
                          void *d_moments_out, double *d_moments_f64_out,
                          void *stream);
 
+/* --- new: tree topology built on the device --------------------- */
+/* The single-TreePiece tree of csrc/treewalk.cpp (GenericTreeNode.h:473-598,
+ * Compute.cpp:2476-2477, DataManager.cpp:797-828) from UNSORTED device arrays:
+ * Morton keys in [rootlo, roothi), stable sort, binary splits on key bits, nodes
+ * breadth first, buckets in particle order, tight boxes.  Every array equals the
+ * host build bit for bit.  The result feeds cb200_build_moments and
+ * cb200_walk_device directly; d_order[i] = caller index of sorted particle i.
+ * Arrays live in the stream-ordered pool (cb200_tree_free).  error != 0: the node
+ * capacity (1.5 n + 4096) was exceeded. */
+typedef struct cb200_tree {
+  double *d_pos, *d_mass, *d_soft; /* sorted particles */
+  void *d_packedParts;             /* the same as packed particles (layout of the force kernels) */
+  int *d_order;
+  int *d_child0, *d_child1, *d_parent, *d_first, *d_last;
+  double *d_geolo, *d_geohi, *d_boxlo, *d_boxhi;
+  int *d_bucketNode, *d_bucketFirst, *d_bucketCount, *d_bucketStarts, *d_bucketSizes;
+  int numParticles, numNodes, numBuckets, numLevels;
+  int levelStart[66]; /* HOST: node offsets of the levels, numLevels + 1 entries */
+  int error;
+} cb200_tree;
+
+void cb200_build_tree(const double *d_pos_xyz, const double *d_mass, const double *d_soft,
+                      int numParticles, int maxBucket, const double *rootlo,
+                      const double *roothi, cb200_tree *out, void *stream);
+void cb200_tree_free(cb200_tree *tree, void *stream);
+
 /* --- new: interaction lists built on the device ----------------- */
 /* The double walk of TreeWalk.cpp:308-397 / Compute.cpp:690-884,1608-1863 on the
  * GPU: per bucket exactly the entries, order and offsetID bits of ChaNGa's host

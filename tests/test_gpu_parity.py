@@ -405,3 +405,57 @@ def test_device_walk_bucket_range(hc):
         step.free()
     assert np.array_equal(dev["cell_mark"], host["cell_mark"].astype(np.int32))
     assert np.array_equal(dev["cell"], host["cell"])
+
+
+# ---------------------------------------------------------------------------------------
+# tree topology built on the device
+# ---------------------------------------------------------------------------------------
+def _raw_config(name, n):
+    from changa_b200 import workloads as W
+    if name == "cube300":
+        return W.cosmo_box(int(round(n ** (1 / 3)))) + ((-0.5,) * 3, (0.5,) * 3, 1)
+    if name == "king":
+        pos, mass, soft = W.plummer_sphere(n, rs=1.0)
+        ext = float(np.abs(pos).max()) * 1.0001
+        return pos, mass, soft, (-ext,) * 3, (ext,) * 3, 0
+    rng = np.random.default_rng(5)  # duplicates: equal keys must keep the caller's order
+    pos = rng.uniform(-0.5, 0.5, (n // 2, 3))
+    pos = np.concatenate([pos, pos[: n - n // 2]])
+    return pos, np.full(n, 1.0 / n), np.full(n, 0.01), (-0.5,) * 3, (0.5,) * 3, 1
+
+
+@pytest.mark.parametrize("name,n", [("cube300", 14 ** 3), ("king", 6000), ("duplicates", 3000)])
+def test_device_tree_is_bit_exact(hc, name, n):
+    """cb200_build_tree reproduces every array of the host tree (csrc/treewalk.cpp)"""
+    from changa_b200.device_step import RawParticleStep
+    from changa_b200.tree import Tree
+    pos, mass, soft, lo, hi, nrep = _raw_config(name, n)
+    host = Tree(pos, mass, soft, max_bucket=12, root_lo=lo, root_hi=hi)
+    step = RawParticleStep(hc, pos, mass, soft, theta=0.7, n_replicas=nrep, period=1.0, ewald=None, root_lo=lo, root_hi=hi)
+    try:
+        step.run(keep_tree=True)
+        dev = step.kept_tree
+    finally:
+        step.free()
+    assert len(dev["child0"]) == host.num_nodes and len(dev["bucket_node"]) == host.num_buckets
+    assert np.array_equal(dev["order"], host.order)
+    assert np.array_equal(dev["pos"], host.parts[:, 2:5])
+    assert np.array_equal(dev["level_start"], host.level_start)
+    for k in ("child0", "child1", "parent", "first", "last", "bucket_first", "bucket_count", "bucket_node",
+              "bucket_starts", "bucket_sizes", "geolo", "geohi", "boxlo", "boxhi"):
+        assert np.array_equal(dev[k], getattr(host, k)), k
+
+
+def test_raw_particle_step_matches_oracle(hc):
+    """unsorted particles in, accelerations out in the caller's order; everything in between on the device"""
+    from changa_b200.workloads import config_workload, cosmo_box
+    from changa_b200.device_step import RawParticleStep
+    wl = config_workload("cube300", n=16 ** 3)
+    pos, mass, soft = cosmo_box(16)
+    step = RawParticleStep(hc, pos, mass, soft, theta=0.7, n_replicas=1, period=1.0, ewald={})
+    try:
+        got = step.run().copy()
+    finally:
+        step.free()
+    want = oracle_forces_tree(wl)  # sorted order
+    compare(got[wl["order"]], want, median_tol=5e-6, max_tol=3e-4, pot_tol=2e-5, floor_frac=0.1)

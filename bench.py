@@ -267,40 +267,55 @@ class ResidentStep:
         return sum(a.elapsed_time(b) for a, b in evs)  # ms over exactly `steps` steps
 
 
-def large_box_step(hc, n, steps=3):
-    """The same force step on a box that fills the GPU (uniform, SURVEY 8d recipe C3 at a size one
+def large_box_step(hc, n, torch, dist, rank, world, steps=3):
+    """The same force step on a box that fills a GPU (uniform, SURVEY 8d recipe C3 at a size one
     default run can afford), from UNSORTED host particles: upload 40 B/particle, then keys, sort,
     tree, moments, double walk, p-c / p-p / Ewald all on the device, accelerations back in the
-    caller's order (changa_b200.device_step.RawParticleStep).  Reported next to the headline
-    numbers: kernel rates without the launch ramp and tail of the 110k-particle box."""
+    caller's order (changa_b200.device_step.RawParticleStep).  At N > 1 the SAME box is shared
+    (strong scaling): every rank uploads 1/N of the records, one NCCL all-gather replicates them,
+    tree and moments are built redundantly, each rank walks and evaluates its own SFC range of
+    buckets.  Reported next to the headline numbers: kernel rates without the launch ramp and
+    tail of the 110k-particle box."""
     from changa_b200.device_step import RawParticleStep
     from changa_b200.workloads import uniform_box
     pos, mass, soft = uniform_box(n, seed=1)
     st = RawParticleStep(hc, pos, mass, soft, theta=0.7, n_replicas=1, period=1.0,
-                         ewald={"dEwCut": 2.6, "dEwhCut": 2.8}, max_bucket=12)
+                         ewald={"dEwCut": 2.6, "dEwhCut": 2.8}, max_bucket=12, dist=dist, rank=rank, world=world)
     st.run(count_pairs=True)  # warm-up (pool growth); the markers give the pair counts
     info = dict(st.info)
-    pc, pp = info["pc_pairs"], info["pp_pairs"]
     hc.timing(True)
     phases = {}
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         out = st.run(phases=phases)
+    torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / steps
-    finite = bool(np.isfinite(out).all())
+    rows = out[1] if world > 1 else out
+    finite = bool(np.isfinite(rows).all())
     taps = hc.timing_read()
     hc.timing(False)
     h2d, d2h = st.h2d_bytes, st.d2h_bytes
     st.free()
+    agg = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([info["pc_pairs"], info["pp_pairs"], h2d, d2h, len(rows)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    wall = float(agg[0])
+    pc, pp, h2d, d2h, nrows = (float(x) for x in tot.tolist())
     pc_ms = taps["cell_ms"] / max(taps["cell_launches"], 1)
     return {"workload": f"uniform(N={n},theta=0.7,nReplicas=1,bucket=12), tree and lists built on the device",
+            "scaling": "strong" if world > 1 else None, "n_gpus": world,
             "ms_per_step": wall * 1e3, "steps": steps, "interactions_per_s": (pc + pp) / wall,
-            "nodes": info["nodes"], "buckets": info["buckets"], "pc_pairs": pc, "pp_pairs": pp,
-            "phases_ms": {a: round(b / steps, 3) for a, b in phases.items()},
-            "pc_ms": pc_ms, "pc_tflops": pc * FLOP_PC / (pc_ms * 1e-3) / 1e12,
-            "pp_ms": taps["part_ms"] / steps, "ewald_ms": taps["ewald_ms"] / max(taps["ewald_launches"], 1),
+            "nodes": info["nodes"], "buckets": info["buckets"], "pc_pairs": pc, "pp_pairs": pp, "result_rows": nrows,
+            "rank0_phases_ms": {a: round(b / steps, 3) for a, b in phases.items()},
+            "rank0_pc_ms": pc_ms, "rank0_pc_tflops": info["pc_pairs"] * FLOP_PC / (pc_ms * 1e-3) / 1e12,
+            "rank0_pp_ms": taps["part_ms"] / steps, "rank0_ewald_ms": taps["ewald_ms"] / max(taps["ewald_launches"], 1),
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "finite": finite,
-            "timing": "wall clock around RawParticleStep.run(); phases and kernels by CUDA events on its stream"}
+            "timing": "wall clock around RawParticleStep.run() (max over ranks); phases and kernels by CUDA events on rank 0's stream"}
 
 
 def run_reference(args, rank, world):
@@ -343,7 +358,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 50)")
     ap.add_argument("--large-n", type=int, default=1 << 22,
-                    help="particles of the extra device-built-lists box at N=1 (0: skip)")
+                    help="particles of the extra box whose tree and lists are built on the device; "
+                         "shared by all ranks at N > 1 (0: skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -359,6 +375,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT: the line below must be the only one
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from changa_b200.hostcuda import HostCUDA, ForceStep
     from changa_b200.workloads import config_workload, interaction_counts
@@ -403,11 +421,14 @@ def main():
     fs.free()
 
     large = None
-    if world == 1 and args.large_n > 0:
-        try:
-            large = large_box_step(hc, args.large_n)
-        except Exception as e:  # extra information: never takes the headline line down
-            large = {"error": repr(e)}
+    if args.large_n > 0:
+        if world > 1:
+            large = large_box_step(hc, args.large_n, torch, dist, rank, world)
+        else:
+            try:
+                large = large_box_step(hc, args.large_n, torch, dist, rank, world)
+            except Exception as e:  # extra information: never takes the headline line down
+                large = {"error": repr(e)}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- aggregate over ranks ------------------------------------------------------------
@@ -462,8 +483,8 @@ def main():
             "clocks": clocks,
         }
         if large is not None:
-            if "pc_tflops" in large:
-                large["pc_frac_of_fp32_peak"] = large["pc_tflops"] / peaks["fp32_tflops"]
+            if "rank0_pc_tflops" in large:
+                large["rank0_pc_frac_of_fp32_peak"] = large["rank0_pc_tflops"] / peaks["fp32_tflops"]
             line["large_box"] = large
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -156,9 +156,15 @@ class RawParticleStep:
     cb200_walk_device, cb200_*_list_device_ex, cb200_EwaldHost)."""
 
     def __init__(self, hc, pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, ewald=None, max_bucket=12,
-                 root_lo=(-0.5, -0.5, -0.5), root_hi=(0.5, 0.5, 0.5)):
+                 root_lo=(-0.5, -0.5, -0.5), root_hi=(0.5, 0.5, 0.5), dist=None, rank=0, world=1):
+        """world > 1 (one process per GPU, torch.distributed `dist`): every rank holds rows
+        [rank*chunk, (rank+1)*chunk) of the particle set on its host; ONE all-gather per step
+        replicates the 40-byte records, every rank builds the same tree and moments, then walks,
+        evaluates and returns only its own contiguous SFC range of buckets (equal particle counts;
+        accelerations never leave the owning GPU).  run() then returns (caller indices, rows)."""
         import torch
         self.torch, self.hc = torch, hc
+        self.dist, self.rank, self.world = dist, int(rank), int(world)
         self.theta, self.nrep, self.period = float(theta), int(n_replicas), float(period)
         self.ewald, self.max_bucket = ewald, int(max_bucket)
         self.lo = np.ascontiguousarray(root_lo, dtype=np.float64)
@@ -167,10 +173,23 @@ class RawParticleStep:
         self.stream = self.ext.cuda_stream
         n = len(pos)
         self.n = n
-        pin = lambda a: torch.from_numpy(np.array(a, dtype=np.float64, order="C")).pin_memory()
-        self.h = {"pos": pin(pos), "mass": pin(np.broadcast_to(mass, (n,))), "soft": pin(np.broadcast_to(soft, (n,)))}
-        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.h.values())
-        self.out = torch.zeros((n, 5), dtype=torch.float32).pin_memory()
+        rec = np.empty((n, 5))  # {x, y, z, mass, soft}: the record that crosses PCIe and NVLink
+        rec[:, :3] = pos
+        rec[:, 3] = mass
+        rec[:, 4] = soft
+        self.chunk = -(-n // self.world)
+        mine = np.zeros((self.chunk, 5))
+        mine[:, 4] = 1.0
+        # pad rows (only when world does not divide n) sit at the far corner with zero mass;
+        # they never reach the tree: the gathered array is cut back to n rows
+        lo_r = self.rank * self.chunk
+        hi_r = min(n, lo_r + self.chunk)
+        mine[: max(0, hi_r - lo_r)] = rec[lo_r:hi_r]
+        self.h = {"rec": torch.from_numpy(mine).pin_memory()}
+        self.h2d_bytes = self.h["rec"].numel() * 8
+        rows = n if self.world == 1 else 2 * self.chunk + 64
+        self.out = torch.zeros((rows, 5), dtype=torch.float32).pin_memory()
+        self.out_idx = torch.zeros(rows, dtype=torch.int32).pin_memory()
         self.d2h_bytes = self.out.numel() * 4
         self.dev = None
         self.info = None
@@ -190,14 +209,26 @@ class RawParticleStep:
 
         with torch.cuda.stream(self.ext):
             if self.dev is None:
-                self.dev = {k: torch.empty_like(v, device="cuda") for k, v in self.h.items()}
-                self.dev["vars"] = torch.empty((n, 5), dtype=torch.float32, device="cuda")
-                self.dev["out"] = torch.empty((n, 5), dtype=torch.float32, device="cuda")
+                self.dev = {"rec": torch.empty_like(self.h["rec"], device="cuda"),
+                            "all": torch.empty((self.chunk * self.world, 5), dtype=torch.float64, device="cuda"),
+                            "pos": torch.empty((n, 3), dtype=torch.float64, device="cuda"),
+                            "mass": torch.empty(n, dtype=torch.float64, device="cuda"),
+                            "soft": torch.empty(n, dtype=torch.float64, device="cuda"),
+                            "vars": torch.empty((n, 5), dtype=torch.float32, device="cuda"),
+                            "out": torch.empty((n, 5), dtype=torch.float32, device="cuda")}
             d = self.dev
             mark("start")
-            for k, v in self.h.items():
-                d[k].copy_(v, non_blocking=True)
+            d["rec"].copy_(self.h["rec"], non_blocking=True)
             mark("h2d")
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(d["all"], d["rec"])
+                full = d["all"]
+            else:
+                full = d["rec"]
+            d["pos"].copy_(full[:n, :3])
+            d["mass"].copy_(full[:n, 3])
+            d["soft"].copy_(full[:n, 4])
+            mark("gather")
             tr = hc.T.DevTree()
             L.cb200_build_tree(d["pos"].data_ptr(), d["mass"].data_ptr(), d["soft"].data_ptr(), n, self.max_bucket,
                                self.lo.ctypes.data, self.hi.ctypes.data, C.byref(tr), s)
@@ -217,10 +248,23 @@ class RawParticleStep:
                                   tr.d_geolo, tr.d_geohi, tr.d_boxlo, tr.d_boxhi, lvl, tr.numLevels, nn,
                                   mom32.data_ptr(), mom64.data_ptr(), s)
             mark("moments")
+            b0, b1, p0, p1 = 0, nb, 0, n
+            if self.world > 1:  # my contiguous SFC range of buckets: equal particle counts, never splits a bucket
+                starts = torch.empty(nb, dtype=torch.int32, device="cuda")
+                L.cb200_copy_device(starts.data_ptr(), tr.d_bucketStarts, nb * 4, s)
+                want = torch.tensor([self.rank * n // self.world, (self.rank + 1) * n // self.world],
+                                    dtype=torch.int32, device="cuda")
+                cut = torch.searchsorted(starts, want, right=False).tolist()
+                b0 = 0 if self.rank == 0 else int(cut[0])
+                b1 = nb if self.rank == self.world - 1 else int(cut[1])
+                edge = starts[[min(b0, nb - 1), min(b1, nb - 1)]].tolist()
+                p0 = int(edge[0]) if b0 < nb else n
+                p1 = int(edge[1]) if b1 < nb else n
+            self.range = (b0, b1, p0, p1)
             lists = hc.T.Lists()
             L.cb200_walk_device(nn, nb, tr.numLevels, lvl, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first,
                                 tr.d_last, tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo,
-                                tr.d_boxhi, mom64.data_ptr(), self.theta, self.nrep, self.period, 0, nb,
+                                tr.d_boxhi, mom64.data_ptr(), self.theta, self.nrep, self.period, b0, b1,
                                 C.byref(lists), s)
             if lists.error:
                 raise RuntimeError(f"device walk: per-node capacity exceeded (error {lists.error})")
@@ -238,9 +282,10 @@ class RawParticleStep:
                 momc, ewt = ewald_tables(root, self.period, self.ewald.get("dEwhCut", 2.8))
                 if self._ew is None:
                     self._ew = hc.EwaldHostMemorySetup(1, len(ewt), 0)
-                hc.fill_ewald(self._ew, root, momc, ewt, self.period, float(self.ewald.get("dEwCut", 2.6)), self.nrep,
-                              active=None, first=0, last=n - 1)
-                L.cb200_EwaldHost(P, V, C.byref(self._ew), s, None, 0, 0)
+                if p1 > p0:
+                    hc.fill_ewald(self._ew, root, momc, ewt, self.period, float(self.ewald.get("dEwCut", 2.6)),
+                                  self.nrep, active=None, first=p0, last=p1 - 1)
+                    L.cb200_EwaldHost(P, V, C.byref(self._ew), s, None, 0, 0)
             mark("ewald")
             mx = self.max_bucket
             L.cb200_cell_list_device_ex(P, V, M, lists.d_cell, lists.d_cellMarkers, lists.d_starts, lists.d_sizes,
@@ -254,8 +299,14 @@ class RawParticleStep:
             # back to the caller's particle order: out[order[i]] = vars[i]
             order = torch.empty(n, dtype=torch.int32, device="cuda")
             L.cb200_copy_device(order.data_ptr(), tr.d_order, n * 4, s)
-            d["out"].index_copy_(0, order.long(), vars_)
-            self.out.copy_(d["out"], non_blocking=True)
+            if self.world == 1:
+                d["out"].index_copy_(0, order.long(), vars_)
+                self.out.copy_(d["out"], non_blocking=True)
+            else:  # my rows only, with the caller indices they belong to
+                if p1 - p0 > self.out.shape[0]:
+                    raise RuntimeError("bucket range larger than the result buffer")
+                self.out[: p1 - p0].copy_(vars_[p0:p1], non_blocking=True)
+                self.out_idx[: p1 - p0].copy_(order[p0:p1], non_blocking=True)
             mark("d2h")
             self.info = {"nodes": nn, "buckets": nb, "levels": tr.numLevels, "nCell": int(lists.nCell),
                          "nSoft": int(lists.nSoft), "nPart": int(lists.nPart)}
@@ -276,6 +327,10 @@ class RawParticleStep:
         if phases is not None:
             for (_, a), (name, b) in zip(marks, marks[1:]):
                 phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
+        if self.world > 1:
+            k = self.range[3] - self.range[2]
+            self.d2h_bytes = k * 24  # 5 floats + the caller index per row
+            return self.out_idx.numpy()[:k], self.out.numpy()[:k]
         return self.out.numpy()
 
     def _download_tree(self, tr):

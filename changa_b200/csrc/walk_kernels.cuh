@@ -175,7 +175,10 @@ __device__ __forceinline__ void walk_append(WalkEntry *dst, int &count, bool fla
 
 /* One level of the local tree: nodes [lo, lo+n).  scratch: per warp 4 x kWalkCap entries
  * (checklist, clist, lplist, undlist). */
-__global__ void __launch_bounds__(kWalkWarps * 32)
+#ifndef CB200_WALK_MINB
+#define CB200_WALK_MINB 1
+#endif
+__global__ void __launch_bounds__(kWalkWarps * 32, CB200_WALK_MINB)
 walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict__ lists, WalkPools pools,
                   WalkEntry *__restrict__ scratch) {
   const int lane = threadIdx.x & 31;

@@ -375,8 +375,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT: the line below must be the only one
+        # NCCL writes its debug output (the version banner at NCCL_DEBUG=VERSION/WARN) to STDOUT;
+        # the JSON line must be the only thing there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from changa_b200.hostcuda import HostCUDA, ForceStep
     from changa_b200.workloads import config_workload, interaction_counts

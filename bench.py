@@ -182,18 +182,23 @@ class ResidentStep:
         with torch.cuda.stream(self.ext):
             parts = np.ascontiguousarray(wl["parts"], dtype=f32)
             mom = np.ascontiguousarray(wl["moments"], dtype=f32)
-            if world > 1:  # every rank owns an equal, padded slice of both arrays; one all-gather each
+            pb, mb = L.cb200_packed_particle_bytes(), L.cb200_packed_moment_bytes()
+            if world > 1:
+                # every rank owns an equal, padded slice of both arrays.  It packs ITS slice into the
+                # kernels' layout and the all-gather lands the slices directly in the replicated packed
+                # arrays: no rank ever repacks the other ranks' records
                 from changa_b200.multigpu import shard_rows
                 mine_p, self.pc = shard_rows(parts, rank, world)
                 mine_m, self.mc = shard_rows(mom, rank, world)
                 self.my_parts, self.my_mom = up(mine_p), up(mine_m)
-                self.raw_parts = torch.zeros((self.pc * world, 5), dtype=torch.float32, device=dev)
-                self.raw_mom = torch.zeros((self.mc * world, 27), dtype=torch.float32, device=dev)
+                self.send_p = torch.empty(self.pc * pb, dtype=torch.uint8, device=dev)
+                self.send_m = torch.empty(self.mc * mb, dtype=torch.uint8, device=dev)
+                self.npk, self.nmk = self.pc * world, self.mc * world
             else:
                 self.raw_parts, self.raw_mom = up(parts), up(mom)
-            self.npk, self.nmk = self.raw_parts.shape[0], self.raw_mom.shape[0]
-            self.pk_parts = torch.empty(self.npk * L.cb200_packed_particle_bytes(), dtype=torch.uint8, device=dev)
-            self.pk_mom = torch.empty(self.nmk * L.cb200_packed_moment_bytes(), dtype=torch.uint8, device=dev)
+                self.npk, self.nmk = self.raw_parts.shape[0], self.raw_mom.shape[0]
+            self.pk_parts = torch.empty(self.npk * pb, dtype=torch.uint8, device=dev)
+            self.pk_mom = torch.empty(self.nmk * mb, dtype=torch.uint8, device=dev)
             self.vars = torch.zeros((self.n, 5), dtype=torch.float32, device=dev)
             self.lists = {}
             for key in ("cell", "part", "softcell"):
@@ -220,11 +225,13 @@ class ResidentStep:
     def step(self):
         L, s = self.hc.L, self.stream
         if self.world > 1:
-            from changa_b200.multigpu import gather_rows
-            gather_rows(self.dist, self.torch, self.my_parts, self.world, out=self.raw_parts)
-            gather_rows(self.dist, self.torch, self.my_mom, self.world, out=self.raw_mom)
-        L.cb200_pack_moments_device(self.raw_mom.data_ptr(), self.pk_mom.data_ptr(), self.nmk, s)
-        L.cb200_pack_particles_device(self.raw_parts.data_ptr(), self.pk_parts.data_ptr(), self.npk, s)
+            L.cb200_pack_moments_device(self.my_mom.data_ptr(), self.send_m.data_ptr(), self.mc, s)
+            L.cb200_pack_particles_device(self.my_parts.data_ptr(), self.send_p.data_ptr(), self.pc, s)
+            self.dist.all_gather_into_tensor(self.pk_mom, self.send_m)
+            self.dist.all_gather_into_tensor(self.pk_parts, self.send_p)
+        else:
+            L.cb200_pack_moments_device(self.raw_mom.data_ptr(), self.pk_mom.data_ptr(), self.nmk, s)
+            L.cb200_pack_particles_device(self.raw_parts.data_ptr(), self.pk_parts.data_ptr(), self.npk, s)
         L.cb200_zero_vars_device(self.vars.data_ptr(), self.n, s)
         P, V, M = self.pk_parts.data_ptr(), self.vars.data_ptr(), self.pk_mom.data_ptr()
         if self.ew is not None:  # same order as ForceStep.run: Ewald needs only the particles
@@ -375,10 +382,20 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its debug output (the version banner at NCCL_DEBUG=VERSION/WARN) to STDOUT;
-        # the JSON line must be the only thing there
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION/WARN) to STDOUT when the communicator
+        # comes up; the JSON line must be the only thing there, so fd 1 points at stderr meanwhile
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from changa_b200.hostcuda import HostCUDA, ForceStep
     from changa_b200.workloads import config_workload, interaction_counts
     hc = HostCUDA(double=False, device=local)
@@ -463,7 +480,7 @@ def main():
                        "theta": 0.7, "expansion": "hexadecapole", "bucket_size": 12,
                        "pc_pairs": g_pc, "pp_pairs": g_pp, "ewald_particles": g_ewn,
                        "l2": "flushed between steps (256 MiB device write)",
-                       "parallelism": f"buckets sharded by SFC range x{world}; particles+moments all-gathered per step" if world > 1 else "single GPU"},
+                       "parallelism": f"buckets sharded by SFC range x{world}; packed particle and moment slices all-gathered per step" if world > 1 else "single GPU"},
             "force_step_ms": ms_step,
             "kernels": {"pc_ms": pc_ms, "pp_ms": pp_ms, "ewald_ms": ew_ms,
                         "pc_interactions_per_s": cnt["cell"] / (pc_ms * 1e-3) if pc_ms else None,

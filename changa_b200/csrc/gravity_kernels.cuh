@@ -601,6 +601,8 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
   cp_async_commit();
 
   while (k < nBuckets) {
+    /* one bucket ahead only: reserving further ahead costs more at the tail (a warp sits on
+     * buckets it has not started) than the atomic's round trip costs here -- measured */
     const int kn = grab();
     BucketMeta mn = {0, 0, 0, 0};
     if (kn < nBuckets) mn = load_bucket_meta(markers, starts, sizes, kn);
@@ -713,8 +715,11 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
           sts(r0 + 9 * kRedPitch, idt[2 * j + 1]);
         }
       }
-      __syncwarp();
       float *out = reinterpret_cast<float *>(vars + m.first + p0);
+      float old[2]; /* the accumulators' current values: loaded under the shared-memory reduction */
+#pragma unroll
+      for (int h = 0; h < 2; ++h) old[h] = (lane + 32 * h < 5 * np) ? out[lane + 32 * h] : 0.0f;
+      __syncwarp();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int v = lane + 32 * h;
@@ -730,7 +735,7 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
             for (int i = 0; i < 32; ++i) acc += lds(row + i * 4);
           }
           /* accumulate, never overwrite (HostCUDA.cu:1196-1200); dtGrav is a running max */
-          out[v] = isMax ? fmaxf(out[v], acc) : out[v] + acc;
+          out[v] = isMax ? fmaxf(old[h], acc) : old[h] + acc;
         }
       }
       __syncwarp();
@@ -1069,8 +1074,11 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
           r0[160] = a1; r0[192] = b1; r0[224] = c1; r0[256] = e1; r0[288] = idt[2 * j + 1];
         }
       }
-      __syncwarp();
       float *out = reinterpret_cast<float *>(vars + m.first + p0);
+      float old[2]; /* the accumulators' current values: loaded under the shared-memory reduction */
+#pragma unroll
+      for (int h = 0; h < 2; ++h) old[h] = (lane + 32 * h < 5 * np) ? out[lane + 32 * h] : 0.0f;
+      __syncwarp();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int v = lane + 32 * h;
@@ -1083,7 +1091,7 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
             const float x = row[(i + lane) & 31];
             acc = isMax ? fmaxf(acc, x) : acc + x;
           }
-          out[v] = isMax ? fmaxf(out[v], acc) : out[v] + acc;
+          out[v] = isMax ? fmaxf(old[h], acc) : old[h] + acc;
         }
       }
       __syncwarp();

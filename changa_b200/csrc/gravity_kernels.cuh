@@ -1117,6 +1117,42 @@ __device__ __forceinline__ double exp_dev(double x) { return exp(x); }
 __device__ __forceinline__ void sincos_dev(float x, float *s, float *c) { sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_dev(double x, double *s, double *c) { sincos(x, s, c); }
 
+/* g0 = (erfc(x) or, inside the hole, -erf(x) = erfc(x) - 1) * dir and a = exp(-x^2) * scale.
+ * Float build: erfc(x) = t P(u) exp(-x^2) with t = 1/(1 + x/2), u = A t + B and P of degree 8
+ * fitted to erfc(x) exp(x^2)/t on [0.75, 6] (1.2e-7 relative in float arithmetic, the accuracy
+ * of erfcf), sharing its one exp(-x^2) = ex2(-x^2 log2 e) with the Gaussian term: ~18
+ * instructions instead of ~50 for erfcf + expf.  x >= 0.8 here (smaller x takes the series) and
+ * x <= 2 fEwCut; erfc(6) = 2e-17, so t is clamped there.  Double build: the library functions. */
+__device__ __forceinline__ void ewald_erfc_gauss(float x, float x2, bool hole, float scale, float dir,
+                                                 float &g0, float &a) {
+  float ex, t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * x2));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.5f, fminf(x, 6.0f), 1.0f)));
+  const float u = fmaf(4.190476190e+00f, t, -2.047619048e+00f);
+  float p = -7.590534245e-07f;
+  p = fmaf(p, u, 2.597246448e-06f); p = fmaf(p, u, 1.730812692e-05f); p = fmaf(p, u, -8.525551993e-05f);
+  p = fmaf(p, u, -5.383136886e-04f); p = fmaf(p, u, 2.085378610e-03f); p = fmaf(p, u, 3.153986530e-02f);
+  p = fmaf(p, u, 1.609637792e-01f); p = fmaf(p, u, 5.030546696e-01f);
+  const float e = t * p * ex;
+  g0 = (hole ? e - 1.0f : e) * dir;
+  a = ex * scale;
+}
+__device__ __forceinline__ void ewald_erfc_gauss(double x, double x2, bool hole, double scale, double dir,
+                                                 double &g0, double &a) {
+  a = exp(-x2) * scale;
+  g0 = (hole ? -erf(x) : erfc(x)) * dir;
+}
+/* sin and cos of h.x (|h.x| < ~20): one Cody-Waite reduction to [-pi, pi], then the SFU
+ * (absolute error 4e-7, which is what the reference's -use_fast_math sincosf gives) */
+__device__ __forceinline__ void ewald_sincos(float x, float &s, float &c) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);
+  r = fmaf(-k, -1.7484555314695172e-07f, r);
+  s = __sinf(r);
+  c = __cosf(r);
+}
+__device__ __forceinline__ void ewald_sincos(double x, double &s, double &c) { sincos(x, &s, &c); }
+
 constexpr int kEwaldThreads = 128;
 
 /* sum_j (-x)^j / (j! (2j + 2n + 1)), Horner from the highest term; enough terms
@@ -1214,8 +1250,8 @@ ewald_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict_
         } else {
           const real dir = rsqrt_dev(r2), dir2 = dir * dir;
           const real r = r2 * dir;
-          real a = exp_dev(-r2 * alpha2) * ka * dir2;
-          g0 = (hole ? -erf_dev(alpha * r) : erfc_dev(alpha * r)) * dir;
+          real a;
+          ewald_erfc_gauss(alpha * r, xa, hole, ka * dir2, dir, g0, a);
           g1 = g0 * dir2 + a;
           real an = twoa2;
           g2 = 3 * g1 * dir2 + an * a;
@@ -1260,7 +1296,7 @@ ewald_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict_
     const EwtData &e = P.ewt[i];
     const real hdotx = e.hx * dx + e.hy * dy + e.hz * dz;
     real s, c;
-    sincos_dev(hdotx, &s, &c);
+    ewald_sincos(hdotx, s, c);
     fPot += e.hCfac * c + e.hSfac * s;
     const real w = e.hCfac * s - e.hSfac * c;
     ax += e.hx * w; ay += e.hy * w; az += e.hz * w;

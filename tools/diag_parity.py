@@ -4,7 +4,7 @@ sys.path.insert(0, ".")
 from changa_b200.hostcuda import HostCUDA, ForceStep
 from changa_b200.workloads import config_workload
 from oracle import oracle as orc
-hc = HostCUDA(double=False, device=0)
+hc = HostCUDA(double=False, device=0)  # CB200_LIB selects another build
 wl = config_workload("cube300", n=16 ** 3)
 f32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32).astype(np.float64))
 parts, mom = f32(wl["parts"]), f32(wl["moments"])

@@ -438,6 +438,8 @@ def main():
     h2d, d2h = fs.h2d_bytes, fs.d2h_bytes
     fs.free()
 
+    clocks = sampler.stop() if rank == 0 else None  # the sampled region ends here: nvidia-smi polling stalls the driver for
+    # milliseconds at a time, which the long kernels of the extra box below would show
     large = None
     if args.large_n > 0:
         if world > 1:
@@ -447,7 +449,6 @@ def main():
                 large = large_box_step(hc, args.large_n, torch, dist, rank, world)
             except Exception as e:  # extra information: never takes the headline line down
                 large = {"error": repr(e)}
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- aggregate over ranks ------------------------------------------------------------
     agg = torch.tensor([ms_total, e2e_s, taps["cell_ms"], taps["part_ms"], taps["ewald_ms"]], dtype=torch.float64, device="cuda")

@@ -99,15 +99,107 @@ static const DeviceInfo &device_info() {
   return d;
 }
 
+/* Exact-size block cache in front of the stream-ordered pool.  A force step asks for the same
+ * sizes step after step (request blocks, tree arrays, walk pools: gigabytes at 10^7 particles);
+ * handing every one of them back to cudaFreeAsync and asking again makes the driver re-stitch
+ * virtual ranges, which shows up as random 20-200 ms stalls (measured on the 4 M box: 34 ms
+ * steps with occasional 300 ms ones).  A block of >= 1 MiB freed on a stream is parked under
+ * (device, stream, size) and handed to the next request of that size ON THAT STREAM -- stream order
+ * makes that safe with no event -- so in steady state the large blocks never reach the driver.
+ * The cache is capped at half of the device memory; over the cap it is flushed. */
+struct BlockKey {
+  int dev; cudaStream_t stream; size_t bytes;
+  bool operator==(const BlockKey &o) const { return dev == o.dev && stream == o.stream && bytes == o.bytes; }
+};
+struct BlockKeyHash {
+  size_t operator()(const BlockKey &k) const {
+    return std::hash<size_t>()(k.bytes) ^ (std::hash<void *>()((void *)k.stream) * 1315423911u) ^ (size_t)k.dev;
+  }
+};
+static std::mutex g_blockMutex;
+static std::unordered_map<BlockKey, std::vector<void *>, BlockKeyHash> g_blockFree;
+struct BlockInfo { size_t bytes; cudaStream_t stream; };
+static std::unordered_map<void *, BlockInfo> g_blockSize; /* large blocks handed out by pool_alloc */
+static size_t g_blockCached = 0, g_blockCap = 0;
+constexpr size_t kBlockCacheMin = 1u << 20;
+
+static void block_cache_flush_locked(int dev, cudaStream_t only, bool matchStream) {
+  for (auto it = g_blockFree.begin(); it != g_blockFree.end();) {
+    if (it->first.dev == dev && (!matchStream || it->first.stream == only)) {
+      for (void *p : it->second) {
+        /* the stream may be gone (stream_destroy) or about to be: cudaFree synchronises */
+        cudaChk(matchStream ? cudaFree(p) : cudaFreeAsync(p, it->first.stream));
+        g_blockCached -= it->first.bytes;
+      }
+      it = g_blockFree.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
 static void *pool_alloc(size_t bytes, cudaStream_t stream) {
   void *p = nullptr;
   if (bytes == 0) return nullptr;
   device_info();
+  int dev = 0;
+  cudaChk(cudaGetDevice(&dev));
+  if (bytes >= kBlockCacheMin) {
+    std::lock_guard<std::mutex> lock(g_blockMutex);
+    auto it = g_blockFree.find(BlockKey{dev, stream, bytes});
+    if (it != g_blockFree.end() && !it->second.empty()) {
+      p = it->second.back();
+      it->second.pop_back();
+      g_blockCached -= bytes;
+      g_blockSize[p] = BlockInfo{bytes, stream};
+      return p;
+    }
+  }
   cudaChk(cudaMallocAsync(&p, bytes, stream));
+  {
+    /* every block is recorded, small ones too: a caller may cudaFree() what we returned
+     * (DataManager.cpp:992-996), and the address can come back for a block of another size */
+    std::lock_guard<std::mutex> lock(g_blockMutex);
+    g_blockSize[p] = BlockInfo{bytes, stream};
+  }
   return p;
 }
 static void pool_free(void *p, cudaStream_t stream) {
-  if (p) cudaChk(cudaFreeAsync(p, stream));
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lock(g_blockMutex);
+    auto it = g_blockSize.find(p);
+    if (it != g_blockSize.end()) {
+      const size_t bytes = it->second.bytes;
+      /* a block allocated on one stream and released on another (a staging block: filled by the
+       * copy stream, released by the kernel's stream) goes back to the driver pool, which
+       * re-uses it only once this release has completed */
+      const bool sameStream = it->second.stream == stream;
+      g_blockSize.erase(it);
+      if (!sameStream || bytes < kBlockCacheMin) goto to_driver;
+      int dev = 0;
+      cudaChk(cudaGetDevice(&dev));
+      if (g_blockCap == 0) {
+        size_t freeB = 0, totalB = 0;
+        cudaChk(cudaMemGetInfo(&freeB, &totalB));
+        g_blockCap = totalB / 2;
+      }
+      if (g_blockCached + bytes > g_blockCap) block_cache_flush_locked(dev, nullptr, false);
+      if (g_blockCached + bytes <= g_blockCap) {
+        g_blockFree[BlockKey{dev, stream, bytes}].push_back(p);
+        g_blockCached += bytes;
+        return;
+      }
+    }
+  }
+to_driver:
+  cudaChk(cudaFreeAsync(p, stream));
+}
+static void pool_forget_stream(cudaStream_t stream) {
+  int dev = 0;
+  cudaChk(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_blockMutex);
+  block_cache_flush_locked(dev, stream, true);
 }
 
 /* ------------------------------------------------------- copy/compute overlap */
@@ -146,6 +238,7 @@ static void drop_companion(cudaStream_t user) {
   std::lock_guard<std::mutex> lock(g_compMutex);
   auto it = g_comp.find(user);
   if (it == g_comp.end()) return;
+  pool_forget_stream(it->second->copy);
   cudaStreamDestroy(it->second->copy);
   for (cudaEvent_t &e : it->second->ev) cudaEventDestroy(e);
   delete it->second;
@@ -622,6 +715,7 @@ void *cb200_stream_create(void) {
   return (void *)s;
 }
 void cb200_stream_destroy(void *stream) {
+  pool_forget_stream((cudaStream_t)stream);
   drop_companion((cudaStream_t)stream);
   cudaChk(cudaStreamDestroy((cudaStream_t)stream));
 }
@@ -971,6 +1065,7 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
   emit_count_kernel<<<emitGrid, kWalkWarps * 32, 0, s>>>(t, p, lists, pools, counts, counts + nb1, counts + 2 * nb1,
                                                        out->d_starts, out->d_sizes);
   cudaChk(cudaPeekAtLastError());
+  walk_totals_kernel<<<((int)nb1 + 255) / 256, 256, 0, s>>>(counts, (int)nb1, (unsigned long long *)(ctl + 160));
   size_t tmpBytes = 0;
   cudaChk(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts, out->d_cellMarkers, (int)nb1, s));
   void *tmp = pool_alloc(tmpBytes, s);
@@ -983,8 +1078,13 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
   cudaChk(cudaMemcpyAsync(&totals[1], out->d_softMarkers + numBuckets, sizeof(int), cudaMemcpyDeviceToHost, s));
   cudaChk(cudaMemcpyAsync(&totals[2], out->d_partMarkers + numBuckets, sizeof(int), cudaMemcpyDeviceToHost, s));
   cudaChk(cudaMemcpyAsync(&totals[3], pools.error, sizeof(int), cudaMemcpyDeviceToHost, s));
+  unsigned long long wide[3] = {0, 0, 0};
+  cudaChk(cudaMemcpyAsync(wide, ctl + 160, sizeof wide, cudaMemcpyDeviceToHost, s));
   cudaChk(cudaStreamSynchronize(s)); /* the list sizes decide the allocations below */
-  out->nCell = totals[0]; out->nSoft = totals[1]; out->nPart = totals[2]; out->error = totals[3];
+  out->nCell = (long long)wide[0]; out->nSoft = (long long)wide[1]; out->nPart = (long long)wide[2];
+  out->error = totals[3];
+  for (int k = 0; k < 3; ++k)
+    if (wide[k] > 0x7fffffffull) out->error = 3; /* 32-bit markers: walk a narrower bucket range */
   if (!out->error) {
     out->d_cell = (ILCell *)pool_alloc((size_t)(totals[0] > 0 ? totals[0] : 1) * sizeof(ILCell), s);
     out->d_soft = (ILCell *)pool_alloc((size_t)(totals[1] > 0 ? totals[1] : 1) * sizeof(ILCell), s);

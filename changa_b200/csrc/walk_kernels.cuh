@@ -354,6 +354,19 @@ emit_count_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists,
   }
 }
 
+/* 64-bit totals of the three count arrays: the markers are 32-bit (the ABI's ILCell lists are
+ * addressed by int markers), so a range whose lists exceed 2^31-1 entries must be refused */
+__global__ void walk_totals_kernel(const int *__restrict__ counts, int nb1, unsigned long long *__restrict__ totals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    unsigned long long v = i < nb1 ? (unsigned long long)counts[(size_t)k * nb1 + i] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(totals + k, v);
+  }
+}
+
 /* markers are exclusive prefix sums of the counts (numBuckets + 1 entries each) */
 __global__ void __launch_bounds__(kWalkWarps * 32)
 emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, WalkPools pools,

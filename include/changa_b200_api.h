@@ -232,7 +232,9 @@ void cb200_tree_free(cb200_tree *tree, void *stream);
  * cb200_build_moments; boxes are the tight bounding boxes.  Only buckets
  * [bucketLo, bucketHi) get lists (a rank's SFC share; the whole tree is the source).
  * Every array of the result lives in the stream-ordered pool; release it with
- * cb200_lists_free.  error != 0: a per-node capacity was exceeded (nothing usable). */
+ * cb200_lists_free.  error 1/2: a per-node or pool capacity was exceeded; error 3: a list of the
+ * range has more than 2^31-1 entries (the markers are int, like the ABI's): walk a narrower
+ * bucket range.  Nothing is usable when error != 0. */
 typedef struct cb200_lists {
   ILCell *d_cell, *d_soft, *d_part; /* cells | softened cells (index = node) | particles, expanded */
   int *d_cellMarkers, *d_softMarkers, *d_partMarkers; /* numBuckets+1 each; empty lists outside the range */

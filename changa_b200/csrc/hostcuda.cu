@@ -1023,10 +1023,16 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
 
   /* per-node list slices come from three pools sized from the tree (host walk: ~110 cell,
    * ~45 undecided, ~12 bucket entries per node); the error flag reports an overflow */
+  /* only nodes above the range's buckets are visited: a rank that walks 1/N of the buckets
+   * needs ~1/N of the pools (plus the shared top of the tree) */
+  const double frac = (double)(p.bucketHi > p.bucketLo ? p.bucketHi - p.bucketLo : 0) / (double)numBuckets;
+  unsigned long long visited = (unsigned long long)((double)numNodes * (frac * 1.25 < 1.0 ? frac * 1.25 : 1.0)) +
+                               65536ull + 4096ull * (unsigned long long)numLevels;
+  if (visited > (unsigned long long)numNodes) visited = (unsigned long long)numNodes;
   WalkPools pools;
-  pools.capC = (unsigned long long)numNodes * 256 + (1u << 16);
-  pools.capU = (unsigned long long)numNodes * 128 + (1u << 16);
-  pools.capL = (unsigned long long)numNodes * 64 + (1u << 16);
+  pools.capC = visited * 256 + (1u << 16);
+  pools.capU = visited * 128 + (1u << 16);
+  pools.capL = visited * 64 + (1u << 16);
   pools.clist = (WalkEntry *)pool_alloc(pools.capC * sizeof(WalkEntry), s);
   pools.lplist = (WalkEntry *)pool_alloc(pools.capL * sizeof(WalkEntry), s);
   pools.undlist = (WalkEntry *)pool_alloc(pools.capU * sizeof(WalkEntry), s);

@@ -173,18 +173,18 @@ class RawParticleStep:
         self.stream = self.ext.cuda_stream
         n = len(pos)
         self.n = n
-        rec = np.empty((n, 5))  # {x, y, z, mass, soft}: the record that crosses PCIe and NVLink
-        rec[:, :3] = pos
-        rec[:, 3] = mass
-        rec[:, 4] = soft
+        # {x, y, z, mass, soft}: the 40-byte record that crosses PCIe and NVLink; only this rank's rows
         self.chunk = -(-n // self.world)
         mine = np.zeros((self.chunk, 5))
         mine[:, 4] = 1.0
-        # pad rows (only when world does not divide n) sit at the far corner with zero mass;
-        # they never reach the tree: the gathered array is cut back to n rows
+        # pad rows (only when world does not divide n) never reach the tree: the gathered array is
+        # cut back to n rows
         lo_r = self.rank * self.chunk
         hi_r = min(n, lo_r + self.chunk)
-        mine[: max(0, hi_r - lo_r)] = rec[lo_r:hi_r]
+        k = max(0, hi_r - lo_r)
+        mine[:k, :3] = np.asarray(pos)[lo_r:hi_r]
+        mine[:k, 3] = np.broadcast_to(mass, (n,))[lo_r:hi_r]
+        mine[:k, 4] = np.broadcast_to(soft, (n,))[lo_r:hi_r]
         self.h = {"rec": torch.from_numpy(mine).pin_memory()}
         self.h2d_bytes = self.h["rec"].numel() * 8
         rows = n if self.world == 1 else 2 * self.chunk + 64
@@ -214,8 +214,9 @@ class RawParticleStep:
                             "pos": torch.empty((n, 3), dtype=torch.float64, device="cuda"),
                             "mass": torch.empty(n, dtype=torch.float64, device="cuda"),
                             "soft": torch.empty(n, dtype=torch.float64, device="cuda"),
-                            "vars": torch.empty((n, 5), dtype=torch.float32, device="cuda"),
-                            "out": torch.empty((n, 5), dtype=torch.float32, device="cuda")}
+                            "vars": torch.empty((n, 5), dtype=torch.float32, device="cuda")}
+                if self.world == 1:
+                    self.dev["out"] = torch.empty((n, 5), dtype=torch.float32, device="cuda")
             d = self.dev
             mark("start")
             d["rec"].copy_(self.h["rec"], non_blocking=True)

@@ -100,38 +100,41 @@ struct WalkPools {
   int *error;                           /* != 0: a capacity was exceeded */
 };
 
+/* Space::intersect(box, sphere) as the host walk states it (treewalk.cpp box_sphere; restated
+ * in-tree at CUDAMoments.cu:137-159), without its early exits: the distance only grows, so
+ * "rsq < dsq at some axis" and "dsq > rsq at the end" are the same answer; a zero term adds
+ * exactly 0.  Products and sums are rounded separately, like the host build (-ffp-contract=off). */
 __device__ __forceinline__ bool walk_box_sphere(const double *lo, const double *hi, const double *c, double r) {
-  double dsq = 0.0, delta;
-  const double rsq = r * r;
+  double dsq = 0.0;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    if ((delta = lo[d] - c[d]) > 0) dsq += delta * delta;
-    else if ((delta = c[d] - hi[d]) > 0) dsq += delta * delta;
-    if (rsq < dsq) return false;
+    const double delta = fmax(fmax(__dsub_rn(lo[d], c[d]), __dsub_rn(c[d], hi[d])), 0.0);
+    dsq = __dadd_rn(dsq, __dmul_rn(delta, delta));
   }
-  return dsq <= rsq;
+  return dsq <= __dmul_rn(r, r);
 }
 __device__ __forceinline__ bool walk_box_inside_sphere(const double *lo, const double *hi, const double *c, double r) {
   double s = 0.0;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double a = fabs(lo[d] - c[d]), b = fabs(hi[d] - c[d]);
-    const double w = a > b ? a : b;
-    s += w * w;
+    const double w = fmax(fabs(__dsub_rn(lo[d], c[d])), fabs(__dsub_rn(hi[d], c[d])));
+    s = __dadd_rn(s, __dmul_rn(w, w));
   }
-  return s <= r * r;
+  return s <= __dmul_rn(r, r);
 }
 __device__ __forceinline__ void walk_shifted_cm(const WalkNodeRec &m, int offsetID, double period, double *c) {
-  c[0] = m.cx + (((offsetID >> 22) & 7) - 3) * period;
-  c[1] = m.cy + (((offsetID >> 25) & 7) - 3) * period;
-  c[2] = m.cz + (((offsetID >> 28) & 7) - 3) * period;
+  c[0] = __dadd_rn(m.cx, __dmul_rn((double)(((offsetID >> 22) & 7) - 3), period));
+  c[1] = __dadd_rn(m.cy, __dmul_rn((double)(((offsetID >> 25) & 7) - 3), period));
+  c[2] = __dadd_rn(m.cz, __dmul_rn((double)(((offsetID >> 28) & 7) - 3), period));
 }
 /* gravity.h:251-260; mm: the local node */
 __device__ __forceinline__ bool walk_open_softening(const WalkNodeRec &m, const double *c, const WalkNodeRec &mm,
                                                     const double *mylo, const double *myhi) {
   const double rs = 2.0 * m.soft, rm = 2.0 * mm.soft;
-  const double dx = mm.cx - c[0], dy = mm.cy - c[1], dz = mm.cz - c[2];
-  if (dx * dx + dy * dy + dz * dz <= (rs + rm) * (rs + rm)) return true;
+  const double dx = __dsub_rn(mm.cx, c[0]), dy = __dsub_rn(mm.cy, c[1]), dz = __dsub_rn(mm.cz, c[2]);
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  const double rr = __dadd_rn(rs, rm);
+  if (d2 <= __dmul_rn(rr, rr)) return true;
   return walk_box_sphere(mylo, myhi, c, rs);
 }
 /* gravity.h:652-723: 1 open, -1 undecided, 0 accept */
@@ -140,7 +143,7 @@ __device__ __forceinline__ int walk_open_criterion(const WalkParams &p, const Wa
                                                    bool myIsBucket) {
   if (m.last - m.first + 1 <= 6) return 1;
   const double geom = 2.0 / sqrt(3.0);
-  double radius = geom * m.radius / p.theta;
+  double radius = __ddiv_rn(__dmul_rn(geom, m.radius), p.theta);
   if (radius < m.radius) radius = m.radius;
   double c[3];
   walk_shifted_cm(m, offsetID, p.period, c);
@@ -149,7 +152,7 @@ __device__ __forceinline__ int walk_open_criterion(const WalkParams &p, const Wa
     return walk_box_inside_sphere(lo, hi, c, radius) ? 1 : -1;
   }
   if (!walk_open_softening(m, c, mine, lo, hi)) return 0;
-  radius = geom * m.radius / p.thetaMono;
+  radius = __ddiv_rn(__dmul_rn(geom, m.radius), p.thetaMono);
   return walk_box_sphere(lo, hi, c, radius) ? 1 : 0;
 }
 
@@ -243,7 +246,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
            * bucket can see the cell softened: emit then skips the test and the 64-byte gather */
           double c[3];
           walk_shifted_cm(src, e.offsetID, p.period, c);
-          if (walk_box_sphere(mylo, myhi, c, 2.0 * src.soft + rmMax)) e.offsetID |= kWalkMaybeSoft;
+          if (walk_box_sphere(mylo, myhi, c, __dadd_rn(2.0 * src.soft, rmMax))) e.offsetID |= kWalkMaybeSoft;
         }
       }
       /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */

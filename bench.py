@@ -48,7 +48,8 @@ FLOP_EW_REAL, FLOP_EW_K = 350.0, 58.0
 
 
 def measured_peaks():
-    out = {"fp32_tflops": 71.64, "fp32_source": "fallback: tools/fp32_peak.cu FFMA run of round 1 (profiles/r01_fp32_peak.json)",
+    out = {"fp64_tflops": 36.98, "fp64_source": "fallback: DFMA run of round 1 (profiles/r01_fp32_peak.json)",
+           "fp32_tflops": 71.64, "fp32_source": "fallback: tools/fp32_peak.cu FFMA run of round 1 (profiles/r01_fp32_peak.json)",
            "hbm_gbs": 6650.0, "hbm_source": "fallback (B200_PROFILING.md)"}
     p = os.path.join(ROOT, "profiles", "r01_fp32_peak.json")
     if os.path.exists(p):
@@ -56,6 +57,8 @@ def measured_peaks():
             j = json.load(open(p))
             out["fp32_tflops"] = float(j["ffma_tflops"])
             out["fp32_source"] = "measured: tools/fp32_peak.cu scalar FFMA chains on this pool's B200 (profiles/r01_fp32_peak.json)"
+            out["fp64_tflops"] = float(j["dfma_tflops"])
+            out["fp64_source"] = "measured: tools/fp32_peak.cu DFMA chains on this pool's B200 (profiles/r01_fp32_peak.json)"
         except Exception:
             pass
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -175,7 +178,7 @@ class ResidentStep:
         L = hc.L
         self.stream = hc.stream_create()
         self.ext = torch.cuda.ExternalStream(self.stream)
-        f32 = np.float32
+        f32 = hc.np_real  # float32, or float64 under --double (the CUDA_USE_DOUBLE build)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.n, self.nn = len(wl["parts"]), len(wl["moments"])
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -199,7 +202,7 @@ class ResidentStep:
                 self.npk, self.nmk = self.raw_parts.shape[0], self.raw_mom.shape[0]
             self.pk_parts = torch.empty(self.npk * pb, dtype=torch.uint8, device=dev)
             self.pk_mom = torch.empty(self.nmk * mb, dtype=torch.uint8, device=dev)
-            self.vars = torch.zeros((self.n, 5), dtype=torch.float32, device=dev)
+            self.vars = torch.zeros((self.n, 5), dtype=torch.float64 if f32 == np.float64 else torch.float32, device=dev)
             self.lists = {}
             for key in ("cell", "part", "softcell"):
                 if wl.get(key) and len(wl[key][0]):
@@ -367,6 +370,8 @@ def main():
     ap.add_argument("--workload", default="cube300", choices=["cube300", "king", "uniform", "clustered"])
     ap.add_argument("--n", type=int, default=0, help="particles per GPU (default: the config's own size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--double", action="store_true",
+                    help="the CUDA_USE_DOUBLE build (cudatype = double): roofline against the measured DFMA peak")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 50)")
     ap.add_argument("--large-n", type=int, default=1 << 22,
                     help="particles of the extra box whose tree and lists are built on the device; "
@@ -402,7 +407,9 @@ def main():
             os.close(saved)
     from changa_b200.hostcuda import HostCUDA, ForceStep
     from changa_b200.workloads import config_workload, interaction_counts
-    hc = HostCUDA(double=False, device=local)
+    hc = HostCUDA(double=args.double, device=local)
+    if args.double:
+        args.large_n = 0  # the device-built-lists box is a float pipeline
 
     per_gpu = args.n or (48 ** 3 if args.workload == "cube300" else None)
     wl = config_workload(args.workload, n=per_gpu * world if per_gpu else None,
@@ -480,7 +487,7 @@ def main():
         line = {
             "metric": "gravity_interactions_per_s", "value": value, "unit": "interactions/s",
             "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.double else "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "particles_total": len(wl["parts"]), "particles_per_gpu": len(wl["parts"]) // world,
                        "theta": 0.7, "expansion": "hexadecapole", "bucket_size": 12,
                        "pc_pairs": g_pc, "pp_pairs": g_pp, "ewald_particles": g_ewn,
@@ -492,11 +499,14 @@ def main():
                         "pp_interactions_per_s": (cnt["part"] + cnt["softcell"]) / (pp_ms * 1e-3) if pp_ms else None,
                         "ewald_particles_per_s": ew_n / (ew_ms * 1e-3) if ew_ms else None,
                         "ewald_real_terms_per_particle": ew_real / max(ew_n, 1), "note": "rank 0, CUDA events around each launch"},
-            "roofline": {"bound": "fp32_fma", "kernel": "cell_list_kernel (p-c hexadecapole)", "achieved": pc_tflops,
-                         "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": pc_tflops / peaks["fp32_tflops"],
-                         "traffic": peaks["pc_traffic"] if args.workload == "cube300" and not args.n and world == 1 else None,
+            "roofline": {"bound": "fp64_fma" if args.double else "fp32_fma",
+                         "kernel": "cell_list_kernel (p-c hexadecapole, scalar FP64)" if args.double else "cell_list_x2_kernel (p-c hexadecapole, packed f32x2)",
+                         "achieved": pc_tflops,
+                         "peak": peaks["fp64_tflops" if args.double else "fp32_tflops"], "unit": "TFLOP/s",
+                         "frac": pc_tflops / peaks["fp64_tflops" if args.double else "fp32_tflops"],
+                         "traffic": peaks["pc_traffic"] if args.workload == "cube300" and not args.n and world == 1 and not args.double else None,
                          "traffic_source": peaks["pc_traffic_source"], "flop_per_pair": FLOP_PC, "achieved_ref170": pc_tflops * FLOP_PC_REF / FLOP_PC,
-                         "peak_source": peaks["fp32_source"],
+                         "peak_source": peaks["fp64_source" if args.double else "fp32_source"],
                          "hbm": {"algorithmic_bytes": pc_bytes, "achieved_gbs": pc_bytes / (pc_ms * 1e-3) / 1e9 if pc_ms else None,
                                  "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["hbm_source"]}},
             "e2e": {"value": g_pairs / (e2e_s / e2e_steps), "unit": "interactions/s", "ms_per_step": e2e_s / e2e_steps * 1e3,

@@ -227,11 +227,14 @@ class ResidentStep:
 
     def step(self):
         L, s = self.hc.L, self.stream
+        pending = None
         if self.world > 1:
-            L.cb200_pack_moments_device(self.my_mom.data_ptr(), self.send_m.data_ptr(), self.mc, s)
+            # particles first: Ewald needs nothing else, so the (larger) moment all-gather runs on
+            # NCCL's stream under the Ewald kernel and is waited for only in front of the p-c lists
             L.cb200_pack_particles_device(self.my_parts.data_ptr(), self.send_p.data_ptr(), self.pc, s)
-            self.dist.all_gather_into_tensor(self.pk_mom, self.send_m)
+            L.cb200_pack_moments_device(self.my_mom.data_ptr(), self.send_m.data_ptr(), self.mc, s)
             self.dist.all_gather_into_tensor(self.pk_parts, self.send_p)
+            pending = self.dist.all_gather_into_tensor(self.pk_mom, self.send_m, async_op=True)
         else:
             L.cb200_pack_moments_device(self.raw_mom.data_ptr(), self.pk_mom.data_ptr(), self.nmk, s)
             L.cb200_pack_particles_device(self.raw_parts.data_ptr(), self.pk_parts.data_ptr(), self.npk, s)
@@ -239,6 +242,8 @@ class ResidentStep:
         P, V, M = self.pk_parts.data_ptr(), self.vars.data_ptr(), self.pk_mom.data_ptr()
         if self.ew is not None:  # same order as ForceStep.run: Ewald needs only the particles
             L.cb200_ewald_device(P, V, self.ew_markers.data_ptr(), self.ew_n, self.ew.cachedData, self.ew.ewt, s)
+        if pending is not None:
+            pending.wait()  # stream-level: the step's stream waits for the moment all-gather
         if "cell" in self.lists:
             il, m, st, sz, nb, mx = self.lists["cell"]
             L.cb200_cell_list_device_ex(P, V, M, il.data_ptr(), m.data_ptr(), st.data_ptr(), sz.data_ptr(), nb,

@@ -29,3 +29,16 @@ def bucket_cuts_by_particles(bucket_sizes, world):
     cuts = np.searchsorted(csum, np.arange(1, world) * n / world, side="left") + 1
     cuts = np.concatenate([[0], np.minimum(cuts, len(bucket_sizes)), [len(bucket_sizes)]])
     return np.maximum.accumulate(cuts).astype(np.int64)
+
+
+def bucket_range_by_starts(bucket_starts, n, rank, world):
+    """what RawParticleStep does on the device with torch.searchsorted: rank r owns the buckets whose
+    first particle lies in [r n / world, (r+1) n / world) -- contiguous in SFC order, never splits a
+    bucket, at most one bucket of imbalance.  Returns (b0, b1, p0, p1): bucket and particle ranges."""
+    starts = np.asarray(bucket_starts)
+    nb = len(starts)
+    b0 = 0 if rank == 0 else int(np.searchsorted(starts, rank * n // world, side="left"))
+    b1 = nb if rank == world - 1 else int(np.searchsorted(starts, (rank + 1) * n // world, side="left"))
+    p0 = int(starts[b0]) if b0 < nb else n
+    p1 = int(starts[b1]) if b1 < nb else n
+    return b0, b1, p0, p1

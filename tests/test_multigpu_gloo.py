@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from changa_b200.multigpu import shard_rows, gather_rows, bucket_cuts_by_particles
+from changa_b200.multigpu import shard_rows, gather_rows, bucket_cuts_by_particles, bucket_range_by_starts
 
 
 def _free_port():
@@ -71,3 +71,19 @@ def test_shard_rows_and_cuts():
         assert cuts[0] == 0 and cuts[-1] == 1000 and len(cuts) == w + 1 and np.all(np.diff(cuts) > 0)
         loads = np.add.reduceat(sizes, cuts[:-1])
         assert loads.max() - loads.min() <= 24
+
+
+def test_bucket_ranges_by_starts_tile_the_box():
+    """the device driver's cut rule (RawParticleStep): ranges are contiguous, disjoint, cover every
+    bucket and particle, and differ by at most one bucket's particles from n / world"""
+    sizes = np.random.default_rng(2).integers(1, 13, 5000)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    n = int(sizes.sum())
+    for w in (1, 2, 3, 8):
+        r = [bucket_range_by_starts(starts, n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == len(sizes) and r[0][2] == 0 and r[-1][3] == n
+        for a, b in zip(r, r[1:]):
+            assert a[1] == b[0] and a[3] == b[2]
+        for b0, b1, p0, p1 in r:
+            assert p1 - p0 == int(sizes[b0:b1].sum())
+            assert abs((p1 - p0) - n / w) <= 12

@@ -430,7 +430,7 @@ __device__ __forceinline__ void pc_pair2(const float *__restrict__ c, float ccx,
   tx = fma2s(c[PK_XYYZ], yyz, tx); ty = fma2s(c[PK_YYYZ], yyz, ty); tz = fma2s(-c[PK_YYYY], yyz, tz);
   tx = fma2s(c[PK_XYYY], yyy, tx); ty = fma2s(c[PK_YYYY], yyy, ty); tz = fma2s(c[PK_YYYZ], yyy, tz);
   tz = fma2s(-c[PK_XXYY], add2(xxz, yyz), tz);
-  const f32x2 A4 = fma2(tz, Z, fma2(ty, Y, mul2(tx, X)));
+  const f32x2 t4x = tx, t4y = ty, t4z = tz;
 
   /* octupole: 5 + 5 + 5 terms */
   tx = fma2s(c[PK_XXX], xxm, tx); ty = fma2s(c[PK_XXY], xxm, ty); tz = fma2s(c[PK_XXZ], xxm, tz);
@@ -438,13 +438,16 @@ __device__ __forceinline__ void pc_pair2(const float *__restrict__ c, float ccx,
   tx = fma2s(c[PK_XXY], xy, tx); ty = fma2s(c[PK_XYY], xy, ty); tz = fma2s(c[PK_XYZ], xy, tz);
   tx = fma2s(c[PK_XYZ], yz, tx); ty = fma2s(c[PK_YYZ], yz, ty); tz = fma2s(c[PK_YZZ], yz, tz);
   tx = fma2s(c[PK_XYY], yym, tx); ty = fma2s(c[PK_YYY], yym, ty); tz = fma2s(c[PK_YYZ], yym, tz);
-  const f32x2 A34 = fma2(tz, Z, fma2(ty, Y, mul2(tx, X)));
+  const f32x2 t3x = tx, t3y = ty, t3z = tz;
 
   /* quadrupole: 3 + 3 + 3 terms */
   tx = fma2s(c[PK_XX], X, tx); ty = fma2s(c[PK_XY], X, ty); tz = fma2s(c[PK_XZ], X, tz);
   tx = fma2s(c[PK_XZ], Z, tx); ty = fma2s(c[PK_YZ], Z, ty); tz = fma2s(c[PK_ZZ], Z, tz);
   tx = fma2s(c[PK_XY], Y, tx); ty = fma2s(c[PK_YY], Y, ty); tz = fma2s(c[PK_YZ], Y, tz);
-  const f32x2 A234 = fma2(tz, Z, fma2(ty, Y, mul2(tx, X)));
+  /* the three projections side by side: X, then Y, then Z stays latched in its slot */
+  f32x2 A4 = mul2(t4x, X), A34 = mul2(t3x, X), A234 = mul2(tx, X);
+  A4 = fma2(t4y, Y, A4); A34 = fma2(t3y, Y, A34); A234 = fma2(ty, Y, A234);
+  A4 = fma2(t4z, Z, A4); A34 = fma2(t3z, Z, A34); A234 = fma2(tz, Z, A234);
 
   /* phi = M + s2/2 + s3/3 + s4/4;  G = M + 5/2 s2 + 7/3 s3 + 9/4 s4 = phi + 2 (s2+s3+s4) */
   const float M = c[PK_MASS];
@@ -453,9 +456,8 @@ __device__ __forceinline__ void pc_pair2(const float *__restrict__ c, float ccx,
   const f32x2 d3 = mul2(d2, d);
   pot = fma2(neg2(d), phi, pot);
   const f32x2 e = mul2s(c[PK_RADIUS], d3), g = neg2(mul2(G, d3));
-  ax = fma2(g, rx, fma2(e, tx, ax));
-  ay = fma2(g, ry, fma2(e, ty, ay));
-  az = fma2(g, rz, fma2(e, tz, az));
+  ax = fma2(e, tx, ax); ay = fma2(e, ty, ay); az = fma2(e, tz, az);
+  ax = fma2(g, rx, ax); ay = fma2(g, ry, ay); az = fma2(g, rz, az);
   float i0, i1;
   unpk2(mul2(add2(p.m, bc2(M)), d3), i0, i1);
   idt0 = fmaxf(idt0, i0);

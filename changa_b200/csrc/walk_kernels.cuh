@@ -415,15 +415,31 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
   }
   for (int k = 0; k < plen; ++k) { /* particle buckets, expanded per particle (Compute.cpp:1823-1863, 1174-1187) */
     const NodeLists nl = lists[path[k]];
-    for (int i = 0; i < nl.lLen; ++i) {
-      const WalkEntry e = pools.lplist[nl.lOff + i];
-      const int f = t.first[e.node], cnt = t.last[e.node] - f + 1;
-      for (int j = lane; j < cnt; j += 32) {
-        ILCell o;
-        o.index = f + j; o.offsetID = e.offsetID & kWalkOffsetMask; /* encodeOffset(0, x, y, z) */
-        partOut[wp + j] = o;
+    /* 32 source buckets at a time: every lane fetches one entry and its particle range, a warp
+     * scan places the ranges, then each lane writes its own <= bucket-size entries */
+    for (int i0 = 0; i0 < nl.lLen; i0 += 32) {
+      const int i = i0 + lane;
+      int f = 0, cnt = 0, code = 0;
+      if (i < nl.lLen) {
+        const WalkEntry e = pools.lplist[nl.lOff + i];
+        const WalkNodeRec &src = t.rec[e.node];
+        f = src.first;
+        cnt = src.last - f + 1;
+        code = e.offsetID & kWalkOffsetMask; /* encodeOffset(0, x, y, z) */
       }
-      wp += cnt;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      ILCell *dst = partOut + wp + (incl - cnt);
+      for (int j = 0; j < cnt; ++j) {
+        ILCell o;
+        o.index = f + j; o.offsetID = code;
+        dst[j] = o;
+      }
+      wp += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
 }

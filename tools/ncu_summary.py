@@ -42,7 +42,10 @@ def main():
     res = {"report": rep, "kernel": v[h.index("Kernel Name")] if "Kernel Name" in h else None, "stalls_per_issue": {}}
     for n, un, val in zip(h, u, v):
         if n in KEYS:
-            res[KEYS[n]] = to_bytes(val, un) if n.startswith("dram__bytes") else float(val.replace(",", ""))
+            x = to_bytes(val, un) if n.startswith("dram__bytes") else float(val.replace(",", ""))
+            if n == "gpu__time_duration.sum":
+                x *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(un, 1.0)
+            res[KEYS[n]] = x
         elif n.startswith(STALLS) and n.endswith("_per_issue_active.ratio"):
             x = float(val)
             if x >= 0.05:

@@ -459,3 +459,34 @@ def test_raw_particle_step_matches_oracle(hc):
         step.free()
     want = oracle_forces_tree(wl)  # sorted order
     compare(got[wl["order"]], want, median_tol=5e-6, max_tol=3e-4, pot_tol=2e-5, floor_frac=0.1)
+
+
+def test_clustered_box_device_path(hc):
+    """SURVEY config C4's recipe at a testable size (Plummer halos on a uniform background: 40-level
+    tree, softened cells, long lists): device tree == host tree, device lists == host lists, forces
+    from unsorted particles == forces through the host-built lists"""
+    from changa_b200.workloads import clustered_box
+    from changa_b200.device_step import RawParticleStep, DeviceTreeStep
+    from changa_b200.tree import Tree
+    pos, mass, soft = clustered_box(20000, seed=2, n_halos=12)
+    host = Tree(pos, mass, soft, max_bucket=12)
+    want = host.walk(theta=0.7, n_replicas=1, period=1.0)
+    ex, em = host.expand_part_list(want["part"], want["part_mark"])
+    assert len(want["soft"]) > 0 and host.num_levels > 25
+    dstep = DeviceTreeStep(hc, host, theta=0.7, n_replicas=1, period=1.0, ewald={})
+    rstep = RawParticleStep(hc, pos, mass, soft, theta=0.7, n_replicas=1, period=1.0, ewald={})
+    try:
+        a = dstep.run(keep_lists=True).copy()
+        dev = dstep.kept
+        b = rstep.run(keep_tree=True).copy()
+        tree = rstep.kept_tree
+    finally:
+        dstep.free()
+        rstep.free()
+    assert np.array_equal(dev["cell"], want["cell"]) and np.array_equal(dev["soft"], want["soft"])
+    assert np.array_equal(dev["part"], ex) and np.array_equal(dev["part_mark"], em.astype(np.int32))
+    assert np.array_equal(tree["order"], host.order) and np.array_equal(tree["child0"], host.child0)
+    assert np.array_equal(tree["boxlo"], host.boxlo) and np.array_equal(tree["bucket_node"], host.bucket_node)
+    # same lists, same kernels: the two drivers agree to the last bit once un-sorted
+    assert np.array_equal(b[host.order], a)
+    assert np.isfinite(a).all()

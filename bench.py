@@ -282,7 +282,7 @@ class ResidentStep:
         return sum(a.elapsed_time(b) for a, b in evs)  # ms over exactly `steps` steps
 
 
-def large_box_step(hc, n, torch, dist, rank, world, steps=3):
+def large_box_step(hc, n, torch, dist, rank, world, steps=3, kind="uniform"):
     """The same force step on a box that fills a GPU (uniform, SURVEY 8d recipe C3 at a size one
     default run can afford), from UNSORTED host particles: upload 40 B/particle, then keys, sort,
     tree, moments, double walk, p-c / p-p / Ewald all on the device, accelerations back in the
@@ -292,8 +292,8 @@ def large_box_step(hc, n, torch, dist, rank, world, steps=3):
     buckets.  Reported next to the headline numbers: kernel rates without the launch ramp and
     tail of the 110k-particle box."""
     from changa_b200.device_step import RawParticleStep
-    from changa_b200.workloads import uniform_box
-    pos, mass, soft = uniform_box(n, seed=1)
+    from changa_b200.workloads import uniform_box, clustered_box
+    pos, mass, soft = uniform_box(n, seed=1) if kind == "uniform" else clustered_box(n, seed=2)
     mass, soft = float(mass[0]), float(soft[0])  # equal-mass box: scalars (1/N, N^(-1/3)/20)
     st = RawParticleStep(hc, pos, mass, soft, theta=0.7, n_replicas=1, period=1.0,
                          ewald={"dEwCut": 2.6, "dEwhCut": 2.8}, max_bucket=12, dist=dist, rank=rank, world=world)
@@ -325,7 +325,7 @@ def large_box_step(hc, n, torch, dist, rank, world, steps=3):
     wall = float(agg[0])
     pc, pp, h2d, d2h, nrows = (float(x) for x in tot.tolist())
     pc_ms = taps["cell_ms"] / max(taps["cell_launches"], 1)
-    return {"workload": f"uniform(N={n},theta=0.7,nReplicas=1,bucket=12), tree and lists built on the device",
+    return {"workload": f"{kind}(N={n},theta=0.7,nReplicas=1,bucket=12), tree and lists built on the device",
             "scaling": "strong" if world > 1 else None, "n_gpus": world,
             "ms_per_step": wall * 1e3, "steps": steps, "interactions_per_s": (pc + pp) / wall,
             "nodes": info["nodes"], "buckets": info["buckets"], "pc_pairs": pc, "pp_pairs": pp, "result_rows": nrows,
@@ -378,6 +378,8 @@ def main():
     ap.add_argument("--double", action="store_true",
                     help="the CUDA_USE_DOUBLE build (cudatype = double): roofline against the measured DFMA peak")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 50)")
+    ap.add_argument("--large-kind", default="uniform", choices=["uniform", "clustered"],
+                    help="particle distribution of the extra box (SURVEY 8d recipes C3 / C4)")
     ap.add_argument("--large-n", type=int, default=1 << 22,
                     help="particles of the extra box whose tree and lists are built on the device; "
                          "shared by all ranks at N > 1 (0: skip)")
@@ -459,10 +461,10 @@ def main():
     large = None
     if args.large_n > 0:
         if world > 1:
-            large = large_box_step(hc, args.large_n, torch, dist, rank, world)
+            large = large_box_step(hc, args.large_n, torch, dist, rank, world, kind=args.large_kind)
         else:
             try:
-                large = large_box_step(hc, args.large_n, torch, dist, rank, world)
+                large = large_box_step(hc, args.large_n, torch, dist, rank, world, kind=args.large_kind)
             except Exception as e:  # extra information: never takes the headline line down
                 large = {"error": repr(e)}
 

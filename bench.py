@@ -491,6 +491,7 @@ def main():
         pc_bytes = len(il_c) * (8 + 128) + int(wl["cell"][3].sum()) * (32 + 40)  # list + packed-cell gather + targets
         pp_ms = taps["part_ms"] / max(taps["part_launches"], 1)
         ew_ms = taps["ewald_ms"] / max(taps["ewald_launches"], 1)
+        n_ewh = len(wl["ewald"]["ewt"]) if wl.get("ewald") else 0
         line = {
             "metric": "gravity_interactions_per_s", "value": value, "unit": "interactions/s",
             "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -505,7 +506,12 @@ def main():
                         "pc_interactions_per_s": cnt["cell"] / (pc_ms * 1e-3) if pc_ms else None,
                         "pp_interactions_per_s": (cnt["part"] + cnt["softcell"]) / (pp_ms * 1e-3) if pp_ms else None,
                         "ewald_particles_per_s": ew_n / (ew_ms * 1e-3) if ew_ms else None,
-                        "ewald_real_terms_per_particle": ew_real / max(ew_n, 1), "note": "rank 0, CUDA events around each launch"},
+                        "ewald_real_terms_per_particle": ew_real / max(ew_n, 1),
+                        # the other two kernels against the same FMA peak, by the stated conventions
+                        # (p-p 30 flop/pair; Ewald 350 per evaluated replica + 58 per h-vector)
+                        "pp_tflops": (cnt["part"] + cnt["softcell"]) * FLOP_PP / (pp_ms * 1e-3) / 1e12 if pp_ms else None,
+                        "ewald_tflops": (ew_real * FLOP_EW_REAL + ew_n * n_ewh * FLOP_EW_K) / (ew_ms * 1e-3) / 1e12 if ew_ms else None,
+                        "note": "rank 0, CUDA events around each launch"},
             "roofline": {"bound": "fp64_fma" if args.double else "fp32_fma",
                          "kernel": "cell_list_kernel (p-c hexadecapole, scalar FP64)" if args.double else "cell_list_x2_kernel (p-c hexadecapole, packed f32x2)",
                          "achieved": pc_tflops,

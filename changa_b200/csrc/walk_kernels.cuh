@@ -90,8 +90,14 @@ struct WalkParams {
 /* per-node results: slices of the three pools */
 struct NodeLists {
   int cOff, cLen, lOff, lLen, uOff, uLen;
-  int visited, pad;
+  int visited;
+  /* totals along the visited part of the path root -> this node: accepted cells, expanded
+   * particle entries, cells flagged maybe-softened.  A bucket's list sizes are its node's
+   * totals (minus the softened cells, which only flagged entries can be) */
+  int pathCells, pathParts, pathFlagged;
+  int pad0, pad1;
 };
+static_assert(sizeof(NodeLists) == 48, "NodeLists");
 
 struct WalkPools {
   WalkEntry *clist, *lplist, *undlist;
@@ -192,13 +198,17 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
 
   for (int w = warpGlobal; w < n; w += totalWarps) {
     const int my = lo + w;
-    NodeLists out = {0, 0, 0, 0, 0, 0, 0, 0};
+    NodeLists out = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int target = 0;
     bool go = walk_node_active(t, p, my, target);
     const int par = t.parent[my];
-    if (go && par >= 0) go = lists[par].visited && lists[par].uLen > 0; /* descend only under a non-empty undecided list */
+    if (par >= 0) {
+      const NodeLists up = lists[par];
+      if (go) go = up.visited && up.uLen > 0; /* descend only under a non-empty undecided list */
+      out.pathCells = up.pathCells; out.pathParts = up.pathParts; out.pathFlagged = up.pathFlagged;
+    }
     if (!go) {
-      if (lane == 0) lists[my] = out;
+      if (lane == 0) lists[my] = out; /* not visited: the path totals of the last visited ancestor */
       continue;
     }
     target &= kWalkBucketMask;
@@ -209,6 +219,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     for (int d = 0; d < 3; ++d) { mylo[d] = t.boxlo[3 * (size_t)my + d]; myhi[d] = t.boxhi[3 * (size_t)my + d]; }
     const double rmMax = 2.0 * __longlong_as_double((long long)*t.softMaxBits);
     int head = 0, tail = 0, nc = 0, nl = 0, nu = 0;
+    int myParts = 0, myFlagged = 0; /* per lane; summed over the warp at the end */
     /* initial checklist: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757) */
     if (par < 0) {
       const int side = 2 * p.nReplicas + 1, total = side * side * side;
@@ -246,7 +257,12 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
            * bucket can see the cell softened: emit then skips the test and the 64-byte gather */
           double c[3];
           walk_shifted_cm(src, e.offsetID, p.period, c);
-          if (walk_box_sphere(mylo, myhi, c, __dadd_rn(2.0 * src.soft, rmMax))) e.offsetID |= kWalkMaybeSoft;
+          if (walk_box_sphere(mylo, myhi, c, __dadd_rn(2.0 * src.soft, rmMax))) {
+            e.offsetID |= kWalkMaybeSoft;
+            ++myFlagged;
+          }
+        } else if (srcBucket) {
+          myParts += src.last - src.first + 1;
         }
       }
       /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */
@@ -291,8 +307,14 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     for (int i = lane; i < nc; i += 32) pools.clist[oc + i] = cl[i];
     for (int i = lane; i < nl; i += 32) pools.lplist[ol + i] = lp[i];
     for (int i = lane; i < nu; i += 32) pools.undlist[ou + i] = und[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      myParts += __shfl_xor_sync(0xffffffffu, myParts, o);
+      myFlagged += __shfl_xor_sync(0xffffffffu, myFlagged, o);
+    }
     out.cOff = (int)oc; out.cLen = nc; out.lOff = (int)ol; out.lLen = nl; out.uOff = (int)ou; out.uLen = nu;
     out.visited = 1;
+    out.pathCells += nc; out.pathParts += myParts; out.pathFlagged += myFlagged;
     if (lane == 0) lists[my] = out;
     __syncwarp();
   }
@@ -321,33 +343,30 @@ emit_count_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists,
   int cells = 0, soft = 0, part = 0;
   if (b >= p.bucketLo && b < p.bucketHi) {
     const int bn = t.bucketNode[b];
-    int path[64];
-    const int plen = walk_path(t, lists, bn, path);
-    const WalkNodeRec mm = t.rec[bn];
-    const double *lo = t.boxlo + 3 * (size_t)bn, *hi = t.boxhi + 3 * (size_t)bn;
-    for (int k = 0; k < plen; ++k) {
-      const NodeLists nl = lists[path[k]];
-      for (int i = lane; i < nl.cLen; i += 32) {
-        const WalkEntry e = pools.clist[nl.cOff + i];
-        bool isSoft = false;
-        if (e.offsetID & kWalkMaybeSoft) {
-          const WalkNodeRec m = t.rec[e.node];
-          double c[3];
-          walk_shifted_cm(m, e.offsetID, p.period, c);
-          isSoft = walk_open_softening(m, c, mm, lo, hi);
+    const NodeLists tot = lists[bn];
+    cells = tot.pathCells;
+    part = tot.pathParts;
+    if (tot.pathFlagged > 0) {
+      /* only flagged cells can be softened for this bucket: test them (gravity.h:251-260) */
+      int path[64];
+      const int plen = walk_path(t, lists, bn, path);
+      const WalkNodeRec mm = t.rec[bn];
+      const double *lo = t.boxlo + 3 * (size_t)bn, *hi = t.boxhi + 3 * (size_t)bn;
+      for (int k = 0; k < plen; ++k) {
+        const NodeLists nl = lists[path[k]];
+        for (int i = lane; i < nl.cLen; i += 32) {
+          const WalkEntry e = pools.clist[nl.cOff + i];
+          if (e.offsetID & kWalkMaybeSoft) {
+            const WalkNodeRec m = t.rec[e.node];
+            double c[3];
+            walk_shifted_cm(m, e.offsetID, p.period, c);
+            if (walk_open_softening(m, c, mm, lo, hi)) ++soft;
+          }
         }
-        if (isSoft) ++soft; else ++cells;
       }
-      for (int i = lane; i < nl.lLen; i += 32) {
-        const WalkNodeRec src = t.rec[pools.lplist[nl.lOff + i].node];
-        part += src.last - src.first + 1;
-      }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      cells += __shfl_xor_sync(0xffffffffu, cells, o);
-      soft += __shfl_xor_sync(0xffffffffu, soft, o);
-      part += __shfl_xor_sync(0xffffffffu, part, o);
+      for (int o = 16; o > 0; o >>= 1) soft += __shfl_xor_sync(0xffffffffu, soft, o);
+      cells -= soft;
     }
   }
   if (lane == 0) {

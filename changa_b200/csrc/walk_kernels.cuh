@@ -95,7 +95,8 @@ struct NodeLists {
    * particle entries, cells flagged maybe-softened.  A bucket's list sizes are its node's
    * totals (minus the softened cells, which only flagged entries can be) */
   int pathCells, pathParts, pathFlagged;
-  int pad0, pad1;
+  int ownParts; /* expanded particle entries of this node's own lplist */
+  int pad1;
 };
 static_assert(sizeof(NodeLists) == 48, "NodeLists");
 
@@ -315,6 +316,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     out.cOff = (int)oc; out.cLen = nc; out.lOff = (int)ol; out.lLen = nl; out.uOff = (int)ou; out.uLen = nu;
     out.visited = 1;
     out.pathCells += nc; out.pathParts += myParts; out.pathFlagged += myFlagged;
+    out.ownParts = myParts;
     if (lane == 0) lists[my] = out;
     __syncwarp();
   }
@@ -398,6 +400,50 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= t.numBuckets || b < p.bucketLo || b >= p.bucketHi) return;
   const int bn = t.bucketNode[b];
+  if (lists[bn].pathFlagged == 0) {
+    /* no cell on the path can be softened for any bucket: every level's entries go to a place the
+     * path totals name, so one climb bucket -> root (a single chain of parent links) does it all,
+     * cells (Compute.cpp:1653-1743) and particle buckets expanded per particle
+     * (Compute.cpp:1823-1863, 1174-1187) level by level */
+    const int cbase = cellMark[b], pbase = partMark[b];
+    for (int v = bn; v >= 0; v = t.parent[v]) {
+      const NodeLists nl = lists[v];
+      if (!nl.visited) continue;
+      ILCell *co = cellOut + cbase + (nl.pathCells - nl.cLen);
+      for (int i = lane; i < nl.cLen; i += 32) {
+        const WalkEntry e = pools.clist[nl.cOff + i];
+        ILCell o;
+        o.index = e.node; o.offsetID = e.offsetID;
+        co[i] = o;
+      }
+      int wp = pbase + (nl.pathParts - nl.ownParts);
+      for (int i0 = 0; i0 < nl.lLen; i0 += 32) {
+        const int i = i0 + lane;
+        int f = 0, cnt = 0, code = 0;
+        if (i < nl.lLen) {
+          const WalkEntry e = pools.lplist[nl.lOff + i];
+          const WalkNodeRec &src = t.rec[e.node];
+          f = src.first;
+          cnt = src.last - f + 1;
+          code = e.offsetID & kWalkOffsetMask; /* encodeOffset(0, x, y, z) */
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += u;
+        }
+        ILCell *dst = partOut + wp + (incl - cnt);
+        for (int j = 0; j < cnt; ++j) {
+          ILCell o;
+          o.index = f + j; o.offsetID = code;
+          dst[j] = o;
+        }
+        wp += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    return;
+  }
   int path[64];
   const int plen = walk_path(t, lists, bn, path);
   const WalkNodeRec mm = t.rec[bn];

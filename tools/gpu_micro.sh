@@ -1,7 +1,5 @@
 #!/bin/bash
-# microbenchmarks + quick bench (one GPU box visit)
-cd tools/bin
-echo "== rf_reuse_rates"; ./rf_reuse_rates
-echo "== ceiling old"; ./pc_pair_ceiling_old
-echo "== ceiling new"; ./pc_pair_ceiling
-cd ../..
+# compute ceiling of the packed p-c pair evaluation (build first:
+#   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr -Iinclude \
+#        -o tools/bin/pc_pair_ceiling tools/pc_pair_ceiling.cu)
+tools/bin/pc_pair_ceiling

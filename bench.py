@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cube300", choices=["cube300", "king", "uniform", "clustered"])
+    ap.add_argument("--workload", default="cube300", choices=["cube300", "king", "uniform", "clustered", "collapse"])
     ap.add_argument("--n", type=int, default=0, help="particles per GPU (default: the config's own size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--double", action="store_true",

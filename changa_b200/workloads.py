@@ -191,7 +191,20 @@ CONFIGS = {
     "king": dict(gen="plummer", n=36000, theta=0.7, n_replicas=0, ewald=False),
     "uniform": dict(gen="uniform", n=1 << 20, theta=0.7, n_replicas=1, ewald=True),
     "clustered": dict(gen="clustered", n=1 << 20, theta=0.7, n_replicas=1, ewald=True),
+    # config 5 (testcollapse/adiabtophat_glass_28721.bin: a uniform sphere at rest, gravity only,
+    # theta = 0.55, isolated; the reference runs it in double)
+    "collapse": dict(gen="tophat", n=28721, theta=0.55, n_replicas=0, ewald=False),
 }
+
+
+def tophat_sphere(n, seed=5, radius=0.5):
+    """stand-in for testcollapse/adiabtophat_glass_28721.bin: a homogeneous sphere of unit mass
+    (the fixture is a glass; a Poisson sphere has the same tree depth and list lengths)"""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = radius * rng.uniform(0, 1, n) ** (1.0 / 3.0)
+    return d * r[:, None], np.full(n, 1.0 / n), np.full(n, radius * n ** (-1.0 / 3.0) / 2.0)
 
 
 def plummer_sphere(n, seed=7, rs=2.0, soft=0.2):
@@ -219,6 +232,8 @@ def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_ran
         pos, mass, soft = uniform_box(n or cfg["n"], seed=seed or 1)
     elif cfg["gen"] == "clustered":
         pos, mass, soft = clustered_box(n or cfg["n"], seed=seed or 2)
+    elif cfg["gen"] == "tophat":
+        pos, mass, soft = tophat_sphere(n or cfg["n"], seed=seed or 5)
     else:
         pos, mass, soft = plummer_sphere(n or cfg["n"], seed=seed or 7, **(gen_kwargs or {}))
     root_lo, root_hi = (-0.5,) * 3, (0.5,) * 3

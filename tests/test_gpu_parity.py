@@ -205,6 +205,26 @@ def test_double_build_matches_oracle_to_1e6(hc64):
         assert med < 1e-9
 
 
+def test_collapse_config_in_double(hc64):
+    """config 5 (testcollapse: isolated homogeneous sphere, theta = 0.55, double precision):
+    full step through the C ABI of the CUDA_USE_DOUBLE build against the double CPU oracle"""
+    from changa_b200.hostcuda import ForceStep
+    from changa_b200.workloads import config_workload
+    wl = config_workload("collapse", n=5000)
+    assert wl["ewald"] is None and wl["fperiod"] == 0.0
+    step = ForceStep(hc64, wl)
+    try:
+        got = step.run().copy()
+    finally:
+        step.free()
+    med, worst = compare(got, oracle_forces_tree(wl, np.float64), median_tol=1e-9, max_tol=1e-6, pot_tol=1e-9,
+                         floor_frac=0.1)
+    assert med < 1e-9
+    # a sphere at rest falls towards its centre: accelerations point inwards
+    order_pos = wl["parts"][:, 2:5]
+    assert (np.einsum("ij,ij->i", got[:, :3], order_pos) < 0).mean() > 0.95
+
+
 def _upload(hc, wl):
     rt = hc.np_real
     n = len(wl["parts"])

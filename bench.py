@@ -7,10 +7,10 @@
 A "step" is one force evaluation of one synthetic box: (all-gather of particle and
 moment slices when N > 1) -> layout pack -> zero accumulators -> particle-cell lists
 (hexadecapole) -> particle-particle lists -> softened cells -> Ewald.  Default workload
-= BASELINE.json configs[1] (testcosmo cube300: 48^3 periodic box, theta 0.7, nReplicas 1,
-Ewald), a synthetic stand-in with the same N and clustering (the .tbin fixture stays in
-the reference tree).  At N GPUs the box holds N x 48^3 particles and every rank owns a
-contiguous SFC range of buckets (weak scaling).
+= BASELINE.json configs[1] (testcosmo cube300.tbin: 48^3 periodic box, theta 0.7, nReplicas 1,
+Ewald) on the reference's own particle set (positions committed under tests/golden/).  At N > 1
+GPUs the box holds N x 48^3 particles of a synthetic stand-in (a Zel'dovich-displaced grid) and
+every rank owns a contiguous SFC range of buckets (weak scaling).
 
   value   pair interactions (p-c + p-p, counted like Compute.cpp:1643-1651) per second of
           the whole step with raw inputs and lists already in HBM, CUDA-event timed on
@@ -337,13 +337,24 @@ def large_box_step(hc, n, torch, dist, rank, world, steps=3, kind="uniform"):
             "timing": "wall clock around RawParticleStep.run() (max over ranks); phases and kernels by CUDA events on rank 0's stream"}
 
 
+def workload_size(args, world):
+    """None = the config's own particle set (at N=1 the reference's Tipsy fixture, committed under
+    tests/golden/); at N > 1 the box grows with the GPU count (weak scaling), which only the
+    synthetic generators can do: cube300 then means the 48^3-per-GPU Zel'dovich stand-in"""
+    if args.n:
+        return args.n * world
+    if world > 1 and args.workload == "cube300":
+        return 48 ** 3 * world
+    return None
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port (kind "port": gravity.h / Ewald.cpp need Charm++ and do not
     compile here) with all host threads; rank 0 only."""
     if rank != 0:
         return
     from changa_b200.workloads import config_workload, interaction_counts
-    wl = config_workload(args.workload, n=args.n * world if args.n else (48 ** 3 * world if args.workload == "cube300" else None),
+    wl = config_workload(args.workload, n=workload_size(args, world),
                          bucket_range_of=(0, world) if world > 1 else None)
     cnt = interaction_counts(wl)
     pairs = cnt["cell"] + cnt["part"] + cnt["softcell"]
@@ -418,8 +429,7 @@ def main():
     if args.double:
         args.large_n = 0  # the device-built-lists box is a float pipeline
 
-    per_gpu = args.n or (48 ** 3 if args.workload == "cube300" else None)
-    wl = config_workload(args.workload, n=per_gpu * world if per_gpu else None,
+    wl = config_workload(args.workload, n=workload_size(args, world),
                          bucket_range_of=(rank, world) if world > 1 else None)
     cnt = interaction_counts(wl)
     pairs = cnt["cell"] + cnt["part"] + cnt["softcell"]

@@ -13,6 +13,8 @@ points after serialisation:
   ewald    None | {root (27), momc (32), ewt (nh,5), L, fEwCut, nReps, active}
 Arrays are float64 here; the C-ABI front end converts to cudatype on staging.
 """
+import os
+
 import numpy as np
 
 from .hostcuda import encode_offset
@@ -217,6 +219,27 @@ def plummer_sphere(n, seed=7, rs=2.0, soft=0.2):
     return d * r[:, None], np.full(n, 1.0 / n), np.full(n, soft)
 
 
+_FIXTURES = None
+
+
+def fixture_particles(name):
+    """(pos, mass, soft) of the reference's Tipsy fixture of a config (testcosmo/cube300.tbin,
+    teststep/king_soft.bin, testcollapse/adiabtophat_glass_28721.bin) from the committed
+    tests/golden/fixture_positions.npz, or None.  The periodic box is wrapped into [-0.5, 0.5)."""
+    global _FIXTURES
+    if _FIXTURES is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                            "fixture_positions.npz")
+        _FIXTURES = dict(np.load(path)) if os.path.exists(path) else {}
+    if name + "_pos" not in _FIXTURES:
+        return None
+    pos = _FIXTURES[name + "_pos"].astype(np.float64)
+    if name == "cube300":
+        pos = (pos + 0.5) % 1.0 - 0.5
+    n = len(pos)
+    return pos, np.full(n, float(_FIXTURES[name + "_mass"])), np.full(n, float(_FIXTURES[name + "_soft"]))
+
+
 def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_range_of=None, gen_kwargs=None,
                     **over):
     """Tree workload for one of BASELINE.json's configs.  bucket_range_of=(rank, world):
@@ -225,7 +248,13 @@ def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_ran
     from .tree import Tree, tree_workload
     cfg = dict(CONFIGS[name])
     cfg.update(over)
-    if cfg["gen"] == "cosmo":
+    fixture = fixture_particles(name) if (n is None and seed is None and not gen_kwargs) else None
+    label = name
+    if fixture is not None:
+        # the reference's own particle set for this config (tests/golden/fixture_positions.npz)
+        pos, mass, soft = fixture
+        label = {"cube300": "cube300.tbin", "king": "king_soft.bin", "collapse": "adiabtophat_glass_28721.bin"}[name]
+    elif cfg["gen"] == "cosmo":
         side = cfg["n_side"] if n is None else int(round(n ** (1.0 / 3.0)))
         pos, mass, soft = cosmo_box(side, seed=seed or 300)
     elif cfg["gen"] == "uniform":
@@ -249,6 +278,6 @@ def config_workload(name="cube300", n=None, seed=None, max_bucket=12, bucket_ran
         rng_b = (int(cuts[rank]), int(cuts[rank + 1]))
     wl = tree_workload(None, None, None, theta=cfg["theta"], n_replicas=cfg["n_replicas"], period=1.0,
                        ewald={} if cfg["ewald"] else None, bucket_range=rng_b, tree=t,
-                       name=f"{name}(N={t.n},theta={cfg['theta']},nReplicas={cfg['n_replicas']},bucket={max_bucket})")
+                       name=f"{label}(N={t.n},theta={cfg['theta']},nReplicas={cfg['n_replicas']},bucket={max_bucket})")
     wl["bucket_range"] = rng_b or (0, t.num_buckets)
     return wl

@@ -510,3 +510,46 @@ def test_clustered_box_device_path(hc):
     # same lists, same kernels: the two drivers agree to the last bit once un-sorted
     assert np.array_equal(b[host.order], a)
     assert np.isfinite(a).all()
+
+
+@pytest.mark.parametrize("name", ["cube300", "king"])
+def test_reference_fixture_configs(hc, name):
+    """BASELINE.json configs 1 and 2 on the reference's own particle sets (teststep/king_soft.bin,
+    testcosmo/cube300.tbin; positions from tests/golden/fixture_positions.npz): full step through the
+    C ABI against the double CPU oracle"""
+    from changa_b200.hostcuda import ForceStep
+    from changa_b200.workloads import config_workload, fixture_particles
+    if fixture_particles(name) is None:
+        pytest.skip("fixture positions not present")
+    wl = config_workload(name)
+    assert wl["name"].startswith({"cube300": "cube300.tbin", "king": "king_soft.bin"}[name])
+    step = ForceStep(hc, wl)
+    try:
+        got = step.run().copy()
+    finally:
+        step.free()
+    if name == "cube300":
+        # cube300.tbin is an almost uniform box: the net force on a particle is the small residue
+        # of nearly cancelling contributions, so float rounding weighs more against |a| than in a
+        # clustered box.  The bound is the north star's (median |da|/|a| <= 1e-4 in float).
+        med, worst = compare(got, oracle_forces_tree(wl), median_tol=1e-4, max_tol=2e-3, pot_tol=2e-5, floor_frac=0.1)
+        assert med < 5e-5
+    else:
+        compare(got, oracle_forces_tree(wl), median_tol=5e-6, max_tol=3e-4, pot_tol=2e-5, floor_frac=0.1)
+
+
+def test_collapse_fixture_in_double(hc64):
+    """config 5 on testcollapse/adiabtophat_glass_28721.bin, CUDA_USE_DOUBLE build"""
+    from changa_b200.hostcuda import ForceStep
+    from changa_b200.workloads import config_workload, fixture_particles
+    if fixture_particles("collapse") is None:
+        pytest.skip("fixture positions not present")
+    wl = config_workload("collapse")
+    step = ForceStep(hc64, wl)
+    try:
+        got = step.run().copy()
+    finally:
+        step.free()
+    med, worst = compare(got, oracle_forces_tree(wl, np.float64), median_tol=1e-9, max_tol=1e-6, pot_tol=1e-9,
+                         floor_frac=0.1)
+    assert med < 1e-9

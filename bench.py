@@ -282,7 +282,7 @@ class ResidentStep:
         return sum(a.elapsed_time(b) for a, b in evs)  # ms over exactly `steps` steps
 
 
-def large_box_step(hc, n, torch, dist, rank, world, steps=3, kind="uniform"):
+def large_box_step(hc, n, torch, dist, rank, world, steps=3, kind="uniform", active_rung=0):
     """The same force step on a box that fills a GPU (uniform, SURVEY 8d recipe C3 at a size one
     default run can afford), from UNSORTED host particles: upload 40 B/particle, then keys, sort,
     tree, moments, double walk, p-c / p-p / Ewald all on the device, accelerations back in the
@@ -295,8 +295,13 @@ def large_box_step(hc, n, torch, dist, rank, world, steps=3, kind="uniform"):
     from changa_b200.workloads import uniform_box, clustered_box
     pos, mass, soft = uniform_box(n, seed=1) if kind == "uniform" else clustered_box(n, seed=2)
     mass, soft = float(mass[0]), float(soft[0])  # equal-mass box: scalars (1/N, N^(-1/3)/20)
+    rung = None
+    if active_rung > 0:  # multistep force step: rungs by local density
+        from changa_b200.workloads import density_rungs
+        rung = density_rungs(pos)
     st = RawParticleStep(hc, pos, mass, soft, theta=0.7, n_replicas=1, period=1.0,
-                         ewald={"dEwCut": 2.6, "dEwhCut": 2.8}, max_bucket=12, dist=dist, rank=rank, world=world)
+                         ewald={"dEwCut": 2.6, "dEwhCut": 2.8}, max_bucket=12, dist=dist, rank=rank, world=world,
+                         rung=rung, active_rung=active_rung)
     del pos
     st.run(count_pairs=True)  # warm-up (pool growth); the markers give the pair counts
     info = dict(st.info)
@@ -316,6 +321,7 @@ def large_box_step(hc, n, torch, dist, rank, world, steps=3, kind="uniform"):
     hc.timing(False)
     h2d, d2h = st.h2d_bytes, st.d2h_bytes
     free_b, total_b = torch.cuda.mem_get_info()
+    st_active = {"active_" + k: v for k, v in getattr(st, "active", {}).items()}
     st.free()
     agg = torch.tensor([wall], dtype=torch.float64, device="cuda")
     tot = torch.tensor([info["pc_pairs"], info["pp_pairs"], h2d, d2h, len(rows)], dtype=torch.float64, device="cuda")
@@ -325,7 +331,9 @@ def large_box_step(hc, n, torch, dist, rank, world, steps=3, kind="uniform"):
     wall = float(agg[0])
     pc, pp, h2d, d2h, nrows = (float(x) for x in tot.tolist())
     pc_ms = taps["cell_ms"] / max(taps["cell_launches"], 1)
+    multistep = {"active_rung": active_rung, **st_active} if active_rung > 0 else None
     return {"workload": f"{kind}(N={n},theta=0.7,nReplicas=1,bucket=12), tree and lists built on the device",
+            "multistep": multistep,
             "scaling": "strong" if world > 1 else None, "n_gpus": world,
             "ms_per_step": wall * 1e3, "steps": steps, "interactions_per_s": (pc + pp) / wall,
             "nodes": info["nodes"], "buckets": info["buckets"], "pc_pairs": pc, "pp_pairs": pp, "result_rows": nrows,
@@ -394,6 +402,9 @@ def main():
     ap.add_argument("--large-n", type=int, default=1 << 22,
                     help="particles of the extra box whose tree and lists are built on the device; "
                          "shared by all ranks at N > 1 (0: skip)")
+    ap.add_argument("--large-active-rung", type=int, default=0,
+                    help="> 0: the extra box runs a multistep force step at this activeRung (rungs by local "
+                         "density, SURVEY C4): active-bucket lists + Ewald markers made on the device")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -471,10 +482,12 @@ def main():
     large = None
     if args.large_n > 0:
         if world > 1:
-            large = large_box_step(hc, args.large_n, torch, dist, rank, world, kind=args.large_kind)
+            large = large_box_step(hc, args.large_n, torch, dist, rank, world, kind=args.large_kind,
+                                       active_rung=args.large_active_rung)
         else:
             try:
-                large = large_box_step(hc, args.large_n, torch, dist, rank, world, kind=args.large_kind)
+                large = large_box_step(hc, args.large_n, torch, dist, rank, world, kind=args.large_kind,
+                                       active_rung=args.large_active_rung)
             except Exception as e:  # extra information: never takes the headline line down
                 large = {"error": repr(e)}
 

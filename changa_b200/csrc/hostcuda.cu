@@ -36,6 +36,9 @@
 #include "tree_kernels.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/reverse_iterator.h>
 
 #ifdef CB200_WITH_CHARM_HAPI
 #include "hapi.h"
@@ -1005,6 +1008,22 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
                        const int *d_bucketCount, const int *d_bucketNode, const double *d_boxlo_xyz,
                        const double *d_boxhi_xyz, const double *d_moments_f64, double theta, int nReplicas,
                        double period, int bucketLo, int bucketHi, cb200_lists *out, void *stream) {
+  cb200_walk_device_active(numNodes, numBuckets, numLevels, h_levelStart, d_child0, d_child1, d_parent, d_firstPart,
+                           d_lastPart, d_bucketFirst, d_bucketCount, d_bucketNode, d_boxlo_xyz, d_boxhi_xyz,
+                           d_moments_f64, theta, nReplicas, period, bucketLo, bucketHi, nullptr, out, stream);
+}
+
+struct MinOp {
+  __host__ __device__ int operator()(int a, int b) const { return a < b ? a : b; }
+};
+
+void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const int *h_levelStart,
+                              const int *d_child0, const int *d_child1, const int *d_parent,
+                              const int *d_firstPart, const int *d_lastPart, const int *d_bucketFirst,
+                              const int *d_bucketCount, const int *d_bucketNode, const double *d_boxlo_xyz,
+                              const double *d_boxhi_xyz, const double *d_moments_f64, double theta, int nReplicas,
+                              double period, int bucketLo, int bucketHi, const unsigned char *d_bucketActive,
+                              cb200_lists *out, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   memset(out, 0, sizeof *out);
   out->numBuckets = numBuckets;
@@ -1020,6 +1039,24 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
   p.period = period; p.nReplicas = nReplicas;
   p.bucketLo = bucketLo < 0 ? 0 : bucketLo;
   p.bucketHi = bucketHi > numBuckets ? numBuckets : bucketHi;
+  p.nextActive = nullptr;
+  int *nextActive = nullptr, *activeIdx = nullptr;
+  void *scanTmp = nullptr;
+  if (d_bucketActive) { /* multistep: only buckets with rungs >= activeRung are walked */
+    const int n1 = numBuckets + 1;
+    activeIdx = (int *)pool_alloc((size_t)n1 * sizeof(int), s);
+    nextActive = (int *)pool_alloc((size_t)n1 * sizeof(int), s);
+    walk_active_index_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(d_bucketActive, numBuckets, activeIdx);
+    cudaChk(cudaPeekAtLastError());
+    auto in = thrust::make_reverse_iterator(activeIdx + n1);
+    auto outIt = thrust::make_reverse_iterator(nextActive + n1);
+    size_t bytes = 0;
+    cudaChk(cub::DeviceScan::InclusiveScan(nullptr, bytes, in, outIt, MinOp(), n1, s));
+    scanTmp = pool_alloc(bytes, s);
+    cudaChk(cub::DeviceScan::InclusiveScan(scanTmp, bytes, in, outIt, MinOp(), n1, s));
+    g_launches.fetch_add(2);
+    p.nextActive = nextActive;
+  }
 
   /* per-node list slices come from three pools sized from the tree (host walk: ~110 cell,
    * ~45 undecided, ~12 bucket entries per node); the error flag reports an overflow */
@@ -1105,8 +1142,33 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
     g_launches.fetch_add(3);
   }
   pool_free(tmp, s); pool_free(counts, s); pool_free(scratch, s); pool_free(lists, s); pool_free(ctl, s);
-  pool_free(rec, s);
+  pool_free(rec, s); pool_free(scanTmp, s); pool_free(activeIdx, s); pool_free(nextActive, s);
   pool_free(pools.clist, s); pool_free(pools.lplist, s); pool_free(pools.undlist, s);
+}
+
+void cb200_active_sets_device(const unsigned char *d_rung, const int *d_order, int numParticles,
+                              const int *d_bucketStarts, const int *d_bucketSizes, int numBuckets, int activeRung,
+                              unsigned char *d_bucketActive, int *d_ewaldMarkers, int *h_counts, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  h_counts[0] = h_counts[1] = 0;
+  if (numParticles <= 0 || numBuckets <= 0) return;
+  unsigned char *flags = (unsigned char *)pool_alloc((size_t)numParticles, s);
+  int *ctl = (int *)pool_alloc(256, s);
+  cudaChk(cudaMemsetAsync(ctl, 0, 256, s));
+  active_particle_flags_kernel<<<(numParticles + 255) / 256, 256, 0, s>>>(d_rung, d_order, numParticles, activeRung, flags);
+  cudaChk(cudaPeekAtLastError());
+  active_bucket_flags_kernel<<<(numBuckets + 255) / 256, 256, 0, s>>>(flags, d_bucketStarts, d_bucketSizes, numBuckets,
+                                                                     d_bucketActive, ctl);
+  cudaChk(cudaPeekAtLastError());
+  thrust::counting_iterator<int> idx(0);
+  size_t bytes = 0;
+  cudaChk(cub::DeviceSelect::Flagged(nullptr, bytes, idx, flags, d_ewaldMarkers, ctl + 1, numParticles, s));
+  void *tmp = pool_alloc(bytes, s);
+  cudaChk(cub::DeviceSelect::Flagged(tmp, bytes, idx, flags, d_ewaldMarkers, ctl + 1, numParticles, s));
+  g_launches.fetch_add(3);
+  cudaChk(cudaMemcpyAsync(h_counts, ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaStreamSynchronize(s)); /* the caller sizes the Ewald launch by the count */
+  pool_free(tmp, s); pool_free(flags, s); pool_free(ctl, s);
 }
 
 void cb200_lists_free(cb200_lists *l, void *stream) {

@@ -85,6 +85,9 @@ __global__ void walk_pack_nodes_kernel(WalkTree t, WalkNodeRec *__restrict__ out
 struct WalkParams {
   double theta, thetaMono, period;
   int nReplicas, bucketLo, bucketHi;
+  /* multistep (bucketList[b]->rungs >= activeRung, Compute.cpp:1278,1574): nextActive[b] = smallest
+   * active bucket >= b (numBuckets when there is none), numBuckets + 1 entries; NULL = every bucket */
+  const int *nextActive;
 };
 
 /* per-node results: slices of the three pools */
@@ -163,12 +166,25 @@ __device__ __forceinline__ int walk_open_criterion(const WalkParams &p, const Wa
   return walk_box_sphere(lo, hi, c, radius) ? 1 : 0;
 }
 
-/* active buckets of a node under the [bucketLo, bucketHi) restriction */
+/* active buckets of a node under the [bucketLo, bucketHi) restriction and the active mask;
+ * firstActive is the walk's target bucket (treewalk.cpp firstActive[]) */
 __device__ __forceinline__ bool walk_node_active(const WalkTree &t, const WalkParams &p, int node, int &firstActive) {
   const int b0 = t.bucketFirst[node], b1 = b0 + t.bucketCount[node];
-  const int lo = b0 > p.bucketLo ? b0 : p.bucketLo, hi = b1 < p.bucketHi ? b1 : p.bucketHi;
+  int lo = b0 > p.bucketLo ? b0 : p.bucketLo;
+  const int hi = b1 < p.bucketHi ? b1 : p.bucketHi;
+  if (p.nextActive && lo < hi) lo = p.nextActive[lo];
   firstActive = lo;
   return lo < hi;
+}
+__device__ __forceinline__ bool walk_bucket_active(const WalkParams &p, int b) {
+  return b >= p.bucketLo && b < p.bucketHi && (!p.nextActive || p.nextActive[b] == b);
+}
+
+/* nextActive from the per-bucket flags: own index where active, numBuckets elsewhere (and at the
+ * end); a suffix minimum (cub, reversed) finishes it */
+__global__ void walk_active_index_kernel(const unsigned char *__restrict__ active, int nb, int *__restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= nb) out[b] = (b < nb && active[b]) ? b : nb;
 }
 
 /* ordered append of the lanes whose flag is set */
@@ -343,7 +359,7 @@ emit_count_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists,
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= t.numBuckets) return;
   int cells = 0, soft = 0, part = 0;
-  if (b >= p.bucketLo && b < p.bucketHi) {
+  if (walk_bucket_active(p, b)) {
     const int bn = t.bucketNode[b];
     const NodeLists tot = lists[bn];
     cells = tot.pathCells;
@@ -398,7 +414,7 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
                  ILCell *__restrict__ cellOut, ILCell *__restrict__ softOut, ILCell *__restrict__ partOut) {
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= t.numBuckets || b < p.bucketLo || b >= p.bucketHi) return;
+  if (b >= t.numBuckets || !walk_bucket_active(p, b)) return;
   const int bn = t.bucketNode[b];
   if (lists[bn].pathFlagged == 0) {
     /* no cell on the path can be softened for any bucket: every level's entries go to a place the
@@ -507,6 +523,28 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
       wp += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
+}
+
+/* multistep sets.  flags[i] = particle i (tree order) has rung >= activeRung (the Ewald markers
+ * are the indices of the set flags, Ewald.cpp:416-437); a bucket is active when any of its
+ * particles is (GenericTreeNode::rungs is the maximum below the node; Compute.cpp:1278) */
+__global__ void active_particle_flags_kernel(const unsigned char *__restrict__ rung, const int *__restrict__ order,
+                                             int n, int activeRung, unsigned char *__restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = rung[order ? order[i] : i] >= activeRung;
+}
+__global__ void active_bucket_flags_kernel(const unsigned char *__restrict__ flags, const int *__restrict__ starts,
+                                           const int *__restrict__ sizes, int nb, unsigned char *__restrict__ active,
+                                           int *__restrict__ nActive) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  bool a = false;
+  if (b < nb) {
+    const int f = starts[b], c = sizes[b];
+    for (int j = 0; j < c; ++j) a = a || flags[f + j];
+    active[b] = a;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, a);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(nActive, __popc(m));
 }
 
 /* softened cells as ad-hoc source particles: every node as {cm, M | soft} */

@@ -9,8 +9,10 @@ import numpy as np
 
 
 class DeviceTreeStep:
-    def __init__(self, hc, tree, theta=0.7, n_replicas=0, period=1.0, ewald=None, bucket_range=None):
-        """tree: changa_b200.tree.Tree (host-built topology).  ewald: None | dict(dEwCut, dEwhCut)."""
+    def __init__(self, hc, tree, theta=0.7, n_replicas=0, period=1.0, ewald=None, bucket_range=None,
+                 rung=None, active_rung=0):
+        """tree: changa_b200.tree.Tree (host-built topology).  ewald: None | dict(dEwCut, dEwhCut).
+        rung (one byte per particle, TREE order) + active_rung: multistep step, see RawParticleStep."""
         import torch
         self.torch, self.hc, self.t = torch, hc, tree
         self.theta, self.nrep, self.period = float(theta), int(n_replicas), float(period)
@@ -29,6 +31,11 @@ class DeviceTreeStep:
             "boxlo": pin(t.boxlo), "boxhi": pin(t.boxhi),
             "parts32": pin(t.parts.astype(np.float32)),
         }
+        self.active_rung = int(active_rung)
+        if rung is not None:
+            self.h["rung"] = pin(np.asarray(rung, dtype=np.uint8))
+            self.h["bstarts"] = pin(np.asarray(t.bucket_starts, dtype=np.int32))
+            self.h["bsizes"] = pin(np.asarray(t.bucket_sizes, dtype=np.int32))
         self.level_start = np.ascontiguousarray(t.level_start, dtype=np.int32)
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.h.values())
         self.out = torch.zeros((t.n, 5), dtype=torch.float32).pin_memory()
@@ -70,12 +77,23 @@ class DeviceTreeStep:
                                   t.num_levels, nn, mom32.data_ptr(), mom64.data_ptr(), s)
             mark("moments")
             lists = hc.T.Lists()
-            L.cb200_walk_device(nn, nb, t.num_levels, self.level_start.ctypes.data, d["child0"].data_ptr(),
-                                d["child1"].data_ptr(), d["parent"].data_ptr(), d["first"].data_ptr(),
-                                d["last"].data_ptr(), d["bfirst"].data_ptr(), d["bcount"].data_ptr(),
-                                d["bnode"].data_ptr(), d["boxlo"].data_ptr(), d["boxhi"].data_ptr(),
-                                mom64.data_ptr(), self.theta, self.nrep, self.period, self.range[0], self.range[1],
-                                C.byref(lists), s)
+            active_ptr, self.n_act = None, n
+            if "rung" in self.h:
+                if "bucket_active" not in d:
+                    d["bucket_active"] = torch.empty(nb, dtype=torch.uint8, device="cuda")
+                    d["markers"] = torch.empty(n, dtype=torch.int32, device="cuda")
+                counts = (C.c_int * 2)()
+                L.cb200_active_sets_device(d["rung"].data_ptr(), None, n, d["bstarts"].data_ptr(),
+                                           d["bsizes"].data_ptr(), nb, self.active_rung,
+                                           d["bucket_active"].data_ptr(), d["markers"].data_ptr(), counts, s)
+                active_ptr, self.n_act = d["bucket_active"].data_ptr(), int(counts[1])
+                self.active = {"buckets": int(counts[0]), "particles": self.n_act}
+            L.cb200_walk_device_active(nn, nb, t.num_levels, self.level_start.ctypes.data, d["child0"].data_ptr(),
+                                       d["child1"].data_ptr(), d["parent"].data_ptr(), d["first"].data_ptr(),
+                                       d["last"].data_ptr(), d["bfirst"].data_ptr(), d["bcount"].data_ptr(),
+                                       d["bnode"].data_ptr(), d["boxlo"].data_ptr(), d["boxhi"].data_ptr(),
+                                       mom64.data_ptr(), self.theta, self.nrep, self.period, self.range[0],
+                                       self.range[1], active_ptr, C.byref(lists), s)
             mark("walk")
             if lists.error:
                 raise RuntimeError(f"device walk: per-node capacity exceeded (error {lists.error})")
@@ -123,6 +141,13 @@ class DeviceTreeStep:
             self._ew = hc.EwaldHostMemorySetup(1, len(ewt), 0)
         hc.fill_ewald(self._ew, root, momc, ewt, self.period, float(self.ewald.get("dEwCut", 2.6)), self.nrep,
                       active=None, first=first, last=last)
+        if "rung" in self.h:  # large-phase form: device markers of my particle range
+            torch = self.torch
+            mk = self.dev["markers"][:self.n_act]
+            i0, i1 = torch.searchsorted(mk, torch.tensor([first, last + 1], dtype=torch.int32, device="cuda")).tolist()
+            if i1 > i0:
+                hc.L.cb200_ewald_device(P, V, mk.data_ptr() + 4 * i0, i1 - i0, self._ew.cachedData, self._ew.ewt, s)
+            return
         # small-phase form: a contiguous particle range, no marker array
         hc.L.cb200_EwaldHost(P, V, C.byref(self._ew), s, None, 0, 0)
 
@@ -156,8 +181,15 @@ class RawParticleStep:
     cb200_walk_device, cb200_*_list_device_ex, cb200_EwaldHost)."""
 
     def __init__(self, hc, pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, ewald=None, max_bucket=12,
-                 root_lo=(-0.5, -0.5, -0.5), root_hi=(0.5, 0.5, 0.5), dist=None, rank=0, world=1):
-        """world > 1 (one process per GPU, torch.distributed `dist`): every rank holds rows
+                 root_lo=(-0.5, -0.5, -0.5), root_hi=(0.5, 0.5, 0.5), dist=None, rank=0, world=1,
+                 rung=None, active_rung=0):
+        """rung (one byte per particle, caller order) + active_rung: a multistep force step
+         -- only buckets holding a particle with rung >= active_rung get lists and
+        forces (Compute.cpp:1278,1574), only particles with rung >= active_rung get the Ewald sum
+        (Ewald.cpp:416-437); the sets are made on the device (cb200_active_sets_device) and the
+        walk is cb200_walk_device_active.  Rows of inactive buckets come back zero.
+
+        world > 1 (one process per GPU, torch.distributed `dist`): every rank holds rows
         [rank*chunk, (rank+1)*chunk) of the particle set on its host; ONE all-gather per step
         replicates the 40-byte records, every rank builds the same tree and moments, then walks,
         evaluates and returns only its own contiguous SFC range of buckets (equal particle counts;
@@ -187,6 +219,12 @@ class RawParticleStep:
         mine[:k, 4] = np.broadcast_to(soft, (n,))[lo_r:hi_r]
         self.h = {"rec": torch.from_numpy(mine).pin_memory()}
         self.h2d_bytes = self.h["rec"].numel() * 8
+        self.active_rung = int(active_rung)
+        if rung is not None:
+            r = np.zeros(self.chunk, dtype=np.uint8)
+            r[:k] = np.asarray(rung, dtype=np.uint8)[lo_r:hi_r]
+            self.h["rung"] = torch.from_numpy(r).pin_memory()
+            self.h2d_bytes += self.chunk
         rows = n if self.world == 1 else 2 * self.chunk + 64
         self.out = torch.zeros((rows, 5), dtype=torch.float32).pin_memory()
         self.out_idx = torch.zeros(rows, dtype=torch.int32).pin_memory()
@@ -218,14 +256,25 @@ class RawParticleStep:
                 if self.world == 1:
                     self.dev["out"] = torch.empty((n, 5), dtype=torch.float32, device="cuda")
             d = self.dev
+            multistep = "rung" in self.h
+            if multistep and "rung" not in d:
+                d["rung"] = torch.empty_like(self.h["rung"], device="cuda")
+                d["rung_all"] = torch.empty(self.chunk * self.world, dtype=torch.uint8, device="cuda")
+                d["markers"] = torch.empty(n, dtype=torch.int32, device="cuda")
             mark("start")
             d["rec"].copy_(self.h["rec"], non_blocking=True)
+            if multistep:
+                d["rung"].copy_(self.h["rung"], non_blocking=True)
             mark("h2d")
             if self.world > 1:
                 self.dist.all_gather_into_tensor(d["all"], d["rec"])
                 full = d["all"]
+                if multistep:
+                    self.dist.all_gather_into_tensor(d["rung_all"], d["rung"])
             else:
                 full = d["rec"]
+                if multistep:
+                    d["rung_all"] = d["rung"]
             d["pos"].copy_(full[:n, :3])
             d["mass"].copy_(full[:n, 3])
             d["soft"].copy_(full[:n, 4])
@@ -250,11 +299,26 @@ class RawParticleStep:
                                   mom32.data_ptr(), mom64.data_ptr(), s)
             mark("moments")
             b0, b1, p0, p1 = 0, nb, 0, n
+            active_ptr, n_act = None, n
+            if multistep:
+                if d.get("nb") != nb:
+                    d["bucket_active"] = torch.empty(nb, dtype=torch.uint8, device="cuda")
+                    d["nb"] = nb
+                counts = (C.c_int * 2)()
+                L.cb200_active_sets_device(d["rung_all"].data_ptr(), tr.d_order, n, tr.d_bucketStarts,
+                                           tr.d_bucketSizes, nb, self.active_rung, d["bucket_active"].data_ptr(),
+                                           d["markers"].data_ptr(), counts, s)
+                active_ptr, n_act = d["bucket_active"].data_ptr(), int(counts[1])
+                self.active = {"buckets": int(counts[0]), "particles": n_act}
             if self.world > 1:  # my contiguous SFC range of buckets: equal particle counts, never splits a bucket
                 starts = torch.empty(nb, dtype=torch.int32, device="cuda")
                 L.cb200_copy_device(starts.data_ptr(), tr.d_bucketStarts, nb * 4, s)
                 want = torch.tensor([self.rank * n // self.world, (self.rank + 1) * n // self.world],
                                     dtype=torch.int32, device="cuda")
+                if multistep and n_act > 0:  # equal ACTIVE particle counts
+                    at = [min(n_act - 1, self.rank * n_act // self.world),
+                          min(n_act - 1, (self.rank + 1) * n_act // self.world)]
+                    want = d["markers"][at]
                 cut = torch.searchsorted(starts, want, right=False).tolist()
                 b0 = 0 if self.rank == 0 else int(cut[0])
                 b1 = nb if self.rank == self.world - 1 else int(cut[1])
@@ -263,10 +327,10 @@ class RawParticleStep:
                 p1 = int(edge[1]) if b1 < nb else n
             self.range = (b0, b1, p0, p1)
             lists = hc.T.Lists()
-            L.cb200_walk_device(nn, nb, tr.numLevels, lvl, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first,
-                                tr.d_last, tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo,
-                                tr.d_boxhi, mom64.data_ptr(), self.theta, self.nrep, self.period, b0, b1,
-                                C.byref(lists), s)
+            L.cb200_walk_device_active(nn, nb, tr.numLevels, lvl, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first,
+                                       tr.d_last, tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo,
+                                       tr.d_boxhi, mom64.data_ptr(), self.theta, self.nrep, self.period, b0, b1,
+                                       active_ptr, C.byref(lists), s)
             if lists.error:
                 raise RuntimeError(f"device walk: per-node capacity exceeded (error {lists.error})")
             mark("walk")
@@ -286,7 +350,14 @@ class RawParticleStep:
                 if p1 > p0:
                     hc.fill_ewald(self._ew, root, momc, ewt, self.period, float(self.ewald.get("dEwCut", 2.6)),
                                   self.nrep, active=None, first=p0, last=p1 - 1)
-                    L.cb200_EwaldHost(P, V, C.byref(self._ew), s, None, 0, 0)
+                    if multistep:  # large-phase form: the markers of my particle range, already on the device
+                        mk = d["markers"][:n_act]
+                        i0, i1 = torch.searchsorted(mk, torch.tensor([p0, p1], dtype=torch.int32, device="cuda")).tolist()
+                        if i1 > i0:
+                            L.cb200_ewald_device(P, V, mk.data_ptr() + 4 * i0, i1 - i0, self._ew.cachedData,
+                                                 self._ew.ewt, s)
+                    else:
+                        L.cb200_EwaldHost(P, V, C.byref(self._ew), s, None, 0, 0)
             mark("ewald")
             mx = self.max_bucket
             L.cb200_cell_list_device_ex(P, V, M, lists.d_cell, lists.d_cellMarkers, lists.d_starts, lists.d_sizes,

@@ -122,6 +122,7 @@ C_ABI_SYMBOLS = [
     "cb200_pack_moments_device", "cb200_pack_particles_device", "cb200_zero_vars_device", "cb200_copy_device",
     "cb200_timing_enable", "cb200_timing_reset", "cb200_timing_read", "cb200_kernel_launches",
     "cb200_build_moments", "cb200_partition_buckets", "cb200_walk_device", "cb200_lists_free",
+    "cb200_walk_device_active", "cb200_active_sets_device",
     "cb200_build_tree", "cb200_tree_free",
 ]
 
@@ -191,6 +192,9 @@ def load(double=False):
     L.cb200_partition_buckets.argtypes = [vp, i, i, vp]
     L.cb200_walk_device.argtypes = [i, i, i, vp] + [vp] * 11 + [C.c_double, i, C.c_double, i, i,
                                                                  C.POINTER(T.Lists), vp]
+    L.cb200_walk_device_active.argtypes = [i, i, i, vp] + [vp] * 11 + [C.c_double, i, C.c_double, i, i, vp,
+                                                                        C.POINTER(T.Lists), vp]
+    L.cb200_active_sets_device.argtypes = [vp, vp, i, vp, vp, i, i, vp, vp, vp, vp]
     L.cb200_lists_free.argtypes = [C.POINTER(T.Lists), vp]
     L.cb200_build_tree.argtypes = [vp, vp, vp, i, i, vp, vp, C.POINTER(T.DevTree), vp]
     L.cb200_tree_free.argtypes = [C.POINTER(T.DevTree), vp]

@@ -146,6 +146,20 @@ def clustered_box(n, seed=2, n_halos=None, frac_halo=0.7, rs_range=(2e-4, 2e-2))
     return pos, np.full(n, 1.0 / n), np.full(n, n ** (-1.0 / 3.0) / 20.0)
 
 
+def density_rungs(pos, period=1.0, max_rung=6):
+    """particle rung = clamp(floor(log2(rho_local / rho_mean) / 2), 0, 6), so that
+    force steps at activeRung 2, 4 exercise the multistep path (active-bucket subset + Ewald
+    markers).  rho_local: counts on a grid with ~8 particles per cell on average."""
+    pos = np.asarray(pos)
+    n = len(pos)
+    g = max(1, int(round((n / 8.0) ** (1.0 / 3.0))))
+    ijk = np.floor((pos / period + 0.5) * g).astype(np.int64) % g
+    cell = (ijk[:, 0] * g + ijk[:, 1]) * g + ijk[:, 2]
+    cnt = np.bincount(cell, minlength=g ** 3)
+    ratio = cnt[cell] * (float(g) ** 3 / n)
+    return np.clip(np.floor(np.log2(ratio) / 2.0), 0, max_rung).astype(np.uint8)
+
+
 def cosmo_box(n_side=48, seed=300, growth=0.035):
     """Stand-in for testcosmo/cube300.tbin (48^3 = 110592 dark particles, periodic unit box,
     the fixture itself stays in the reference tree): a grid displaced by a Gaussian random

@@ -251,6 +251,26 @@ void cb200_walk_device(int numNodes, int numBuckets, int numLevels, const int *h
                        const double *d_boxlo_xyz, const double *d_boxhi_xyz, const double *d_moments_f64,
                        double theta, int nReplicas, double period, int bucketLo, int bucketHi,
                        cb200_lists *out, void *stream);
+/* Multistep (Compute.cpp:1278,1574: only buckets with rungs >= activeRung get lists):
+ * the same walk restricted to the buckets whose byte in d_bucketActive (numBuckets bytes on the
+ * device) is non-zero; NULL = every bucket = cb200_walk_device.  Entries, order and offsetID bits
+ * equal the host walk's with the same mask (cb200h_walk). */
+void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const int *h_levelStart,
+                              const int *d_child0, const int *d_child1, const int *d_parent,
+                              const int *d_firstPart, const int *d_lastPart,
+                              const int *d_bucketFirst, const int *d_bucketCount, const int *d_bucketNode,
+                              const double *d_boxlo_xyz, const double *d_boxhi_xyz, const double *d_moments_f64,
+                              double theta, int nReplicas, double period, int bucketLo, int bucketHi,
+                              const unsigned char *d_bucketActive, cb200_lists *out, void *stream);
+/* The active sets of a multistep force step from per-particle rungs (one byte per particle, indexed
+ * through d_order when it is not NULL, i.e. in the caller's order): d_bucketActive[b] = some particle
+ * of bucket b has rung >= activeRung (GenericTreeNode::rungs, Compute.cpp:1278); d_ewaldMarkers =
+ * ascending tree-order indices of the particles with rung >= activeRung (the marker array of
+ * EwaldHost's large phase, Ewald.cpp:416-437; capacity numParticles ints).  h_counts[0] = active
+ * buckets, h_counts[1] = active particles; synchronises the stream. */
+void cb200_active_sets_device(const unsigned char *d_rung, const int *d_order, int numParticles,
+                              const int *d_bucketStarts, const int *d_bucketSizes, int numBuckets, int activeRung,
+                              unsigned char *d_bucketActive, int *d_ewaldMarkers, int *h_counts, void *stream);
 void cb200_lists_free(cb200_lists *lists, void *stream);
 
 /* --- new: per-GPU bucket partitioner --------------------------- */

@@ -512,6 +512,46 @@ def test_clustered_box_device_path(hc):
     assert np.isfinite(a).all()
 
 
+@pytest.mark.parametrize("active_rung", [2, 4])
+def test_multistep_device_path(hc, active_rung):
+    """SURVEY D6 / config C4 "multistep buckets": rungs in, the active sets made on the device
+    (bucket active = some particle with rung >= activeRung, Compute.cpp:1278; Ewald markers =
+    those particles, Ewald.cpp:416-437), lists of the active buckets only -- bit-exact against the
+    host walk with the same mask -- and forces against the oracle; inactive buckets stay zero"""
+    from changa_b200.workloads import clustered_box, density_rungs
+    from changa_b200.device_step import RawParticleStep, DeviceTreeStep
+    from changa_b200.tree import Tree, tree_workload
+    pos, mass, soft = clustered_box(20000, seed=2, n_halos=12)
+    rung = density_rungs(pos)
+    host = Tree(pos, mass, soft, max_bucket=12)
+    rs = rung[host.order]  # tree order
+    pact = rs >= active_rung
+    bact = np.array([pact[s:s + z].any() for s, z in zip(host.bucket_starts, host.bucket_sizes)])
+    assert 0 < bact.sum() < host.num_buckets and 0 < pact.sum() < len(pos)
+    wl = tree_workload(pos, mass, soft, theta=0.7, n_replicas=1, period=1.0, ewald={}, bucket_active=bact, tree=host)
+    wl["ewald"]["active"] = np.nonzero(pact)[0].astype(np.int32)
+    want = host.walk(theta=0.7, n_replicas=1, period=1.0, bucket_active=bact)
+    ex, em = host.expand_part_list(want["part"], want["part_mark"])
+    dstep = DeviceTreeStep(hc, host, theta=0.7, n_replicas=1, period=1.0, ewald={}, rung=rs, active_rung=active_rung)
+    rstep = RawParticleStep(hc, pos, mass, soft, theta=0.7, n_replicas=1, period=1.0, ewald={}, rung=rung,
+                            active_rung=active_rung)
+    try:
+        a = dstep.run(keep_lists=True).copy()
+        dev = dstep.kept
+        b = rstep.run().copy()
+    finally:
+        dstep.free()
+        rstep.free()
+    assert dstep.active == rstep.active == {"buckets": int(bact.sum()), "particles": int(pact.sum())}
+    assert np.array_equal(dev["cell_mark"], want["cell_mark"].astype(np.int32))
+    assert np.array_equal(dev["cell"], want["cell"]) and np.array_equal(dev["soft"], want["soft"])
+    assert np.array_equal(dev["part"], ex) and np.array_equal(dev["part_mark"], em.astype(np.int32))
+    assert np.array_equal(b[host.order], a)
+    off = np.repeat(~bact, host.bucket_sizes)  # buckets are contiguous in tree order
+    assert not a[off].any()
+    compare(a, oracle_forces_tree(wl), median_tol=5e-6, max_tol=3e-4, pot_tol=2e-5, floor_frac=0.1)
+
+
 @pytest.mark.parametrize("name", ["cube300", "king"])
 def test_reference_fixture_configs(hc, name):
     """BASELINE.json configs 1 and 2 on the reference's own particle sets (teststep/king_soft.bin,

@@ -363,8 +363,16 @@ static void dispatch_cell_list(int maxBucket, const PackedPart *parts, VariableP
   TapScope tap(TAP_CELL, stream);
 #ifdef CUDA_USE_DOUBLE
   /* doubles take two registers each: 8 targets per pass is what fits in 255 */
+  static const int variant = getenv("CB200_PC64_VARIANT") ? atoi(getenv("CB200_PC64_VARIANT")) : 0; /* tuning switch */
   (void)maxBucket;
-  launch_cell_list<8, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  if (variant == 1)
+    launch_cell_list<6, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else if (variant == 2)
+    launch_cell_list<12, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else if (variant == 3)
+    launch_cell_list<4, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else
+    launch_cell_list<8, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
 #else
   static const bool scalar = getenv("CB200_PC_SCALAR") != nullptr; /* A/B switch: the pre-FFMA2 kernel */
   if (scalar) {
@@ -1080,7 +1088,8 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   NodeLists *lists = (NodeLists *)pool_alloc((size_t)numNodes * sizeof(NodeLists), s);
   WalkNodeRec *rec = (WalkNodeRec *)pool_alloc((size_t)numNodes * sizeof(WalkNodeRec), s);
   t.softMaxBits = (const unsigned long long *)(ctl + 128); /* ctl is zeroed above */
-  walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, rec, (unsigned long long *)(ctl + 128));
+  walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, p.theta, p.thetaMono, rec,
+                                                                (unsigned long long *)(ctl + 128));
   cudaChk(cudaPeekAtLastError());
   g_launches.fetch_add(1);
   t.rec = rec;

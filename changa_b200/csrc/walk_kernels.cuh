@@ -43,9 +43,11 @@ struct WalkEntry { int node; int offsetID; };
 /* what one opening test reads of a SOURCE node, gathered into one 64-byte record (two
  * sectors) instead of five scattered arrays: the walk is a stream of dependent gathers */
 struct __align__(16) WalkNodeRec {
-  double cx, cy, cz, radius, soft;
+  double cx, cy, cz;
+  double ropen;     /* max(2/sqrt(3) * radius / theta, radius): the opening radius of gravity.h:665-668 */
+  double soft;
   int child0, child1, first, last;
-  double pad;
+  double ropenMono; /* 2/sqrt(3) * radius / theta^4 (gravity.h:712) */
 };
 static_assert(sizeof(WalkNodeRec) == 64, "WalkNodeRec");
 
@@ -61,7 +63,8 @@ struct WalkTree {
 
 constexpr int kWalkMaybeSoft = 1 << 31; /* clist entries only: some bucket below the owner MAY see this cell softened */
 
-__global__ void walk_pack_nodes_kernel(WalkTree t, WalkNodeRec *__restrict__ out, unsigned long long *softMaxBits) {
+__global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMono, WalkNodeRec *__restrict__ out,
+                                       unsigned long long *softMaxBits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double soft = 0.0;
   if (i < t.numNodes) soft = fmax(t.mom[(size_t)i * 27 + 1], 0.0);
@@ -76,9 +79,15 @@ __global__ void walk_pack_nodes_kernel(WalkTree t, WalkNodeRec *__restrict__ out
   if (i >= t.numNodes) return;
   const double *m = t.mom + (size_t)i * 27;
   WalkNodeRec r;
-  r.radius = m[0]; r.soft = m[1]; r.cx = m[3]; r.cy = m[4]; r.cz = m[5];
+  /* the two radii of openCriterionNode depend on the source node only: computed once here with the
+   * host walk's operations (one product, one quotient, each rounded) instead of per opening test */
+  const double geom = 2.0 / sqrt(3.0);
+  const double gr = __dmul_rn(geom, m[0]);
+  double ropen = __ddiv_rn(gr, theta);
+  if (ropen < m[0]) ropen = m[0];
+  r.ropen = ropen; r.ropenMono = __ddiv_rn(gr, thetaMono);
+  r.soft = m[1]; r.cx = m[3]; r.cy = m[4]; r.cz = m[5];
   r.child0 = t.child0[i]; r.child1 = t.child1[i]; r.first = t.first[i]; r.last = t.last[i];
-  r.pad = 0.0;
   out[i] = r;
 }
 
@@ -99,7 +108,7 @@ struct NodeLists {
    * totals (minus the softened cells, which only flagged entries can be) */
   int pathCells, pathParts, pathFlagged;
   int ownParts; /* expanded particle entries of this node's own lplist */
-  int pad1;
+  int parent;   /* copy of the tree's parent link: emit climbs bucket -> root with ONE dependent load per level */
 };
 static_assert(sizeof(NodeLists) == 48, "NodeLists");
 
@@ -152,18 +161,14 @@ __device__ __forceinline__ int walk_open_criterion(const WalkParams &p, const Wa
                                                    const WalkNodeRec &mine, const double *lo, const double *hi,
                                                    bool myIsBucket) {
   if (m.last - m.first + 1 <= 6) return 1;
-  const double geom = 2.0 / sqrt(3.0);
-  double radius = __ddiv_rn(__dmul_rn(geom, m.radius), p.theta);
-  if (radius < m.radius) radius = m.radius;
   double c[3];
   walk_shifted_cm(m, offsetID, p.period, c);
-  if (walk_box_sphere(lo, hi, c, radius)) {
+  if (walk_box_sphere(lo, hi, c, m.ropen)) {
     if (myIsBucket) return 1;
-    return walk_box_inside_sphere(lo, hi, c, radius) ? 1 : -1;
+    return walk_box_inside_sphere(lo, hi, c, m.ropen) ? 1 : -1;
   }
   if (!walk_open_softening(m, c, mine, lo, hi)) return 0;
-  radius = __ddiv_rn(__dmul_rn(geom, m.radius), p.thetaMono);
-  return walk_box_sphere(lo, hi, c, radius) ? 1 : 0;
+  return walk_box_sphere(lo, hi, c, m.ropenMono) ? 1 : 0;
 }
 
 /* active buckets of a node under the [bucketLo, bucketHi) restriction and the active mask;
@@ -219,6 +224,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     int target = 0;
     bool go = walk_node_active(t, p, my, target);
     const int par = t.parent[my];
+    out.parent = par;
     if (par >= 0) {
       const NodeLists up = lists[par];
       if (go) go = up.visited && up.uLen > 0; /* descend only under a non-empty undecided list */
@@ -287,21 +293,24 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       const bool toL = have && open != 0 && srcBucket;
       const bool expand = have && open != 0 && !srcBucket && (open == 1 || myIsBucket);
       const bool toU = have && open != 0 && !srcBucket && !expand;
-      walk_append(cl, nc, toC, e, lane, kWalkCap, pools.error);
-      walk_append(lp, nl, toL, e, lane, kWalkCap, pools.error);
-      walk_append(und, nu, toU, e, lane, kWalkCap, pools.error);
-      /* children in order 0, 1 behind everything already queued */
-      const int kids = expand ? (c0 >= 0) + (c1 >= 0) : 0;
-      int incl = kids;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+      /* ordered appends (lane order = checklist order): one ballot per list, one store per lane --
+       * the three lists are consecutive kWalkCap-slices of the warp's scratch */
+      const unsigned below = (1u << lane) - 1;
+      const unsigned bC = __ballot_sync(0xffffffffu, toC), bL = __ballot_sync(0xffffffffu, toL),
+                     bU = __ballot_sync(0xffffffffu, toU);
+      if (toC | toL | toU) {
+        const int pos = toC ? nc + __popc(bC & below) : (toL ? nl + __popc(bL & below) : nu + __popc(bU & below));
+        WalkEntry *dst = toC ? cl : (toL ? lp : und);
+        if (pos < kWalkCap) dst[pos] = e;
+        else *pools.error = 1;
       }
-      const int totalKids = __shfl_sync(0xffffffffu, incl, 31);
+      nc += __popc(bC); nl += __popc(bL); nu += __popc(bU);
+      /* children in order 0, 1 behind everything already queued */
+      const unsigned k0 = __ballot_sync(0xffffffffu, expand && c0 >= 0), k1 = __ballot_sync(0xffffffffu, expand && c1 >= 0);
+      const int totalKids = __popc(k0) + __popc(k1);
       const int batch = min(32, tail - head);
       if (tail - head - batch + totalKids > kWalkCap) { if (lane == 0) *pools.error = 1; break; }
-      int pos = tail + incl - kids;
+      int pos = tail + __popc(k0 & below) + __popc(k1 & below);
       if (expand) {
         if (c0 >= 0) chk[(pos++) & (kWalkCap - 1)] = {c0, e.offsetID};
         if (c1 >= 0) chk[pos & (kWalkCap - 1)] = {c1, e.offsetID};
@@ -422,26 +431,28 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
      * cells (Compute.cpp:1653-1743) and particle buckets expanded per particle
      * (Compute.cpp:1823-1863, 1174-1187) level by level */
     const int cbase = cellMark[b], pbase = partMark[b];
-    for (int v = bn; v >= 0; v = t.parent[v]) {
-      const NodeLists nl = lists[v];
-      if (!nl.visited) continue;
-      ILCell *co = cellOut + cbase + (nl.pathCells - nl.cLen);
-      for (int i = lane; i < nl.cLen; i += 32) {
-        const WalkEntry e = pools.clist[nl.cOff + i];
-        ILCell o;
-        o.index = e.node; o.offsetID = e.offsetID;
-        co[i] = o;
-      }
+    const long long *__restrict__ clist64 = reinterpret_cast<const long long *>(pools.clist);
+    const long long *__restrict__ lplist64 = reinterpret_cast<const long long *>(pools.lplist);
+    NodeLists nl = lists[bn];
+    for (;;) {
+      /* the parent's record is requested before this level's entries are copied: one dependent
+       * load per level instead of three (parent link -> record -> entries) */
+      const int par = nl.parent;
+      NodeLists up = nl;
+      if (par >= 0) up = lists[par];
+      if (nl.visited) {
+      long long *co = reinterpret_cast<long long *>(cellOut + cbase + (nl.pathCells - nl.cLen));
+      for (int i = lane; i < nl.cLen; i += 32) co[i] = __ldg(clist64 + nl.cOff + i); /* {node, offsetID} = {index, offsetID} */
       int wp = pbase + (nl.pathParts - nl.ownParts);
       for (int i0 = 0; i0 < nl.lLen; i0 += 32) {
         const int i = i0 + lane;
         int f = 0, cnt = 0, code = 0;
         if (i < nl.lLen) {
-          const WalkEntry e = pools.lplist[nl.lOff + i];
-          const WalkNodeRec &src = t.rec[e.node];
-          f = src.first;
-          cnt = src.last - f + 1;
-          code = e.offsetID & kWalkOffsetMask; /* encodeOffset(0, x, y, z) */
+          const long long e64 = __ldg(lplist64 + nl.lOff + i);
+          const int2 fl = __ldg(reinterpret_cast<const int2 *>(&t.rec[(int)e64].first));
+          f = fl.x;
+          cnt = fl.y - f + 1;
+          code = (int)(e64 >> 32) & kWalkOffsetMask; /* encodeOffset(0, x, y, z) */
         }
         int incl = cnt;
 #pragma unroll
@@ -457,6 +468,9 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
         }
         wp += __shfl_sync(0xffffffffu, incl, 31);
       }
+      }
+      if (par < 0) break;
+      nl = up;
     }
     return;
   }

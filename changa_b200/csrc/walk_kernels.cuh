@@ -123,20 +123,27 @@ struct WalkPools {
  * in-tree at CUDAMoments.cu:137-159), without its early exits: the distance only grows, so
  * "rsq < dsq at some axis" and "dsq > rsq at the end" are the same answer; a zero term adds
  * exactly 0.  Products and sums are rounded separately, like the host build (-ffp-contract=off). */
-__device__ __forceinline__ bool walk_box_sphere(const double *lo, const double *hi, const double *c, double r) {
+/* max without the NaN bookkeeping of fmax (a dozen SASS instructions per call in double): the
+ * operands are differences of finite coordinates */
+__device__ __forceinline__ double walk_max(double a, double b) { return a > b ? a : b; }
+/* squared distance from the point c to the box: what Space::intersect compares with r^2 */
+__device__ __forceinline__ double walk_box_dist2(const double *lo, const double *hi, const double *c) {
   double dsq = 0.0;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double delta = fmax(fmax(__dsub_rn(lo[d], c[d]), __dsub_rn(c[d], hi[d])), 0.0);
+    const double delta = walk_max(walk_max(__dsub_rn(lo[d], c[d]), __dsub_rn(c[d], hi[d])), 0.0);
     dsq = __dadd_rn(dsq, __dmul_rn(delta, delta));
   }
-  return dsq <= __dmul_rn(r, r);
+  return dsq;
+}
+__device__ __forceinline__ bool walk_box_sphere(const double *lo, const double *hi, const double *c, double r) {
+  return walk_box_dist2(lo, hi, c) <= __dmul_rn(r, r);
 }
 __device__ __forceinline__ bool walk_box_inside_sphere(const double *lo, const double *hi, const double *c, double r) {
   double s = 0.0;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double w = fmax(fabs(__dsub_rn(lo[d], c[d])), fabs(__dsub_rn(hi[d], c[d])));
+    const double w = walk_max(fabs(__dsub_rn(lo[d], c[d])), fabs(__dsub_rn(hi[d], c[d])));
     s = __dadd_rn(s, __dmul_rn(w, w));
   }
   return s <= __dmul_rn(r, r);
@@ -156,19 +163,24 @@ __device__ __forceinline__ bool walk_open_softening(const WalkNodeRec &m, const 
   if (d2 <= __dmul_rn(rr, rr)) return true;
   return walk_box_sphere(mylo, myhi, c, rs);
 }
-/* gravity.h:652-723: 1 open, -1 undecided, 0 accept */
-__device__ __forceinline__ int walk_open_criterion(const WalkParams &p, const WalkNodeRec &m, int offsetID,
+/* gravity.h:652-723: 1 open, -1 undecided, 0 accept.  Every sphere of the test is centred on the
+ * same shifted centre of mass c, so the box distance dsq (walk_box_dist2 of the local node's box)
+ * is computed once by the caller and compared with each radius */
+__device__ __forceinline__ int walk_open_criterion(const WalkNodeRec &m, const double *c, double dsq,
                                                    const WalkNodeRec &mine, const double *lo, const double *hi,
                                                    bool myIsBucket) {
   if (m.last - m.first + 1 <= 6) return 1;
-  double c[3];
-  walk_shifted_cm(m, offsetID, p.period, c);
-  if (walk_box_sphere(lo, hi, c, m.ropen)) {
+  if (dsq <= __dmul_rn(m.ropen, m.ropen)) {
     if (myIsBucket) return 1;
     return walk_box_inside_sphere(lo, hi, c, m.ropen) ? 1 : -1;
   }
-  if (!walk_open_softening(m, c, mine, lo, hi)) return 0;
-  return walk_box_sphere(lo, hi, c, m.ropenMono) ? 1 : 0;
+  /* openSoftening (gravity.h:251-260) */
+  const double rs = 2.0 * m.soft, rm = 2.0 * mine.soft;
+  const double dx = __dsub_rn(mine.cx, c[0]), dy = __dsub_rn(mine.cy, c[1]), dz = __dsub_rn(mine.cz, c[2]);
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  const double rr = __dadd_rn(rs, rm);
+  if (!(d2 <= __dmul_rn(rr, rr)) && !(dsq <= __dmul_rn(rs, rs))) return 0;
+  return dsq <= __dmul_rn(m.ropenMono, m.ropenMono) ? 1 : 0;
 }
 
 /* active buckets of a node under the [bucketLo, bucketHi) restriction and the active mask;
@@ -215,6 +227,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
   const int lane = threadIdx.x & 31;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int totalWarps = (gridDim.x * blockDim.x) >> 5;
+  __shared__ __align__(16) uint4 recRows[kWalkWarps * 32 * 5];
   WalkEntry *chk = scratch + (size_t)warpGlobal * 4 * kWalkCap;
   WalkEntry *cl = chk + kWalkCap, *lp = cl + kWalkCap, *und = lp + kWalkCap;
 
@@ -259,18 +272,46 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     if (tail > kWalkCap) { if (lane == 0) *pools.error = 1; tail = kWalkCap; }
     __syncwarp();
 
+    /* Source records are gathered cooperatively: four lanes fetch the four 16-byte pieces of one
+     * 64-byte record with ONE cp.async instruction per 8 records, into an 80-byte-pitch row of
+     * shared memory (conflict-free 128-bit reads), and every lane then reads its own row.  A
+     * per-lane gather costs one L1 tag lookup per lane and load instruction (five instructions x 32
+     * lines per batch: the L1 was the busiest unit, 74%); this way it is 32 lookups per batch. */
+    uint4 *rows = recRows + (size_t)(threadIdx.x >> 5) * (32 * 5);
+    auto stage = [&](int node) {
+      const int sub = lane >> 2, piece = lane & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int src = __shfl_sync(0xffffffffu, node, 8 * j + sub);
+        if (src >= 0) cp_async16_ca(&rows[(8 * j + sub) * 5 + piece], reinterpret_cast<const uint4 *>(t.rec + src) + piece);
+      }
+      cp_async_commit();
+    };
+    WalkEntry eN = {-1, 0};
+    if (lane < tail) eN = chk[lane];
+    stage(eN.node);
     while (head < tail) {
       const int i = head + lane;
       const bool have = i < tail;
-      WalkEntry e = {0, 0};
+      WalkEntry e = eN;
+      const int batch = min(32, tail - head);
+      cp_async_wait<0>();
+      __syncwarp();
+      WalkNodeRec src;
+      {
+        uint4 *d = reinterpret_cast<uint4 *>(&src);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[k] = rows[lane * 5 + k];
+      }
       int open = 0;
       bool srcBucket = false;
       int c0 = -1, c1 = -1;
       if (have) {
-        e = chk[i & (kWalkCap - 1)];
         e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
-        const WalkNodeRec src = t.rec[e.node];
-        open = walk_open_criterion(p, src, e.offsetID, mine, mylo, myhi, myIsBucket);
+        double c[3];
+        walk_shifted_cm(src, e.offsetID, p.period, c);
+        const double dsq = walk_box_dist2(mylo, myhi, c);
+        open = walk_open_criterion(src, c, dsq, mine, mylo, myhi, myIsBucket);
         c0 = src.child0; c1 = src.child1;
         srcBucket = c0 < 0 && c1 < 0;
         if (open == 0) {
@@ -278,9 +319,8 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
            * below this node has its box and centre of mass inside this node's box, so when the
            * cell's softening sphere, grown by the largest bucket softening, misses the box no
            * bucket can see the cell softened: emit then skips the test and the 64-byte gather */
-          double c[3];
-          walk_shifted_cm(src, e.offsetID, p.period, c);
-          if (walk_box_sphere(mylo, myhi, c, __dadd_rn(2.0 * src.soft, rmMax))) {
+          const double rflag = __dadd_rn(2.0 * src.soft, rmMax);
+          if (dsq <= __dmul_rn(rflag, rflag)) {
             e.offsetID |= kWalkMaybeSoft;
             ++myFlagged;
           }
@@ -308,7 +348,6 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       /* children in order 0, 1 behind everything already queued */
       const unsigned k0 = __ballot_sync(0xffffffffu, expand && c0 >= 0), k1 = __ballot_sync(0xffffffffu, expand && c1 >= 0);
       const int totalKids = __popc(k0) + __popc(k1);
-      const int batch = min(32, tail - head);
       if (tail - head - batch + totalKids > kWalkCap) { if (lane == 0) *pools.error = 1; break; }
       int pos = tail + __popc(k0 & below) + __popc(k1 & below);
       if (expand) {
@@ -318,6 +357,9 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       head += batch;
       tail += totalKids;
       __syncwarp();
+      eN.node = -1;
+      if (head + lane < tail) eN = chk[(head + lane) & (kWalkCap - 1)];
+      stage(eN.node);
     }
 
     /* exact-size slices of the pools */

@@ -227,7 +227,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
   const int lane = threadIdx.x & 31;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int totalWarps = (gridDim.x * blockDim.x) >> 5;
-  __shared__ __align__(16) uint4 recRows[kWalkWarps * 32 * 5];
+  __shared__ __align__(16) uint4 recRows[kWalkWarps * 2 * 32 * 5];
   WalkEntry *chk = scratch + (size_t)warpGlobal * 4 * kWalkCap;
   WalkEntry *cl = chk + kWalkCap, *lp = cl + kWalkCap, *und = lp + kWalkCap;
 
@@ -277,19 +277,22 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
      * shared memory (conflict-free 128-bit reads), and every lane then reads its own row.  A
      * per-lane gather costs one L1 tag lookup per lane and load instruction (five instructions x 32
      * lines per batch: the L1 was the busiest unit, 74%); this way it is 32 lookups per batch. */
-    uint4 *rows = recRows + (size_t)(threadIdx.x >> 5) * (32 * 5);
-    auto stage = [&](int node) {
+    uint4 *rows = recRows + (size_t)(threadIdx.x >> 5) * (2 * 32 * 5);
+    auto stage = [&](uint4 *dstRows, int node) {
       const int sub = lane >> 2, piece = lane & 3;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int src = __shfl_sync(0xffffffffu, node, 8 * j + sub);
-        if (src >= 0) cp_async16_ca(&rows[(8 * j + sub) * 5 + piece], reinterpret_cast<const uint4 *>(t.rec + src) + piece);
+        if (src >= 0) cp_async16_ca(&dstRows[(8 * j + sub) * 5 + piece], reinterpret_cast<const uint4 *>(t.rec + src) + piece);
       }
       cp_async_commit();
     };
+    /* two row buffers: the records of the next batch are requested before the current batch is
+     * tested (entries already in the checklist), the ones this batch appends right after it */
+    int buf = 0;
     WalkEntry eN = {-1, 0};
     if (lane < tail) eN = chk[lane];
-    stage(eN.node);
+    stage(rows, eN.node);
     while (head < tail) {
       const int i = head + lane;
       const bool have = i < tail;
@@ -301,7 +304,14 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       {
         uint4 *d = reinterpret_cast<uint4 *>(&src);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) d[k] = rows[lane * 5 + k];
+        for (int k = 0; k < 4; ++k) d[k] = rows[buf * (32 * 5) + lane * 5 + k];
+      }
+      const int iN = i + batch, oldTail = tail;
+      const bool early = iN < oldTail;
+      eN.node = -1;
+      if (head + batch < oldTail) { /* warp-uniform */
+        if (early) eN = chk[iN & (kWalkCap - 1)];
+        stage(rows + (buf ^ 1) * (32 * 5), eN.node);
       }
       int open = 0;
       bool srcBucket = false;
@@ -357,9 +367,12 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       head += batch;
       tail += totalKids;
       __syncwarp();
-      eN.node = -1;
-      if (head + lane < tail) eN = chk[(head + lane) & (kWalkCap - 1)];
-      stage(eN.node);
+      if (tail > oldTail && oldTail < head + 32) { /* warp-uniform: this batch appended entries of the next one */
+        int late = -1;
+        if (!early && iN < tail) { eN = chk[iN & (kWalkCap - 1)]; late = eN.node; }
+        stage(rows + (buf ^ 1) * (32 * 5), late);
+      }
+      buf ^= 1;
     }
 
     /* exact-size slices of the pools */

@@ -257,12 +257,24 @@ class ResidentStep:
             L.cb200_part_list_device_ex(P, V, self.soft_src.data_ptr(), il.data_ptr(), m.data_ptr(), st.data_ptr(),
                                         sz.data_ptr(), nb, self.fperiod, mx, s)
 
-    def timed(self, steps, warmup):
+    def capture(self):
+        """one step as a CUDA graph (single GPU: the step is kernels and one memset on one stream,
+        all operands resident): replaying it removes the host's launch cost and most of the gap
+        between the step's short kernels.  Returns the kernels the graph holds."""
         torch = self.torch
+        before = self.hc.kernel_launches()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.ext):
+            self.step()
+        return self.hc.kernel_launches() - before
+
+    def timed(self, steps, warmup, graph=False):
+        torch = self.torch
+        run = self.graph.replay if graph else self.step
         with torch.cuda.stream(self.ext):
             for _ in range(warmup):
                 self.flush.zero_()
-                self.step()
+                run()
             torch.cuda.synchronize()
             if self.world > 1:
                 self.dist.barrier()
@@ -272,7 +284,7 @@ class ResidentStep:
                 self.flush.zero_()  # evict the lists / moments / particles from the 126 MB L2
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(self.ext)
-                self.step()
+                run()
                 b.record(self.ext)
                 evs.append((a, b))
             torch.cuda.synchronize()
@@ -402,6 +414,7 @@ def main():
     ap.add_argument("--large-n", type=int, default=1 << 22,
                     help="particles of the extra box whose tree and lists are built on the device; "
                          "shared by all ranks at N > 1 (0: skip)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the resident step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--large-active-rung", type=int, default=0,
                     help="> 0: the extra box runs a multistep force step at this activeRung (rungs by local "
                          "density, SURVEY C4): active-bucket lists + Ewald markers made on the device")
@@ -452,13 +465,23 @@ def main():
 
     # ---- device-resident throughput (value, roofline) --------------------------------
     rs = ResidentStep(hc, wl, torch, dist, rank, world)
-    launches0 = hc.kernel_launches()
     rs.timed(0, max(args.warmup, 3))
+    use_graph = world == 1 and not args.no_graph
+    if use_graph:
+        per_step = rs.capture()
+        rs.timed(0, 3, graph=True)
+        ms_total = rs.timed(args.steps, 0, graph=True)
+        launches = per_step * args.steps
+    else:
+        launches1 = hc.kernel_launches()
+        ms_total = rs.timed(args.steps, 0)
+        launches = hc.kernel_launches() - launches1
+    # per-kernel times: a second pass with an event pair around every launch (not the timed one:
+    # the event records sit between the kernels)
+    tap_steps = max(1, min(args.steps, 50))
     hc.timing(True)
-    launches1 = hc.kernel_launches()
-    ms_total = rs.timed(args.steps, 0)
+    rs.timed(tap_steps, 0)
     taps = hc.timing_read()
-    launches = hc.kernel_launches() - launches1
     hc.timing(False)
 
     # ---- end to end through the reference-facing ABI, host buffers -----------------------
@@ -523,6 +546,7 @@ def main():
                        "theta": 0.7, "expansion": "hexadecapole", "bucket_size": 12,
                        "pc_pairs": g_pc, "pp_pairs": g_pp, "ewald_particles": g_ewn,
                        "l2": "flushed between steps (256 MiB device write)",
+                       "launch": "CUDA graph replay of one resident step" if use_graph else "eager launches",
                        "parallelism": f"buckets sharded by SFC range x{world}; packed particle and moment slices all-gathered per step" if world > 1 else "single GPU"},
             "force_step_ms": ms_step,
             "kernels": {"pc_ms": pc_ms, "pp_ms": pp_ms, "ewald_ms": ew_ms,
@@ -534,7 +558,7 @@ def main():
                         # (p-p 30 flop/pair; Ewald 350 per evaluated replica + 58 per h-vector)
                         "pp_tflops": (cnt["part"] + cnt["softcell"]) * FLOP_PP / (pp_ms * 1e-3) / 1e12 if pp_ms else None,
                         "ewald_tflops": (ew_real * FLOP_EW_REAL + ew_n * n_ewh * FLOP_EW_K) / (ew_ms * 1e-3) / 1e12 if ew_ms else None,
-                        "note": "rank 0, CUDA events around each launch"},
+                        "note": "rank 0, CUDA events around each launch, separate eager pass"},
             "roofline": {"bound": "fp64_fma" if args.double else "fp32_fma",
                          "kernel": "cell_list_kernel (p-c hexadecapole, scalar FP64)" if args.double else "cell_list_x2_kernel (p-c hexadecapole, packed f32x2)",
                          "achieved": pc_tflops,

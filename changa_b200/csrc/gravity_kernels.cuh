@@ -235,6 +235,18 @@ __device__ __forceinline__ void warp_reduce5(real &a0, real &a1, real &a2, real 
 
 constexpr int kListWarps = 4; /* warps (= buckets in flight) per CTA */
 
+/* Next bucket from the grid-wide counter.  Every warp stops at its first index >= nBuckets, so a
+ * launch performs exactly nBuckets + (warps of the grid) increments: the warp that draws the last
+ * value puts the counter back to zero, and the next launch on the stream needs no memset node. */
+__device__ __forceinline__ int grab_bucket(unsigned int *nextBucket, int nBuckets, int lane) {
+  unsigned int k = 0;
+  if (lane == 0) {
+    k = atomicAdd(nextBucket, 1u);
+    if (k == (unsigned int)nBuckets + gridDim.x * kListWarps - 1u) *nextBucket = 0u;
+  }
+  return (int)__shfl_sync(0xffffffffu, k, 0);
+}
+
 template <int PB>
 constexpr size_t cell_list_smem_bytes() {
   return (size_t)kListWarps * (2 * 32 * kCellBytes + PB * sizeof(real4));
@@ -254,9 +266,7 @@ cell_list_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restr
   real4 *sp = reinterpret_cast<real4 *>(smem_raw + (size_t)kListWarps * 2 * 32 * kCellBytes) + warp * PB;
 
   for (;;) {
-    int k = 0;
-    if (lane == 0) k = (int)atomicAdd(nextBucket, 1u);
-    k = __shfl_sync(kFull, k, 0);
+    const int k = grab_bucket(nextBucket, nBuckets, lane);
     if (k >= nBuckets) break;
     const int begin = markers[k], len = markers[k + 1] - begin;
     const int first = starts[k], count = sizes[k];
@@ -566,11 +576,7 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
   const char *srcBase; /* piece q of row 0, pinned: one IMAD.WIDE per gathered row */
   asm volatile("mov.u64 %0, %1;" : "=l"(srcBase) : "l"(reinterpret_cast<const char *>(cells) + (lane & 7) * 16));
 
-  auto grab = [&]() {
-    int k = 0;
-    if (lane == 0) k = (int)atomicAdd(nextBucket, 1u);
-    return __shfl_sync(kFull, k, 0);
-  };
+  auto grab = [&]() { return grab_bucket(nextBucket, nBuckets, lane); };
   /* rows 8g .. 8g+7 of a tile are fetched by lane group g (8 lanes = 8 pieces of one row) */
   auto stage = [&](unsigned dst, int index) {
     /* lanes without an entry re-fetch the tile's first row (never read): no predicate per row,
@@ -813,9 +819,7 @@ part_list_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restr
   real *ssoft = reinterpret_cast<real *>(smem_raw + (size_t)kListWarps * PB * sizeof(real4)) + warp * PB;
 
   for (;;) {
-    int k = 0;
-    if (lane == 0) k = (int)atomicAdd(nextBucket, 1u);
-    k = __shfl_sync(kFull, k, 0);
+    const int k = grab_bucket(nextBucket, nBuckets, lane);
     if (k >= nBuckets) break;
     const int begin = markers[k], len = markers[k + 1] - begin;
     const int first = starts[k], count = sizes[k];
@@ -962,11 +966,7 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
   float *red = reinterpret_cast<float *>(smem_raw) + (size_t)warp * (5 * PB * 32);
   TargetSoftPair *sp = reinterpret_cast<TargetSoftPair *>(smem_raw + (size_t)kListWarps * 5 * PB * 32 * sizeof(float)) + warp * NP;
   const ILCell none = {-1, 0};
-  auto grab = [&]() {
-    int k = 0;
-    if (lane == 0) k = (int)atomicAdd(nextBucket, 1u);
-    return __shfl_sync(kFull, k, 0);
-  };
+  auto grab = [&]() { return grab_bucket(nextBucket, nBuckets, lane); };
   auto load_source = [&](const ILCell &e, float4 &pos, float &soft) {
     pos = make_float4(0.f, 0.f, 0.f, 0.f);
     soft = 0.f;

@@ -205,6 +205,40 @@ static void pool_forget_stream(cudaStream_t stream) {
   block_cache_flush_locked(dev, stream, true);
 }
 
+/* One bucket counter per (device, stream) for the device-resident list launches: zeroed once when
+ * it is made; every list kernel leaves it at zero again (grab_bucket), and launches on one stream
+ * are ordered, so no memset node sits between the kernels of a step. */
+struct CounterKey {
+  int dev; cudaStream_t stream;
+  bool operator==(const CounterKey &o) const { return dev == o.dev && stream == o.stream; }
+};
+struct CounterKeyHash {
+  size_t operator()(const CounterKey &k) const { return std::hash<void *>()((void *)k.stream) * 31u + (size_t)k.dev; }
+};
+static std::mutex g_counterMutex;
+static std::unordered_map<CounterKey, unsigned *, CounterKeyHash> g_streamCounter;
+static unsigned *stream_counter(cudaStream_t stream) {
+  int dev = 0;
+  cudaChk(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_counterMutex);
+  auto it = g_streamCounter.find({dev, stream});
+  if (it != g_streamCounter.end()) return it->second;
+  unsigned *p = nullptr;
+  cudaChk(cudaMalloc((void **)&p, 256));
+  cudaChk(cudaMemsetAsync(p, 0, 256, stream));
+  g_streamCounter[{dev, stream}] = p;
+  return p;
+}
+static void drop_stream_counter(cudaStream_t stream) {
+  int dev = 0;
+  cudaChk(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_counterMutex);
+  auto it = g_streamCounter.find({dev, stream});
+  if (it == g_streamCounter.end()) return;
+  cudaFree(it->second);
+  g_streamCounter.erase(it);
+}
+
 /* ------------------------------------------------------- copy/compute overlap */
 /* A request arrives on ONE caller stream (TreePiece: streams[thisIndex % numStreams],
  * TreePiece.cpp:5380), and the reference enqueues its host->device list copy and
@@ -728,6 +762,7 @@ void *cb200_stream_create(void) {
 void cb200_stream_destroy(void *stream) {
   pool_forget_stream((cudaStream_t)stream);
   drop_companion((cudaStream_t)stream);
+  drop_stream_counter((cudaStream_t)stream);
   cudaChk(cudaStreamDestroy((cudaStream_t)stream));
 }
 void cb200_stream_synchronize(void *stream) { cudaChk(cudaStreamSynchronize((cudaStream_t)stream)); }
@@ -790,12 +825,10 @@ void cb200_cell_list_device_ex(void *d_parts, void *d_vars, void *d_moments, con
                                int numBuckets, cudatype fperiod, int maxBucketSize, void *stream) {
   if (numBuckets <= 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned *counter = (unsigned *)pool_alloc(256, s);
-  cudaChk(cudaMemsetAsync(counter, 0, 256, s));
+  unsigned *counter = stream_counter(s);
   dispatch_cell_list(device_max_bucket(d_sizes, numBuckets, maxBucketSize), (const PackedPart *)d_parts,
                      (VariablePartData *)d_vars, (const PackedCell *)d_moments, d_list, d_markers, d_starts,
                      d_sizes, numBuckets, fperiod, counter, s);
-  pool_free(counter, s);
 }
 void cb200_part_list_device(void *d_parts, void *d_vars, void *d_sources, const ILCell *d_list,
                             const int *d_markers, const int *d_starts, const int *d_sizes,
@@ -808,12 +841,10 @@ void cb200_part_list_device_ex(void *d_parts, void *d_vars, void *d_sources, con
                                int numBuckets, cudatype fperiod, int maxBucketSize, void *stream) {
   if (numBuckets <= 0) return;
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned *counter = (unsigned *)pool_alloc(256, s);
-  cudaChk(cudaMemsetAsync(counter, 0, 256, s));
+  unsigned *counter = stream_counter(s);
   dispatch_part_list(device_max_bucket(d_sizes, numBuckets, maxBucketSize), (const PackedPart *)d_parts,
                      (VariablePartData *)d_vars, (const PackedPart *)d_sources, d_list, d_markers, d_starts,
                      d_sizes, numBuckets, fperiod, counter, s);
-  pool_free(counter, s);
 }
 void cb200_ewald_device(void *d_parts, void *d_vars, const int *d_markers, int nActive,
                         const EwaldReadOnlyData *h_ro, const EwtData *h_ewt, void *stream) {

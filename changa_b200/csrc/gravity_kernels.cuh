@@ -909,8 +909,20 @@ part_list_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restr
  * per two pairs; a pair that needs the spline falls back to the scalar pp_pair
  * for both halves (gravity.h:147-182). */
 struct TargetSoftPair { f32x2 x, y, z, m, soft; float pad[2]; }; /* 48 bytes */
+__device__ __forceinline__ TargetSoftPair lds_target_soft_pair(unsigned saddr) {
+  TargetSoftPair p;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(p.x), "=l"(p.y) : "r"(saddr));
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2+16];" : "=l"(p.z), "=l"(p.m) : "r"(saddr));
+  asm volatile("ld.shared.u64 %0, [%1+32];" : "=l"(p.soft) : "r"(saddr));
+  p.pad[0] = p.pad[1] = 0.0f;
+  return p;
+}
 
-__device__ __forceinline__ void pp_pair2(float sx, float sy, float sz, float sm, float ssoft,
+/* Branch-free Newtonian part of two pairs.  A half that needs the spline (0 < r < soft_s + soft_t)
+ * or is exactly coincident contributes nothing here (d = 0); the return value says whether some half
+ * still needs the spline, which pp_pair2_soft adds afterwards -- rare, so the bodies of a tile carry
+ * no divergent region and the compiler can overlap them. */
+__device__ __forceinline__ bool pp_pair2(float sx, float sy, float sz, float sm, float ssoft,
                                          const TargetSoftPair &p, f32x2 &ax, f32x2 &ay, f32x2 &az,
                                          f32x2 &pot, float &idt0, float &idt1) {
   const f32x2 rx = sub2(bc2(sx), p.x), ry = sub2(bc2(sy), p.y), rz = sub2(bc2(sz), p.z);
@@ -919,32 +931,38 @@ __device__ __forceinline__ void pp_pair2(float sx, float sy, float sz, float sm,
   float q0, q1, h0, h1;
   unpk2(rsq, q0, q1);
   unpk2(mul2(twoh, twoh), h0, h1);
-  /* Newtonian, or exactly coincident (self pair: contributes nothing, d = 0 below) */
-  if ((q0 >= h0 || q0 == 0.0f) && (q1 >= h1 || q1 == 0.0f)) {
-    float d0 = rsqrt_dev(q0), d1 = rsqrt_dev(q1);
-    d0 = (q0 != 0.0f) ? d0 : 0.0f;
-    d1 = (q1 != 0.0f) ? d1 : 0.0f;
-    const f32x2 d = pk2(d0, d1);
-    const f32x2 b = mul2(mul2(d, d), d);
-    const f32x2 bm = mul2s(sm, b);
-    ax = fma2(rx, bm, ax);
-    ay = fma2(ry, bm, ay);
-    az = fma2(rz, bm, az);
-    pot = fma2(bc2(-sm), d, pot);
-    float i0, i1;
-    unpk2(mul2(add2(p.m, bc2(sm)), b), i0, i1);
-    idt0 = fmaxf(idt0, i0);
-    idt1 = fmaxf(idt1, i1);
-  } else { /* at least one softened pair: the scalar spline for both halves */
-    float x0, x1, y0, y1, z0, z1, m0, m1, s0, s1;
-    unpk2(p.x, x0, x1); unpk2(p.y, y0, y1); unpk2(p.z, z0, z1); unpk2(p.m, m0, m1); unpk2(p.soft, s0, s1);
-    float a0, a1, b0, b1, c0, c1, e0, e1;
-    unpk2(ax, a0, a1); unpk2(ay, b0, b1); unpk2(az, c0, c1); unpk2(pot, e0, e1);
-    const real4 t0 = {x0, y0, z0, m0}, t1 = {x1, y1, z1, m1};
-    pp_pair(sx, sy, sz, sm, ssoft, t0, s0, a0, b0, c0, e0, idt0);
-    pp_pair(sx, sy, sz, sm, ssoft, t1, s1, a1, b1, c1, e1, idt1);
-    ax = pk2(a0, a1); ay = pk2(b0, b1); az = pk2(c0, c1); pot = pk2(e0, e1);
-  }
+  float d0 = rsqrt_dev(q0), d1 = rsqrt_dev(q1);
+  d0 = (q0 >= h0 && q0 != 0.0f) ? d0 : 0.0f;
+  d1 = (q1 >= h1 && q1 != 0.0f) ? d1 : 0.0f;
+  const f32x2 d = pk2(d0, d1);
+  const f32x2 b = mul2(mul2(d, d), d);
+  const f32x2 bm = mul2s(sm, b);
+  ax = fma2(rx, bm, ax);
+  ay = fma2(ry, bm, ay);
+  az = fma2(rz, bm, az);
+  pot = fma2(bc2(-sm), d, pot);
+  float i0, i1;
+  unpk2(mul2(add2(p.m, bc2(sm)), b), i0, i1);
+  idt0 = fmaxf(idt0, i0);
+  idt1 = fmaxf(idt1, i1);
+  return (q0 < h0 && q0 != 0.0f) || (q1 < h1 && q1 != 0.0f);
+}
+
+/* the spline halves pp_pair2 left out: the scalar pp_pair (gravity.h:147-182) for exactly those */
+__device__ __forceinline__ void pp_pair2_soft(float sx, float sy, float sz, float sm, float ssoft,
+                                              const TargetSoftPair &p, f32x2 &ax, f32x2 &ay, f32x2 &az,
+                                              f32x2 &pot, float &idt0, float &idt1) {
+  float x0, x1, y0, y1, z0, z1, m0, m1, s0, s1;
+  unpk2(p.x, x0, x1); unpk2(p.y, y0, y1); unpk2(p.z, z0, z1); unpk2(p.m, m0, m1); unpk2(p.soft, s0, s1);
+  float a0, a1, b0, b1, c0, c1, e0, e1;
+  unpk2(ax, a0, a1); unpk2(ay, b0, b1); unpk2(az, c0, c1); unpk2(pot, e0, e1);
+  const float rx0 = sx - x0, ry0 = sy - y0, rz0 = sz - z0, rx1 = sx - x1, ry1 = sy - y1, rz1 = sz - z1;
+  const float q0 = fmaf(rz0, rz0, fmaf(ry0, ry0, rx0 * rx0)), q1 = fmaf(rz1, rz1, fmaf(ry1, ry1, rx1 * rx1));
+  const float t0 = s0 + ssoft, t1 = s1 + ssoft;
+  const real4 p0 = {x0, y0, z0, m0}, p1 = {x1, y1, z1, m1};
+  if (q0 < t0 * t0 && q0 != 0.0f) pp_pair(sx, sy, sz, sm, ssoft, p0, s0, a0, b0, c0, e0, idt0);
+  if (q1 < t1 * t1 && q1 != 0.0f) pp_pair(sx, sy, sz, sm, ssoft, p1, s1, a1, b1, c1, e1, idt1);
+  ax = pk2(a0, a1); ay = pk2(b0, b1); az = pk2(c0, c1); pot = pk2(e0, e1);
 }
 
 template <int PB>
@@ -965,6 +983,7 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float *red = reinterpret_cast<float *>(smem_raw) + (size_t)warp * (5 * PB * 32);
   TargetSoftPair *sp = reinterpret_cast<TargetSoftPair *>(smem_raw + (size_t)kListWarps * 5 * PB * 32 * sizeof(float)) + warp * NP;
+  const unsigned spAddr = pin_u32(smem_u32(sp)); /* one register + immediates: no per-body address rebuild */
   const ILCell none = {-1, 0};
   auto grab = [&]() { return grab_bucket(nextBucket, nBuckets, lane); };
   auto load_source = [&](const ILCell &e, float4 &pos, float &soft) {
@@ -1057,11 +1076,22 @@ part_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
           const float sx = fmaf(float(replica_x(cur.offsetID)), fperiod, s_pos.x);
           const float sy = fmaf(float(replica_y(cur.offsetID)), fperiod, s_pos.y);
           const float sz = fmaf(float(replica_z(cur.offsetID)), fperiod, s_pos.z);
+          unsigned needSoft = 0;
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
             if (j < npairs) {
-              const TargetSoftPair p = sp[j];
-              pp_pair2(sx, sy, sz, s_pos.w, s_soft, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
+              const TargetSoftPair p = lds_target_soft_pair(spAddr + j * (unsigned)sizeof(TargetSoftPair));
+              if (pp_pair2(sx, sy, sz, s_pos.w, s_soft, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]))
+                needSoft |= 1u << j;
+            }
+          }
+          if (needSoft) { /* rare: some pair of this lane is inside the softening length */
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+              if ((needSoft >> j) & 1u) {
+                const TargetSoftPair p = lds_target_soft_pair(spAddr + j * (unsigned)sizeof(TargetSoftPair));
+                pp_pair2_soft(sx, sy, sz, s_pos.w, s_soft, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1]);
+              }
             }
           }
         }

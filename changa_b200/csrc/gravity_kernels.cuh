@@ -931,9 +931,10 @@ __device__ __forceinline__ bool pp_pair2(float sx, float sy, float sz, float sm,
   float q0, q1, h0, h1;
   unpk2(rsq, q0, q1);
   unpk2(mul2(twoh, twoh), h0, h1);
+  const bool far0 = q0 >= h0, far1 = q1 >= h1, some0 = q0 != 0.0f, some1 = q1 != 0.0f;
   float d0 = rsqrt_dev(q0), d1 = rsqrt_dev(q1);
-  d0 = (q0 >= h0 && q0 != 0.0f) ? d0 : 0.0f;
-  d1 = (q1 >= h1 && q1 != 0.0f) ? d1 : 0.0f;
+  d0 = (far0 && some0) ? d0 : 0.0f;
+  d1 = (far1 && some1) ? d1 : 0.0f;
   const f32x2 d = pk2(d0, d1);
   const f32x2 b = mul2(mul2(d, d), d);
   const f32x2 bm = mul2s(sm, b);
@@ -945,7 +946,7 @@ __device__ __forceinline__ bool pp_pair2(float sx, float sy, float sz, float sm,
   unpk2(mul2(add2(p.m, bc2(sm)), b), i0, i1);
   idt0 = fmaxf(idt0, i0);
   idt1 = fmaxf(idt1, i1);
-  return (q0 < h0 && q0 != 0.0f) || (q1 < h1 && q1 != 0.0f);
+  return (!far0 && some0) || (!far1 && some1);
 }
 
 /* the spline halves pp_pair2 left out: the scalar pp_pair (gravity.h:147-182) for exactly those */
@@ -960,8 +961,8 @@ __device__ __forceinline__ void pp_pair2_soft(float sx, float sy, float sz, floa
   const float q0 = fmaf(rz0, rz0, fmaf(ry0, ry0, rx0 * rx0)), q1 = fmaf(rz1, rz1, fmaf(ry1, ry1, rx1 * rx1));
   const float t0 = s0 + ssoft, t1 = s1 + ssoft;
   const real4 p0 = {x0, y0, z0, m0}, p1 = {x1, y1, z1, m1};
-  if (q0 < t0 * t0 && q0 != 0.0f) pp_pair(sx, sy, sz, sm, ssoft, p0, s0, a0, b0, c0, e0, idt0);
-  if (q1 < t1 * t1 && q1 != 0.0f) pp_pair(sx, sy, sz, sm, ssoft, p1, s1, a1, b1, c1, e1, idt1);
+  if (!(q0 >= t0 * t0) && q0 != 0.0f) pp_pair(sx, sy, sz, sm, ssoft, p0, s0, a0, b0, c0, e0, idt0);
+  if (!(q1 >= t1 * t1) && q1 != 0.0f) pp_pair(sx, sy, sz, sm, ssoft, p1, s1, a1, b1, c1, e1, idt1);
   ax = pk2(a0, a1); ay = pk2(b0, b1); az = pk2(c0, c1); pot = pk2(e0, e1);
 }
 

@@ -357,6 +357,26 @@ def large_box_step(hc, n, torch, dist, rank, world, steps=3, kind="uniform", act
             "timing": "wall clock around RawParticleStep.run() (max over ranks); phases and kernels by CUDA events on rank 0's stream"}
 
 
+def gpu_local_affinity(index):
+    """pin this process to the CPUs NVML names as local to GPU `index`; returns the core count or None"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def workload_size(args, world):
     """None = the config's own particle set (at N=1 the reference's Tipsy fixture, committed under
     tests/golden/); at N > 1 the box grows with the GPU count (weak scaling), which only the
@@ -427,6 +447,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    numa = None
+    if world > 1 and not os.environ.get("CB200_NO_AFFINITY"):
+        # one process per GPU: run on the cores next to that GPU, so the pinned buffers (first touch)
+        # and the copies they feed stay on the GPU's own socket instead of crossing the host fabric
+        numa = gpu_local_affinity(local)
+
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
@@ -485,7 +511,27 @@ def main():
     hc.timing(False)
 
     # ---- end to end through the reference-facing ABI, host buffers -----------------------
-    fs = ForceStep(hc, wl)
+    e2e_how = "wall clock around ForceStep.run() (C-ABI entry points, pinned host buffers)"
+    if world > 1:
+        # every rank uploads its slice only; NVLink replicates (ShardedForceStep).  Checked once against
+        # the rank pushing everything through its own PCIe link: same rows, bit for bit.
+        from changa_b200.hostcuda import ShardedForceStep
+        ref = ForceStep(hc, wl)
+        want = ref.run().copy()
+        ref.free()
+        fs = ShardedForceStep(hc, wl, torch, dist, rank, world)
+        got = fs.run()
+        same = torch.tensor([1 if np.array_equal(got[fs.p0:fs.p1], want[fs.p0:fs.p1]) else 0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)  # the ranks decide together: the sharded step holds collectives
+        if int(same.item()) == 0:
+            sys.stderr.write(f"rank {rank}: sharded upload differs from the full upload somewhere; timing the full upload\n")
+            fs.free()
+            fs = ForceStep(hc, wl)
+        else:
+          e2e_how = ("wall clock around ShardedForceStep.run(): slice upload from pinned host buffers, packed arrays "
+                     "all-gathered over NVLink, the reference's list requests, own rows back; equals ForceStep bitwise")
+    else:
+        fs = ForceStep(hc, wl)
     e2e_steps = args.e2e_steps or max(1, min(args.steps, 50))
     for _ in range(3):
         fs.run()
@@ -547,6 +593,7 @@ def main():
                        "pc_pairs": g_pc, "pp_pairs": g_pp, "ewald_particles": g_ewn,
                        "l2": "flushed between steps (256 MiB device write)",
                        "launch": "CUDA graph replay of one resident step" if use_graph else "eager launches",
+                       "cpu_affinity": f"{numa} GPU-local cores per rank (NVML)" if numa else None,
                        "parallelism": f"buckets sharded by SFC range x{world}; packed particle and moment slices all-gathered per step" if world > 1 else "single GPU"},
             "force_step_ms": ms_step,
             "kernels": {"pc_ms": pc_ms, "pp_ms": pp_ms, "ewald_ms": ew_ms,
@@ -571,7 +618,7 @@ def main():
                                  "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["hbm_source"]}},
             "e2e": {"value": g_pairs / (e2e_s / e2e_steps), "unit": "interactions/s", "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "steps": e2e_steps, "h2d_bytes_per_step": g_h2d, "d2h_bytes_per_step": g_d2h,
-                    "timing": "wall clock around ForceStep.run() (C-ABI entry points, pinned host buffers)"},
+                    "timing": e2e_how},
             "gpu_launches": int(g_launch),
             "clocks": clocks,
         }

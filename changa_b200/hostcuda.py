@@ -382,3 +382,79 @@ class ForceStep:
             self.hc.EwaldHostMemoryFree(self.ewald, 1)
         for s in self.streams:
             self.hc.stream_destroy(s)
+
+
+class ShardedForceStep(ForceStep):
+    """ForceStep of ONE rank of a multi-GPU step (one process per GPU): instead of every
+    rank pushing the whole particle and moment arrays through its own PCIe link
+    (DataManagerTransferLocalTree), a rank uploads only ITS slice of the two arrays, packs it, and one
+    all-gather each over NVLink (torch.distributed / NCCL) replicates the packed arrays; the list
+    requests are the reference's (TreePiece*ListDataTransferLocal, EwaldHost) against those arrays, and
+    only the rank's own rows of the accelerations come back.  Same kernels, same packed inputs: the rows
+    equal ForceStep's bit for bit (bench.py checks it once per run)."""
+
+    def __init__(self, hc, wl, torch, dist, rank, world):
+        super().__init__(hc, wl, n_streams=1)
+        from .multigpu import shard_rows
+        self.torch, self.dist = torch, dist
+        rt, L = hc.np_real, hc.L
+        mine_p, self.pc = shard_rows(np.ascontiguousarray(wl["parts"], dtype=rt), rank, world)
+        mine_m, self.mc = shard_rows(np.ascontiguousarray(wl["moments"], dtype=rt), rank, world)
+        for b in (self.moments, self.parts):  # the full-size pinned copies are not used
+            b.free()
+        self.parts = hc.allocatePinnedHostMemory(mine_p.shape, rt)
+        self.moments = hc.allocatePinnedHostMemory(mine_m.shape, rt)
+        self.parts.array[:] = mine_p
+        self.moments.array[:] = mine_m
+        tdt = torch.float64 if np.dtype(rt) == np.float64 else torch.float32
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pb, mb = L.cb200_packed_particle_bytes(), L.cb200_packed_moment_bytes()
+        self.d_parts = torch.empty(mine_p.shape, dtype=tdt, device=dev)
+        self.d_mom = torch.empty(mine_m.shape, dtype=tdt, device=dev)
+        self.send_p = torch.empty(self.pc * pb, dtype=torch.uint8, device=dev)
+        self.send_m = torch.empty(self.mc * mb, dtype=torch.uint8, device=dev)
+        self.pk_parts = torch.empty(self.pc * world * pb, dtype=torch.uint8, device=dev)
+        self.pk_mom = torch.empty(self.mc * world * mb, dtype=torch.uint8, device=dev)
+        self.d_vars = torch.empty((self.np_, 5), dtype=tdt, device=dev)
+        self.ext = torch.cuda.ExternalStream(self.streams[0])
+        # my rows: the particles of my buckets (contiguous in tree order)
+        lo, hi = [], []
+        for key in ("cell", "part", "softcell"):
+            if wl.get(key) and len(wl[key][2]):
+                st, sz = np.asarray(wl[key][2]), np.asarray(wl[key][3])
+                lo.append(int(st.min())); hi.append(int((st + sz).max()))
+        ew = wl.get("ewald")
+        if ew and ew.get("active") is not None and len(ew["active"]):
+            lo.append(int(np.min(ew["active"]))); hi.append(int(np.max(ew["active"])) + 1)
+        self.p0, self.p1 = (min(lo), max(hi)) if lo else (0, self.np_)
+        self.row_bytes = 5 * np.dtype(rt).itemsize
+
+    @property
+    def d2h_bytes(self):
+        return (self.p1 - self.p0) * self.row_bytes
+
+    def run(self, sync=True):
+        hc, L, s0 = self.hc, self.hc.L, self.streams[0]
+        L.cb200_copy_device(self.d_parts.data_ptr(), self.parts.ptr, self.parts.nbytes, s0)
+        L.cb200_copy_device(self.d_mom.data_ptr(), self.moments.ptr, self.moments.nbytes, s0)
+        L.cb200_pack_particles_device(self.d_parts.data_ptr(), self.send_p.data_ptr(), self.pc, s0)
+        L.cb200_pack_moments_device(self.d_mom.data_ptr(), self.send_m.data_ptr(), self.mc, s0)
+        with self.torch.cuda.stream(self.ext):
+            self.dist.all_gather_into_tensor(self.pk_parts, self.send_p)
+            self.dist.all_gather_into_tensor(self.pk_mom, self.send_m)
+        dm, dp, dv = self.pk_mom.data_ptr(), self.pk_parts.data_ptr(), self.d_vars.data_ptr()
+        L.cb200_zero_vars_device(dv, self.np_, s0)
+        if self.ewald:
+            hc.EwaldHost(dp, dv, self.ewald, s0)
+        for req, call, extra in self._requests():
+            req.d_localMoments, req.d_localParts, req.d_localVars = dm, dp, dv
+            if extra is not None:
+                call(req, extra.array)
+            else:
+                call(req)
+        off = self.p0 * self.row_bytes
+        L.cb200_TransferParticleVarsBack(self.vars_out.ptr + off, (self.p1 - self.p0) * self.row_bytes, dv + off, s0, None)
+        if sync:
+            hc.stream_synchronize(s0)
+        return self.vars_out.array
+

@@ -906,7 +906,7 @@ void cb200_build_moments(const double *d_pos_xyz, const double *d_mass, const do
     if (n <= 0) continue;
     build_moments_level_kernel<<<(n + 63) / 64, 64, 0, s>>>(
         d_pos_xyz, d_mass, d_soft, d_child0, d_child1, d_firstPart, d_lastPart, d_geolo_xyz, d_geohi_xyz,
-        d_boxlo_xyz, d_boxhi_xyz, lo, n, work, (real *)d_moments_out, d_moments_f64_out);
+        d_boxlo_xyz, d_boxhi_xyz, lo, n, numNodes, work, (real *)d_moments_out, d_moments_f64_out);
     cudaChk(cudaPeekAtLastError());
     g_launches.fetch_add(1);
   }

@@ -59,13 +59,21 @@ __host__ __device__ inline void fm_point(double *r, double m, double u, double x
 
 /* components of order 2, 3, 4 follow F_M in runs of 5, 7, 9 */
 __host__ __device__ inline void fm_scale_orders(double *r, const double *a, double ratio, double w, bool accumulate) {
-  double s = ratio * w;
-  int k = F_XX;
-  const int len[3] = {5, 7, 9};
-  for (int o = 0; o < 3; ++o) {
-    s *= ratio;
-    for (int j = 0; j < len[o]; ++j, ++k) r[k] = accumulate ? r[k] + s * a[k] : s * a[k];
-  }
+  /* three runs with constant bounds: fully unrolled on the device, so the expansions stay in
+   * registers (a run-length table and a running index put them in local memory) */
+  const double s2 = ratio * w * ratio, s3 = s2 * ratio, s4 = s3 * ratio;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int k = F_XX; k < F_XXX; ++k) r[k] = accumulate ? r[k] + s2 * a[k] : s2 * a[k];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int k = F_XXX; k < F_XXXX; ++k) r[k] = accumulate ? r[k] + s3 * a[k] : s3 * a[k];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int k = F_XXXX; k < F_N; ++k) r[k] = accumulate ? r[k] + s4 * a[k] : s4 * a[k];
 }
 
 __host__ __device__ inline void fm_rescale(double *r, double unew, double uold) {
@@ -120,6 +128,9 @@ __host__ __device__ inline void fm_shift(double *m, double u, double x, double y
   m[F_XYZ] += m[F_XY] * z + m[F_XZ] * y + m[F_YZ] * x;
   /* the monopole, displaced from the new centre, feeds every higher order */
   const double M = m[F_M];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
   for (int k = F_XX; k < F_N; ++k) m[k] += M * f[k];
 }
 
@@ -138,6 +149,9 @@ __host__ __device__ inline void node_add_particle(MomentNode &n, double pm, doub
   fm_shift(n.f, n.radius, old[0] - n.cm[0], old[1] - n.cm[1], old[2] - n.cm[2]);
   double one[F_N];
   fm_point(one, pm, n.radius, px[0] - n.cm[0], px[1] - n.cm[1], px[2] - n.cm[2]);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
   for (int k = 0; k < F_N; ++k) n.f[k] += one[k];
 }
 
@@ -157,6 +171,9 @@ __host__ __device__ inline void node_add_node(MomentNode &n, const MomentNode &o
   for (int d = 0; d < 3; ++d) n.cm[d] = (m1 * n.cm[d] + o.mass * o.cm[d]) / n.mass;
   fm_shift(n.f, n.radius, old[0] - n.cm[0], old[1] - n.cm[1], old[2] - n.cm[2]);
   double g[F_N];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
   for (int k = 0; k < F_N; ++k) g[k] = o.f[k];
   fm_shift(g, o.radius, o.cm[0] - n.cm[0], o.cm[1] - n.cm[1], o.cm[2] - n.cm[2]);
   fm_scaled_add(n.f, n.radius, g, o.radius);
@@ -165,6 +182,9 @@ __host__ __device__ inline void node_add_node(MomentNode &n, const MomentNode &o
 __host__ __device__ inline void node_clear(MomentNode &n) {
   n.radius = n.soft = n.mass = 0.0;
   n.cm[0] = n.cm[1] = n.cm[2] = 0.0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
   for (int k = 0; k < F_N; ++k) n.f[k] = 0.0;
 }
 
@@ -241,23 +261,42 @@ __global__ void build_moments_level_kernel(const double *__restrict__ pos, const
                                            const int *__restrict__ child1, const int *__restrict__ firstPart,
                                            const int *__restrict__ lastPart, const double *__restrict__ geolo,
                                            const double *__restrict__ geohi, const double *__restrict__ boxlo,
-                                           const double *__restrict__ boxhi, int lo, int n,
+                                           const double *__restrict__ boxhi, int lo, int n, int numNodes,
                                            MomentNode *__restrict__ work, real *__restrict__ out,
                                            double *__restrict__ out64) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int i = lo + t;
+  /* the per-node work records are kept component-major (work[k * numNodes + node]): neighbouring
+   * threads own neighbouring nodes and their children are neighbours one level down, so every
+   * load and store of a component is a run of consecutive doubles instead of a 224-byte stride */
+  double *w = reinterpret_cast<double *>(work);
+  constexpr int kWords = (int)(sizeof(MomentNode) / sizeof(double));
   MomentNode m;
   const int c0 = child0[i], c1 = child1[i];
   if (c0 < 0 && c1 < 0) {
     node_make_bucket(m, pos, mass, soft, firstPart[i], lastPart[i], geolo + 3 * i, geohi + 3 * i);
   } else {
     node_clear(m);
-    if (c0 >= 0) node_add_node(m, work[c0]);
-    if (c1 >= 0) node_add_node(m, work[c1]);
+    MomentNode o;
+    double *po = reinterpret_cast<double *>(&o);
+    if (c0 >= 0) {
+#pragma unroll
+      for (int k = 0; k < kWords; ++k) po[k] = w[(size_t)k * numNodes + c0];
+      node_add_node(m, o);
+    }
+    if (c1 >= 0) {
+#pragma unroll
+      for (int k = 0; k < kWords; ++k) po[k] = w[(size_t)k * numNodes + c1];
+      node_add_node(m, o);
+    }
     node_radius_from_box(m, boxlo + 3 * i, boxhi + 3 * i);
   }
-  work[i] = m;
+  {
+    const double *pm = reinterpret_cast<const double *>(&m);
+#pragma unroll
+    for (int k = 0; k < kWords; ++k) w[(size_t)k * numNodes + i] = pm[k];
+  }
   if (out) node_export(m, out + (size_t)i * 27);
   if (out64) node_export(m, out64 + (size_t)i * 27);
 }

@@ -494,8 +494,14 @@ def main():
     rs.timed(0, max(args.warmup, 3))
     use_graph = world == 1 and not args.no_graph
     if use_graph:
-        per_step = rs.capture()
-        rs.timed(0, 3, graph=True)
+        try:
+            per_step = rs.capture()
+            rs.timed(0, 3, graph=True)
+        except Exception as e:  # a capture that fails must not take the line down: launch eagerly
+            sys.stderr.write(f"CUDA graph capture failed ({e!r}); launching eagerly\n")
+            torch.cuda.synchronize()
+            use_graph = False
+    if use_graph:
         ms_total = rs.timed(args.steps, 0, graph=True)
         launches = per_step * args.steps
     else:

@@ -42,3 +42,24 @@ def bucket_range_by_starts(bucket_starts, n, rank, world):
     p0 = int(starts[b0]) if b0 < nb else n
     p1 = int(starts[b1]) if b1 < nb else n
     return b0, b1, p0, p1
+
+
+def bucket_range_by_active(bucket_starts, markers, n, rank, world):
+    """multistep form of bucket_range_by_starts (what RawParticleStep does on the device when rungs are
+    given): the cut points are the particles holding the r * nActive / world -th Ewald markers, so every
+    rank gets about the same number of ACTIVE particles.  markers: ascending tree-order indices of the
+    active particles.  Falls back to the particle-count rule when nothing is active."""
+    markers = np.asarray(markers)
+    n_act = len(markers)
+    if n_act == 0:
+        return bucket_range_by_starts(bucket_starts, n, rank, world)
+    starts = np.asarray(bucket_starts)
+    nb = len(starts)
+    at0 = min(n_act - 1, rank * n_act // world)
+    at1 = min(n_act - 1, (rank + 1) * n_act // world)
+    b0 = 0 if rank == 0 else int(np.searchsorted(starts, markers[at0], side="left"))
+    b1 = nb if rank == world - 1 else int(np.searchsorted(starts, markers[at1], side="left"))
+    p0 = int(starts[b0]) if b0 < nb else n
+    p1 = int(starts[b1]) if b1 < nb else n
+    return b0, b1, p0, p1
+

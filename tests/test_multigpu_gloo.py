@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from changa_b200.multigpu import shard_rows, gather_rows, bucket_cuts_by_particles, bucket_range_by_starts
+from changa_b200.multigpu import (shard_rows, gather_rows, bucket_cuts_by_particles, bucket_range_by_starts,
+                                  bucket_range_by_active)
 
 
 def _free_port():
@@ -87,3 +88,27 @@ def test_bucket_ranges_by_starts_tile_the_box():
         for b0, b1, p0, p1 in r:
             assert p1 - p0 == int(sizes[b0:b1].sum())
             assert abs((p1 - p0) - n / w) <= 12
+
+
+def test_bucket_ranges_by_active_particles():
+    """multistep cut rule: contiguous, disjoint, covering, and balanced in ACTIVE particles even when the
+    active set is concentrated in a corner of the SFC order"""
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(1, 13, 5000)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    n = int(sizes.sum())
+    active = np.zeros(n, dtype=bool)
+    active[: n // 5] = rng.random(n // 5) < 0.9      # dense region: most of the active particles
+    active[n // 5:] = rng.random(n - n // 5) < 0.02
+    markers = np.nonzero(active)[0]
+    for w in (1, 2, 3, 8):
+        r = [bucket_range_by_active(starts, markers, n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == len(sizes) and r[0][2] == 0 and r[-1][3] == n
+        for a, b in zip(r, r[1:]):
+            assert a[1] == b[0] and a[3] == b[2]
+        counts = [int(active[p0:p1].sum()) for _, _, p0, p1 in r]
+        assert sum(counts) == len(markers)
+        assert max(counts) - min(counts) <= 2 * 12 + 1
+    # nothing active: the particle-count rule
+    assert bucket_range_by_active(starts, [], n, 1, 2) == bucket_range_by_starts(starts, n, 1, 2)
+

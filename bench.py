@@ -525,13 +525,19 @@ def main():
         ref = ForceStep(hc, wl)
         want = ref.run().copy()
         ref.free()
-        fs = ShardedForceStep(hc, wl, torch, dist, rank, world)
-        got = fs.run()
-        same = torch.tensor([1 if np.array_equal(got[fs.p0:fs.p1], want[fs.p0:fs.p1]) else 0], device="cuda")
+        fs, good = None, 0
+        try:
+            fs = ShardedForceStep(hc, wl, torch, dist, rank, world)
+            got = fs.run()
+            good = 1 if np.array_equal(got[fs.p0:fs.p1], want[fs.p0:fs.p1]) else 0
+        except Exception as e:
+            sys.stderr.write(f"rank {rank}: sharded step failed: {e!r}\n")
+        same = torch.tensor([good], device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)  # the ranks decide together: the sharded step holds collectives
         if int(same.item()) == 0:
-            sys.stderr.write(f"rank {rank}: sharded upload differs from the full upload somewhere; timing the full upload\n")
-            fs.free()
+            sys.stderr.write(f"rank {rank}: sharded upload unusable or different somewhere; timing the full upload\n")
+            if fs is not None:
+                fs.free()
             fs = ForceStep(hc, wl)
         else:
           e2e_how = ("wall clock around ShardedForceStep.run(): slice upload from pinned host buffers, packed arrays "

@@ -181,6 +181,39 @@ def test_resident_path_equals_abi_path(hc):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_resident_steps_share_one_self_resetting_counter(hc):
+    """the device-pointer list launches draw buckets from one counter per stream that every kernel
+    leaves at zero (grab_bucket): workloads with different bucket counts alternate on ONE stream,
+    eagerly and as a replayed CUDA graph, and every step gives the bits of the host-buffer path"""
+    import torch
+    from changa_b200.hostcuda import ForceStep
+    from changa_b200.workloads import config_workload, random_workload
+    import bench
+    wls = [config_workload("cube300", n=10 ** 3), random_workload(seed=11, n_buckets=37, max_bucket=12),
+           random_workload(seed=12, n_buckets=700, max_bucket=8)]
+    want = []
+    for wl in wls:
+        step = ForceStep(hc, wl)
+        try:
+            want.append(step.run().copy())
+        finally:
+            step.free()
+    steps = [bench.ResidentStep(hc, wl, torch, None, 0, 1) for wl in wls]
+    for rs in steps[1:]:  # all on the first one's stream
+        rs.stream, rs.ext = steps[0].stream, steps[0].ext
+    with torch.cuda.stream(steps[0].ext):
+        for k in (0, 1, 2, 1, 0, 2, 2):
+            steps[k].step()
+            torch.cuda.synchronize()
+            assert np.array_equal(steps[k].vars.cpu().numpy().view(np.uint32), want[k].view(np.uint32)), k
+    steps[1].capture()
+    with torch.cuda.stream(steps[0].ext):
+        for k in (1, 0, 1, 2, 1):
+            (steps[1].graph.replay if k == 1 else steps[k].step)()
+            torch.cuda.synchronize()
+            assert np.array_equal(steps[k].vars.cpu().numpy().view(np.uint32), want[k].view(np.uint32)), k
+
+
 # ---------------------------------------------------------------------------------------
 # the other entry points, the FP64 build, the device moment build
 # ---------------------------------------------------------------------------------------

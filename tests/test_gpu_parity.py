@@ -626,3 +626,23 @@ def test_collapse_fixture_in_double(hc64):
     med, worst = compare(got, oracle_forces_tree(wl, np.float64), median_tol=1e-9, max_tol=1e-6, pot_tol=1e-9,
                          floor_frac=0.1)
     assert med < 1e-9
+
+
+def test_king_energy_on_the_gpu_matches_the_reference_golden_log(hc):
+    """config 1 through the C ABI on the reference's own particle set: the potential energy of the
+    CUDA path against the t = 0 line of teststep/pkdtest.log (see tests/test_oracle_pins.py)"""
+    import json
+    import os
+    from changa_b200.hostcuda import ForceStep
+    from changa_b200.workloads import config_workload
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "king_energy.json")))
+    wl = config_workload("king")
+    step = ForceStep(hc, wl)
+    try:
+        v = step.run().copy()
+    finally:
+        step.free()
+    U = 0.5 * float(np.sum(np.asarray(wl["parts"][:, 0], dtype=np.float64) * np.asarray(v[:, 3], dtype=np.float64)))
+    assert abs(U - g["U"]) < 2e-5 * abs(g["U"])
+    assert abs(U + g["kinetic_from_file"] - g["E"]) < g["makefile_tolerance_on_E"] / 10
+

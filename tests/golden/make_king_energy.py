@@ -3,7 +3,7 @@ king_soft.bin, theta 0.7; teststep/Makefile:3-8 accepts a ChaNGa run whose total
 -32.19) together with the kinetic energy of the file's velocities, which the position fixture does not hold.
 Run in the container that has the reference:
 
-    python tests/golden/make_king_energy.py        -> tests/golden/king_energy.json
+    python tests/golden/make_king_energy.py        -> tests/golden/king_energy.json, king_velocities.npz
 """
 import json
 import os
@@ -27,6 +27,8 @@ def main():
            "time": float(row[0]), "E": float(row[2]), "T": float(row[3]), "U": float(row[4]),
            "kinetic_from_file": kinetic, "n": int(nbodies),
            "makefile_tolerance_on_E": 0.005}
+    # the velocities themselves, for tools/teststep_energy.py on machines without the reference
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "king_velocities.npz"), vel=a[:, 4:7].astype(np.float32))
     dst = os.path.join(ROOT, "tests", "golden", "king_energy.json")
     json.dump(out, open(dst, "w"), indent=1)
     print(out)

@@ -221,6 +221,112 @@ __device__ __forceinline__ void pc_pair(const real *__restrict__ c, real ccx, re
   idt = rmax(idt, (p.w + M) * d3);
 }
 
+/* The same evaluation for N targets at once, statement by statement: the N dependency chains are
+ * interleaved in program order, which is what a latency-bound schedule needs (pc_pair called N
+ * times in a row is scheduled mostly one after the other).  Identical arithmetic to pc_pair. */
+template <int N>
+__device__ __forceinline__ void pc_pairN(const real *__restrict__ c, real ccx, real ccy, real ccz,
+                                         const real4 *p, real *ax, real *ay, real *az, real *pot, real *idt) {
+  const real third = real(1.0 / 3.0);
+  real rx[N], ry[N], rz[N], d[N], d2[N], X[N], Y[N], Z[N];
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    rx[t] = p[t].x - ccx; ry[t] = p[t].y - ccy; rz[t] = p[t].z - ccz;
+  }
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    const real rsq = fma(rz[t], rz[t], fma(ry[t], ry[t], rx[t] * rx[t]));
+    const real r = rsqrt_dev(rsq);
+    d[t] = (rsq != real(0)) ? r : real(0);
+  }
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    d2[t] = d[t] * d[t];
+    const real s = c[PK_RADIUS] * d2[t];
+    X[t] = rx[t] * s; Y[t] = ry[t] * s; Z[t] = rz[t] * s;
+  }
+  real xx[N], yy[N], zz[N], xy[N], xz[N], yz[N], xxx[N], xxz[N], yyy[N], yyz[N], xxy[N], xyy[N], xyz[N];
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    xx[t] = (real(0.5) * X[t]) * X[t]; yy[t] = (real(0.5) * Y[t]) * Y[t]; zz[t] = (real(0.5) * Z[t]) * Z[t];
+    xy[t] = X[t] * Y[t]; xz[t] = X[t] * Z[t]; yz[t] = Y[t] * Z[t];
+  }
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    xxx[t] = X[t] * fma(third, xx[t], -zz[t]);
+    xxz[t] = Z[t] * fma(-third, zz[t], xx[t]);
+    yyy[t] = Y[t] * fma(third, yy[t], -zz[t]);
+    yyz[t] = Z[t] * fma(-third, zz[t], yy[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    xx[t] -= zz[t]; yy[t] -= zz[t];
+    xxy[t] = Y[t] * xx[t]; xyy[t] = X[t] * yy[t]; xyz[t] = xy[t] * Z[t];
+  }
+  real t4x[N], t4y[N], t4z[N], t3x[N], t3y[N], t3z[N];
+#define CB200_ALL(stmt) _Pragma("unroll") for (int t = 0; t < N; ++t) { stmt; }
+  /* hexadecapole */
+  CB200_ALL(t4x[t] = c[PK_XXXX] * xxx[t])
+  CB200_ALL(t4y[t] = c[PK_XYYY] * xyy[t])
+  CB200_ALL(t4z[t] = c[PK_XXXZ] * xxx[t])
+  CB200_ALL(t4x[t] = fma(c[PK_XYYY], yyy[t], t4x[t]))
+  CB200_ALL(t4y[t] = fma(c[PK_XXXY], xxx[t], t4y[t]))
+  CB200_ALL(t4z[t] = fma(c[PK_YYYZ], yyy[t], t4z[t]))
+  CB200_ALL(t4x[t] = fma(c[PK_XXXY], xxy[t], t4x[t]))
+  CB200_ALL(t4y[t] = fma(c[PK_YYYY], yyy[t], t4y[t]))
+  CB200_ALL(t4z[t] = fma(c[PK_XXYZ], xxy[t], t4z[t]))
+  CB200_ALL(t4x[t] = fma(c[PK_XXXZ], xxz[t], t4x[t]))
+  CB200_ALL(t4y[t] = fma(c[PK_YYYZ], yyz[t], t4y[t]))
+  CB200_ALL(t4z[t] = fma(c[PK_XYYZ], xyy[t], t4z[t]))
+  CB200_ALL(t4x[t] = fma(c[PK_XXYY], xyy[t], t4x[t]))
+  CB200_ALL(t4y[t] = fma(c[PK_XXYY], xxy[t], t4y[t]))
+  CB200_ALL(t4z[t] = fma(-c[PK_XXXX], xxz[t], t4z[t]))
+  CB200_ALL(t4x[t] = fma(c[PK_XXYZ], xyz[t], t4x[t]))
+  CB200_ALL(t4y[t] = fma(c[PK_XXYZ], xxz[t], t4y[t]))
+  CB200_ALL(t4z[t] = fma(-c[PK_XY3S], xyz[t], t4z[t]))
+  CB200_ALL(t4x[t] = fma(c[PK_XYYZ], yyz[t], t4x[t]))
+  CB200_ALL(t4y[t] = fma(c[PK_XYYZ], xyz[t], t4y[t]))
+  CB200_ALL(t4z[t] = fma(-c[PK_YYYY], yyz[t], t4z[t]))
+  CB200_ALL(t4z[t] = fma(-c[PK_XXYY], xxz[t] + yyz[t], t4z[t]))
+  /* octupole */
+  CB200_ALL(t3x[t] = c[PK_XXX] * xx[t])
+  CB200_ALL(t3y[t] = c[PK_XYY] * xy[t])
+  CB200_ALL(t3z[t] = c[PK_XZZ] * xz[t])
+  CB200_ALL(t3x[t] = fma(c[PK_XYY], yy[t], t3x[t]))
+  CB200_ALL(t3y[t] = fma(c[PK_XXY], xx[t], t3y[t]))
+  CB200_ALL(t3z[t] = fma(c[PK_YZZ], yz[t], t3z[t]))
+  CB200_ALL(t3x[t] = fma(c[PK_XXY], xy[t], t3x[t]))
+  CB200_ALL(t3y[t] = fma(c[PK_YYY], yy[t], t3y[t]))
+  CB200_ALL(t3z[t] = fma(c[PK_XXZ], xx[t], t3z[t]))
+  CB200_ALL(t3x[t] = fma(c[PK_XXZ], xz[t], t3x[t]))
+  CB200_ALL(t3y[t] = fma(c[PK_YYZ], yz[t], t3y[t]))
+  CB200_ALL(t3z[t] = fma(c[PK_YYZ], yy[t], t3z[t]))
+  CB200_ALL(t3x[t] = fma(c[PK_XYZ], yz[t], t3x[t]))
+  CB200_ALL(t3y[t] = fma(c[PK_XYZ], xz[t], t3y[t]))
+  CB200_ALL(t3z[t] = fma(c[PK_XYZ], xy[t], t3z[t]))
+#undef CB200_ALL
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    const real s4 = fma(t4z[t], Z[t], fma(t4y[t], Y[t], t4x[t] * X[t]));
+    const real s3 = fma(t3z[t], Z[t], fma(t3y[t], Y[t], t3x[t] * X[t]));
+    /* quadrupole */
+    const real t2x = fma(c[PK_XZ], Z[t], fma(c[PK_XY], Y[t], c[PK_XX] * X[t]));
+    const real t2y = fma(c[PK_YZ], Z[t], fma(c[PK_XY], X[t], c[PK_YY] * Y[t]));
+    const real t2z = fma(c[PK_YZ], Y[t], fma(c[PK_XZ], X[t], c[PK_ZZ] * Z[t]));
+    const real s2 = fma(t2z, Z[t], fma(t2y, Y[t], t2x * X[t]));
+    const real M = c[PK_MASS];
+    const real phi = fma(real(0.25), s4, fma(third, s3, fma(real(0.5), s2, M)));
+    const real G = fma(real(2.25), s4, fma(real(7.0 / 3.0), s3, fma(real(2.5), s2, M)));
+    const real d3 = d2[t] * d[t];
+    const real R = c[PK_RADIUS];
+    pot[t] = fma(-d[t], phi, pot[t]);
+    ax[t] = fma(d3, fma(-rx[t], G, R * (t2x + t3x[t] + t4x[t])), ax[t]);
+    ay[t] = fma(d3, fma(-ry[t], G, R * (t2y + t3y[t] + t4y[t])), ay[t]);
+    az[t] = fma(d3, fma(-rz[t], G, R * (t2z + t3z[t] + t4z[t])), az[t]);
+    idt[t] = rmax(idt[t], (p[t].w + M) * d3);
+  }
+}
+
 /* xor-butterfly over the warp; every lane ends with the same totals */
 __device__ __forceinline__ void warp_reduce5(real &a0, real &a1, real &a2, real &a3, real &a4) {
 #pragma unroll
@@ -253,7 +359,11 @@ constexpr size_t cell_list_smem_bytes() {
 }
 
 /* ---------------------------------------------------------- particle-cell */
-template <int PB, int MINB>
+/* PAIR: two targets per bounds check, so that their (independent) evaluations sit in one basic block and
+ * ptxas can interleave them -- the FP64 build is latency-bound at 2 resident warps per scheduler
+ * (DESIGN 4.4).  With an odd particle count the second evaluation of the last pair meets a stale target;
+ * its sums are never reduced.  Experimental: selected by CB200_PC64_VARIANT, not the default. */
+template <int PB, int MINB, bool PAIR = false>
 __global__ void __launch_bounds__(kListWarps * 32, MINB)
 cell_list_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
                  const PackedCell *__restrict__ cells, const ILCell *__restrict__ list,
@@ -308,11 +418,22 @@ cell_list_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restr
           const real ccx = fma(real(replica_x(cur.offsetID)), fperiod, c[PK_CX]);
           const real ccy = fma(real(replica_y(cur.offsetID)), fperiod, c[PK_CY]);
           const real ccz = fma(real(replica_z(cur.offsetID)), fperiod, c[PK_CZ]);
+          if constexpr (PAIR) {
+            static_assert(!PAIR || PB % 2 == 0, "pairs of targets");
 #pragma unroll
-          for (int j = 0; j < PB; ++j) {
-            if (j < np) {
-              const real4 p = sp[j];
-              pc_pair(c, ccx, ccy, ccz, p, ax[j], ay[j], az[j], pot[j], idt[j]);
+            for (int j = 0; j < PB; j += 2) {
+              if (j < np) {
+                const real4 pq[2] = {sp[j], sp[j + 1]};
+                pc_pairN<2>(c, ccx, ccy, ccz, pq, ax + j, ay + j, az + j, pot + j, idt + j);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+              if (j < np) {
+                const real4 p = sp[j];
+                pc_pair(c, ccx, ccy, ccz, p, ax[j], ay[j], az[j], pot[j], idt[j]);
+              }
             }
           }
         }

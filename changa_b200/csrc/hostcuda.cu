@@ -341,13 +341,13 @@ static int list_grid(int nBuckets, int ctasPerSm) {
   return need < cap ? need : cap;
 }
 
-template <int PB, int MINB>
+template <int PB, int MINB, bool PAIR = false>
 static void launch_cell_list(const PackedPart *parts, VariablePartData *vars, const PackedCell *cells,
                              const ILCell *list, const int *markers, const int *starts,
                              const int *sizes, int nBuckets, real fperiod, unsigned *counter,
                              cudaStream_t stream) {
-  static int ctas = resident_ctas(cell_list_kernel<PB, MINB>, cell_list_smem_bytes<PB>());
-  cell_list_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, cell_list_smem_bytes<PB>(), stream>>>(
+  static int ctas = resident_ctas(cell_list_kernel<PB, MINB, PAIR>, cell_list_smem_bytes<PB>());
+  cell_list_kernel<PB, MINB, PAIR><<<list_grid(nBuckets, ctas), kListWarps * 32, cell_list_smem_bytes<PB>(), stream>>>(
       parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter);
   cudaChk(cudaPeekAtLastError());
 }
@@ -405,6 +405,12 @@ static void dispatch_cell_list(int maxBucket, const PackedPart *parts, VariableP
     launch_cell_list<12, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   else if (variant == 3)
     launch_cell_list<4, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else if (variant == 4) /* 4-6: two targets per basic block (not measured yet) */
+    launch_cell_list<4, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else if (variant == 5)
+    launch_cell_list<6, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else if (variant == 6)
+    launch_cell_list<8, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   else
     launch_cell_list<8, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
 #else

@@ -233,6 +233,11 @@ class RawParticleStep:
         self.info = None
         self._ew = None
 
+    def update_positions(self, pos):
+        """new positions (caller order) for the next run(): an integrator's drift.  world == 1 only."""
+        assert self.world == 1
+        self.h["rec"][: self.n, :3] = self.torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float64))
+
     def run(self, phases=None, keep_tree=False, count_pairs=False):
         """count_pairs: also leave {pc_pairs, pp_pairs} (sum over buckets of list length x bucket
         size, as Compute.cpp:1643-1651 counts interactions) in self.info"""

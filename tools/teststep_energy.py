@@ -56,15 +56,17 @@ class GpuEngine:
         from changa_b200.hostcuda import HostCUDA
         self.hc = HostCUDA(double=False, device=0)
 
+        self.st = None
+
     def forces(self, pos, mass, soft):
         from changa_b200.device_step import RawParticleStep
-        ext = float(np.abs(pos).max()) * 1.0001
-        st = RawParticleStep(self.hc, pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, ewald=None,
-                             root_lo=(-ext,) * 3, root_hi=(ext,) * 3)
-        try:
-            return np.asarray(st.run(), dtype=np.float64).copy()
-        finally:
-            st.free()
+        if self.st is None:  # one step object for the whole run; the root box leaves room for the drift
+            ext = float(np.abs(pos).max()) * 1.5
+            self.st = RawParticleStep(self.hc, pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, ewald=None,
+                                      root_lo=(-ext,) * 3, root_hi=(ext,) * 3)
+        else:
+            self.st.update_positions(pos)
+        return np.asarray(self.st.run(), dtype=np.float64).copy()
 
 
 def energy(mass, vel, f):

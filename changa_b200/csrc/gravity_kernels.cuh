@@ -795,7 +795,6 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
 
         if (cur.index >= 0) {
           float c[kCellReals];
-#pragma unroll
           const unsigned row = rowAddr + boff;
 #pragma unroll
           for (int j = 0; j < 8; ++j) unpack_piece(lds128(row ^ (j * 16)), c + j * 4);

@@ -31,6 +31,7 @@
 
 #include "../../include/changa_b200_api.h"
 #include "gravity_kernels.cuh"
+#include "pp_stream_kernel.cuh"
 #include "moments_build.cuh"
 #include "walk_kernels.cuh"
 #include "tree_kernels.cuh"
@@ -73,7 +74,7 @@ static void hapiAddCallback(cudaStream_t stream, void *cb) {
 
 /* --------------------------------------------------------- per-device state */
 struct DeviceInfo {
-  bool ready = false;
+  std::atomic<bool> ready{false};
   int sms = 0;
 };
 static DeviceInfo g_dev[64];
@@ -84,9 +85,9 @@ static const DeviceInfo &device_info() {
   cudaChk(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) dev = 0;
   DeviceInfo &d = g_dev[dev];
-  if (!d.ready) {
+  if (!d.ready.load(std::memory_order_acquire)) {
     std::lock_guard<std::mutex> lock(g_devMutex);
-    if (!d.ready) {
+    if (!d.ready.load(std::memory_order_relaxed)) {
       cudaChk(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
       cudaMemPool_t pool;
       cudaChk(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -96,7 +97,7 @@ static const DeviceInfo &device_info() {
        * completed: never by making the allocating (copy) stream wait for a kernel */
       int off = 0;
       cudaChk(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
-      d.ready = true;
+      d.ready.store(true, std::memory_order_release);
     }
   }
   return d;
@@ -123,16 +124,18 @@ static std::mutex g_blockMutex;
 static std::unordered_map<BlockKey, std::vector<void *>, BlockKeyHash> g_blockFree;
 struct BlockInfo { size_t bytes; cudaStream_t stream; };
 static std::unordered_map<void *, BlockInfo> g_blockSize; /* large blocks handed out by pool_alloc */
-static size_t g_blockCached = 0, g_blockCap = 0;
+static size_t g_blockCached[64], g_blockCap[64]; /* per device (indices as g_dev) */
 constexpr size_t kBlockCacheMin = 1u << 20;
 
 static void block_cache_flush_locked(int dev, cudaStream_t only, bool matchStream) {
   for (auto it = g_blockFree.begin(); it != g_blockFree.end();) {
     if (it->first.dev == dev && (!matchStream || it->first.stream == only)) {
       for (void *p : it->second) {
-        /* the stream may be gone (stream_destroy) or about to be: cudaFree synchronises */
-        cudaChk(matchStream ? cudaFree(p) : cudaFreeAsync(p, it->first.stream));
-        g_blockCached -= it->first.bytes;
+        /* the remembered stream may be gone (a caller-owned stream destroyed without
+         * cb200_stream_destroy) or about to be: cudaFree synchronises instead of naming it */
+        (void)matchStream;
+        cudaChk(cudaFree(p));
+        g_blockCached[it->first.dev & 63] -= it->first.bytes;
       }
       it = g_blockFree.erase(it);
     } else {
@@ -153,7 +156,7 @@ static void *pool_alloc(size_t bytes, cudaStream_t stream) {
     if (it != g_blockFree.end() && !it->second.empty()) {
       p = it->second.back();
       it->second.pop_back();
-      g_blockCached -= bytes;
+      g_blockCached[dev & 63] -= bytes;
       g_blockSize[p] = BlockInfo{bytes, stream};
       return p;
     }
@@ -182,15 +185,16 @@ static void pool_free(void *p, cudaStream_t stream) {
       if (!sameStream || bytes < kBlockCacheMin) goto to_driver;
       int dev = 0;
       cudaChk(cudaGetDevice(&dev));
-      if (g_blockCap == 0) {
+      size_t &cached = g_blockCached[dev & 63], &cap = g_blockCap[dev & 63];
+      if (cap == 0) {
         size_t freeB = 0, totalB = 0;
         cudaChk(cudaMemGetInfo(&freeB, &totalB));
-        g_blockCap = totalB / 2;
+        cap = totalB / 2;
       }
-      if (g_blockCached + bytes > g_blockCap) block_cache_flush_locked(dev, nullptr, false);
-      if (g_blockCached + bytes <= g_blockCap) {
+      if (cached + bytes > cap) block_cache_flush_locked(dev, nullptr, false);
+      if (cached + bytes <= cap) {
         g_blockFree[BlockKey{dev, stream, bytes}].push_back(p);
-        g_blockCached += bytes;
+        cached += bytes;
         return;
       }
     }
@@ -327,12 +331,22 @@ struct TapScope {
 };
 
 /* ---------------------------------------------------------- kernel launchers */
+/* resident CTAs per SM of a list kernel, and the opt-in to its dynamic shared memory: both are
+ * per-device facts (the attribute is set on the current device's copy of the function), so they are
+ * cached per (kernel instantiation, device) -- a process may drive several GPUs (cb200_set_device) */
+struct CtaCache { std::atomic<int> n[64]; };
 template <typename K>
-static int resident_ctas(K kernel, size_t smem) {
-  int n = 0;
+static int resident_ctas(CtaCache &cache, K kernel, size_t smem) {
+  int dev = 0;
+  cudaChk(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache.n[dev].load(std::memory_order_acquire);
+  if (n > 0) return n;
   cudaChk(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaChk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kListWarps * 32, smem));
-  return n > 0 ? n : 1;
+  n = n > 0 ? n : 1;
+  cache.n[dev].store(n, std::memory_order_release);
+  return n;
 }
 
 static int list_grid(int nBuckets, int ctasPerSm) {
@@ -346,7 +360,8 @@ static void launch_cell_list(const PackedPart *parts, VariablePartData *vars, co
                              const ILCell *list, const int *markers, const int *starts,
                              const int *sizes, int nBuckets, real fperiod, unsigned *counter,
                              cudaStream_t stream) {
-  static int ctas = resident_ctas(cell_list_kernel<PB, MINB, PAIR>, cell_list_smem_bytes<PB>());
+  static CtaCache cache;
+  const int ctas = resident_ctas(cache, cell_list_kernel<PB, MINB, PAIR>, cell_list_smem_bytes<PB>());
   cell_list_kernel<PB, MINB, PAIR><<<list_grid(nBuckets, ctas), kListWarps * 32, cell_list_smem_bytes<PB>(), stream>>>(
       parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter);
   cudaChk(cudaPeekAtLastError());
@@ -358,7 +373,8 @@ static void launch_cell_list_x2(const PackedPart *parts, VariablePartData *vars,
                                 const ILCell *list, const int *markers, const int *starts,
                                 const int *sizes, int nBuckets, real fperiod, unsigned *counter,
                                 cudaStream_t stream) {
-  static int ctas = resident_ctas(cell_list_x2_kernel<PB, MINB>, cell_list_x2_smem_bytes<PB>());
+  static CtaCache cache;
+  const int ctas = resident_ctas(cache, cell_list_x2_kernel<PB, MINB>, cell_list_x2_smem_bytes<PB>());
   cell_list_x2_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, cell_list_x2_smem_bytes<PB>(), stream>>>(
       parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter);
   cudaChk(cudaPeekAtLastError());
@@ -370,7 +386,8 @@ static void launch_part_list(const PackedPart *parts, VariablePartData *vars, co
                              const ILCell *list, const int *markers, const int *starts,
                              const int *sizes, int nBuckets, real fperiod, unsigned *counter,
                              cudaStream_t stream) {
-  static int ctas = resident_ctas(part_list_kernel<PB, MINB>, part_list_smem_bytes<PB>());
+  static CtaCache cache;
+  const int ctas = resident_ctas(cache, part_list_kernel<PB, MINB>, part_list_smem_bytes<PB>());
   part_list_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, part_list_smem_bytes<PB>(), stream>>>(
       parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter);
   cudaChk(cudaPeekAtLastError());
@@ -382,8 +399,23 @@ static void launch_part_list_x2(const PackedPart *parts, VariablePartData *vars,
                                 const ILCell *list, const int *markers, const int *starts,
                                 const int *sizes, int nBuckets, real fperiod, unsigned *counter,
                                 cudaStream_t stream) {
-  static int ctas = resident_ctas(part_list_x2_kernel<PB, MINB>, part_list_x2_smem_bytes<PB>());
+  static CtaCache cache;
+  const int ctas = resident_ctas(cache, part_list_x2_kernel<PB, MINB>, part_list_x2_smem_bytes<PB>());
   part_list_x2_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, part_list_x2_smem_bytes<PB>(), stream>>>(
+      parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter);
+  cudaChk(cudaPeekAtLastError());
+}
+#endif
+
+#ifndef CUDA_USE_DOUBLE
+template <int PB, int MINB>
+static void launch_part_list_stream(const PackedPart *parts, VariablePartData *vars, const PackedPart *sources,
+                                    const ILCell *list, const int *markers, const int *starts,
+                                    const int *sizes, int nBuckets, real fperiod, unsigned *counter,
+                                    cudaStream_t stream) {
+  static CtaCache cache;
+  const int ctas = resident_ctas(cache, part_list_stream_kernel<PB, MINB>, part_list_stream_smem_bytes<PB>());
+  part_list_stream_kernel<PB, MINB><<<list_grid(nBuckets, ctas), kListWarps * 32, part_list_stream_smem_bytes<PB>(), stream>>>(
       parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter);
   cudaChk(cudaPeekAtLastError());
 }
@@ -447,14 +479,24 @@ static void dispatch_part_list(int maxBucket, const PackedPart *parts, VariableP
       launch_part_list<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
     else
       launch_part_list<16, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-  } else if (maxBucket <= 8) {
-    launch_part_list_x2<8, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   } else {
-    static const int variant = getenv("CB200_PP_VARIANT") ? atoi(getenv("CB200_PP_VARIANT")) : 0; /* tuning switch */
-    if (variant == 1)
-      launch_part_list_x2<12, 3>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-    else
-      launch_part_list_x2<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    /* CB200_PP_VARIANT: 0 = part_list_stream_kernel at 4 CTAs/SM (default), 3 = the same at 3 CTAs/SM;
+     * 1/2 = the round-1 part_list_x2_kernel (A/B) */
+    static const int variant = getenv("CB200_PP_VARIANT") ? atoi(getenv("CB200_PP_VARIANT")) : 0;
+    if (variant == 1 || variant == 2) {
+      if (maxBucket <= 8)
+        launch_part_list_x2<8, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+      else if (variant == 1)
+        launch_part_list_x2<12, 3>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+      else
+        launch_part_list_x2<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    } else if (maxBucket <= 8) {
+      launch_part_list_stream<8, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    } else if (variant == 3) {
+      launch_part_list_stream<12, 3>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    } else {
+      launch_part_list_stream<12, 4>(parts, vars, sources, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+    }
   }
 #endif
 }

@@ -14,6 +14,7 @@ class DeviceTreeStep:
         """tree: changa_b200.tree.Tree (host-built topology).  ewald: None | dict(dEwCut, dEwhCut).
         rung (one byte per particle, TREE order) + active_rung: multistep step, see RawParticleStep."""
         import torch
+        assert hc.L.cb200_real_bytes() == 4, "DeviceTreeStep holds float32 device buffers: use the float build"
         self.torch, self.hc, self.t = torch, hc, tree
         self.theta, self.nrep, self.period = float(theta), int(n_replicas), float(period)
         self.ewald = ewald
@@ -195,6 +196,7 @@ class RawParticleStep:
         evaluates and returns only its own contiguous SFC range of buckets (equal particle counts;
         accelerations never leave the owning GPU).  run() then returns (caller indices, rows)."""
         import torch
+        assert hc.L.cb200_real_bytes() == 4, "RawParticleStep holds float32 device buffers: use the float build"
         self.torch, self.hc = torch, hc
         self.dist, self.rank, self.world = dist, int(rank), int(world)
         self.theta, self.nrep, self.period = float(theta), int(n_replicas), float(period)

@@ -273,7 +273,10 @@ class ForceStep:
     """DataManager + TreePiece for one force evaluation of one workload (a dict, see
     changa_b200.workloads): every call below is one the reference's host code makes."""
 
-    def __init__(self, hc, wl, n_streams=1):
+    def __init__(self, hc, wl):
+        """All requests of the step go on ONE stream, as every request of a TreePiece does in the
+        reference (TreePiece.cpp:5380): the list kernels accumulate into the particle rows with plain
+        read-modify-write, so requests that touch the same buckets must be ordered."""
         self.hc, self.wl = hc, wl
         rt = hc.np_real
         self.np_ = len(wl["parts"])
@@ -293,7 +296,7 @@ class ForceStep:
             src = wl["softcell"][4]
             self.soft_src = hc.allocatePinnedHostMemory(src.shape, rt)
             self.soft_src.array[:] = src
-        self.streams = [hc.stream_create() for _ in range(n_streams)]
+        self.streams = [hc.stream_create()]
         self.ewald = None
         ew = wl.get("ewald")
         if ew:
@@ -394,7 +397,7 @@ class ShardedForceStep(ForceStep):
     equal ForceStep's bit for bit (bench.py checks it once per run)."""
 
     def __init__(self, hc, wl, torch, dist, rank, world):
-        super().__init__(hc, wl, n_streams=1)
+        super().__init__(hc, wl)
         from .multigpu import shard_rows
         self.torch, self.dist = torch, dist
         rt, L = hc.np_real, hc.L

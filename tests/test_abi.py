@@ -82,3 +82,31 @@ def test_partition_buckets_host_side():
         assert cuts[0] == 0 and cuts[-1] == 1000 and np.all(np.diff(cuts) > 0)
         loads = np.add.reduceat(cost, cuts[:-1])
         assert loads.max() / loads.mean() < 1.02
+
+
+LINK_TEST = os.path.join(ROOT, "oracle", "_ref", "abi_link_test")
+
+
+@pytest.mark.skipif(not os.path.exists(LINK_TEST), reason="oracle/_ref/abi_link_test not built (needs /root/reference)")
+def test_reference_headers_translation_unit_links_the_product_library():
+    """SURVEY row f4 surrogate, CPU half: oracle/abi_link_test.cu includes the REFERENCE's HostCUDA.h /
+    EwaldCUDA.h / cuda_typedef.h / CudaFunctions.h, static_asserts every field offset against
+    include/changa_b200_types.h (so the binary existing means the layouts agree), and its undefined
+    symbols -- the reference's mangled names -- resolve against libchanga_b200.so."""
+    out = subprocess.run(["nm", "-D", "--undefined-only", LINK_TEST], capture_output=True, text=True, check=True).stdout
+    wanted = {ln.split()[-1] for ln in out.splitlines() if ln.strip()} & set(REFERENCE_MANGLED)
+    assert len(wanted) >= 7, wanted
+    assert wanted <= exported(lib.library_path(False))
+    ldd = subprocess.run(["ldd", LINK_TEST], capture_output=True, text=True).stdout
+    assert "libchanga_b200.so" in ldd and "not found" not in ldd.split("libchanga_b200.so")[1].splitlines()[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(LINK_TEST), reason="oracle/_ref/abi_link_test not built (needs /root/reference)")
+def test_reference_headers_translation_unit_runs_requests_on_the_gpu():
+    """GPU half: the same binary uploads a tree, issues a Local cell request, a Local particle request,
+    EwaldHost and TransferParticleVarsBack through the reference-declared C++ functions, and checks the
+    result against a double direct sum and the five completion callbacks."""
+    r = subprocess.run([LINK_TEST], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "-> ok" in r.stdout, r.stdout

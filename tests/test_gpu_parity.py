@@ -397,6 +397,99 @@ def test_against_the_reference_cuda_kernels(hc):
     np.testing.assert_allclose(got[:, 4], ref[:, 4], rtol=1e-4)
 
 
+def test_ewald_against_the_reference_cuda_kernel(hc):
+    """Pin of row a4 to the reference itself: EwaldKernel (HostCUDA.cu:1958-2192) compiled unmodified
+    (oracle/_ref/libhostcuda_ref.so, -use_fast_math) vs ours vs the double CPU restatement of
+    Ewald.cpp:100-281, Ewald term only, on the reference's own cube300.tbin particle set.
+    Outside the radius where the reference GPU switches to its two-term hole series
+    (r^2 >= fInner2 = 1.1e-2 L^2, Ewald.cpp:516) both kernels evaluate the same recurrences: they must
+    agree to float rounding.  Inside it ours sums the series to rounding instead: there it
+    must be no further from the double oracle than the reference kernel is."""
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libhostcuda_ref.so not built")
+    from changa_b200.hostcuda import ForceStep
+    from changa_b200.workloads import config_workload
+    wl = dict(config_workload("cube300"), cell=None, part=None, softcell=None)
+    ew = wl["ewald"]
+    assert ew is not None
+    ref, _ = ref_cuda.RefCuda().force_step(wl)
+    step = ForceStep(hc, wl)
+    try:
+        got = step.run().copy()
+    finally:
+        step.free()
+    want = oracle_forces(wl)                      # CPU series radius 1.2e-3 L^2 (Ewald.cpp:119)
+    ref = ref.astype(np.float64)
+    got = got.astype(np.float64)
+    amag = np.linalg.norm(want[:, :3], axis=1)
+    live = amag > 0
+    scale = np.maximum(amag, 0.1 * np.sqrt((amag ** 2).mean()))   # near-cancelling particles: see compare()
+    err_ours = np.linalg.norm(got[:, :3] - want[:, :3], axis=1) / scale
+    err_ref = np.linalg.norm(ref[:, :3] - want[:, :3], axis=1) / scale
+    diff = np.linalg.norm(got[:, :3] - ref[:, :3], axis=1) / scale
+    L = float(ew["L"])
+    d = wl["parts"][:, 2:5] - np.asarray(ew["root"][3:6])
+    inside = (d ** 2).sum(1) < 1.1e-2 * L * L
+    assert inside.any() and (~inside).any()
+    out = live & ~inside
+    assert np.median(diff[out]) <= 1e-5, np.median(diff[out])
+    assert np.median(err_ours[out]) <= 1e-5 and np.median(err_ref[out]) <= 1e-4
+    assert np.median(err_ours[out]) <= 2 * np.median(err_ref[out]) + 1e-7
+    ins = live & inside
+    assert np.median(err_ours[ins]) <= np.median(err_ref[ins]) + 1e-7, (np.median(err_ours[ins]), np.median(err_ref[ins]))
+    assert err_ours[ins].max() <= max(err_ref[ins].max(), 1e-4), (err_ours[ins].max(), err_ref[ins].max())
+    # potential and the untouched dtGrav column (the Ewald kernels never write it)
+    pl = np.abs(want[:, 3]) > 0
+    assert np.median(np.abs(got[pl, 3] - want[pl, 3]) / np.abs(want[pl, 3])) <= 2e-5
+    assert np.all(got[:, 4] == 0) and np.all(ref[:, 4] == 0)
+
+
+def test_part_list_edge_cases(hc):
+    """p-p lists built by hand around what the streaming kernel special-cases: lists of 1, 32, 33, 64, 65,
+    128, 129 and 200 entries (chunk of 64, second half skipped when <= 32 remain, staging of the first
+    128), zero softening with the self pair in the list, distinct coincident particles, pairs inside
+    the spline radius (both branches), bucket sizes 1..12, replica offsets on some entries."""
+    from changa_b200.hostcuda import ForceStep
+    rng = np.random.default_rng(77)
+    lens = [1, 32, 33, 64, 65, 128, 129, 200, 7, 96, 0, 257]
+    sizes = np.array([1, 2, 3, 5, 8, 12, 11, 7, 12, 4, 6, 9], dtype=np.int32)
+    n = int(sizes.sum())
+    nsrc = 400
+    parts = np.zeros((n + nsrc, 5))
+    parts[:, 0] = rng.uniform(0.5, 1.5, n + nsrc) / (n + nsrc)
+    parts[:, 2:5] = rng.uniform(-0.5, 0.5, (n + nsrc, 3))
+    parts[:, 1] = rng.choice([0.0, 1e-3, 0.05, 0.2], n + nsrc)   # zero, small and large softening lengths
+    parts[n + 5, 2:5] = parts[3, 2:5]                             # a distinct particle exactly on a target
+    parts[n + 6, 2:5] = parts[4, 2:5] + 1e-4                      # and one deep inside a spline radius
+    parts[n + 6, 1] = 0.05
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32)
+    il, marks = [], [0]
+    for b, ln in enumerate(lens):
+        own = np.arange(starts[b], starts[b] + sizes[b])          # the bucket's own particles: self pairs
+        src = np.concatenate([own, rng.integers(0, n + nsrc, max(ln - len(own), 0))])[:ln]
+        if ln > 6:
+            src[5], src[6] = n + 5, n + 6
+        off = np.full(ln, 0xDB << 22, dtype=np.int64)
+        shifted = rng.random(ln) < (0.3 if b % 2 else 0.0)        # every other bucket has replica entries
+        code = lambda k: (int(k[0]) + 3) | ((int(k[1]) + 3) << 3) | ((int(k[2]) + 3) << 6)
+        for i in np.nonzero(shifted)[0]:
+            off[i] = code(rng.integers(-1, 2, 3)) << 22
+        il.append(np.stack([src, off], axis=1))
+        marks.append(marks[-1] + ln)
+    il = np.concatenate(il).astype(np.int32)
+    wl = {"name": "pp-edge", "parts": parts, "moments": np.zeros((1, 27)), "fperiod": 1.0,
+          "cell": None, "part": (il, np.array(marks, dtype=np.int32), starts, sizes), "softcell": None, "ewald": None}
+    step = ForceStep(hc, wl)
+    try:
+        got = step.run().copy()
+        again = step.run().copy()
+    finally:
+        step.free()
+    assert np.array_equal(got.view(np.uint32), again.view(np.uint32))
+    compare(got, oracle_forces(wl), max_tol=5e-4, floor_frac=0.05)
+
+
 # ---------------------------------------------------------------------------------------
 # interaction lists built on the device (SURVEY f1)
 # ---------------------------------------------------------------------------------------

@@ -1,0 +1,623 @@
+/* force_step.cuh -- the whole force step inside the library, one process per GPU (included by hostcuda.cu).
+ *
+ *   cb200_comm_*   one NCCL communicator per process (ncclCommInitRank from a 128-byte id the host
+ *                  program distributes however it likes: Charm++ broadcast, MPI, a file, a TCP store).
+ *                  NCCL is loaded with dlopen("libnccl.so.2") the first time a communicator is made, so
+ *                  a single-GPU host needs no NCCL at all.
+ *   cb200_step_*   the step: every rank holds 1/N of the {x, y, z, mass, soft} records of the box
+ *                  (rows [rank*chunk, (rank+1)*chunk) in the caller's order); ONE ncclAllGather over
+ *                  NVLink replicates them; every rank then builds the same tree and the same
+ *                  moments, walks, evaluates and returns only its own contiguous SFC range of buckets
+ *                  (owner computes: accelerations never leave the GPU that made them).  Keys, sort,
+ *                  topology, boxes, moments, interaction lists, p-c, p-p, softened cells and the Ewald
+ *                  sum all run on the device; the Ewald h-table is built on the device from the root
+ *                  moments (no root-moment round trip to the host).
+ *
+ * Reference analogues: DataManager::serializeLocalTree / transferLocalTree (DataManager.cpp:797-903),
+ * TreePiece::startGravity -> ListCompute::stateReady -> sendNodeInteractionsToGpu (Compute.cpp:1608-2253),
+ * TreePiece::EwaldGPU (Ewald.cpp:387-517), DataManager::transferParticleVarsBack (DataManager.cpp:962-996);
+ * one logical node per device as in DataManager.h:329-337.  The reference has no counterpart of the
+ * all-gather (it ships needed remote data through CkCache).
+ *
+ * Host synchronisations per step: one in the tree build (node / bucket / level counts), one in the walk
+ * (list lengths size the lists), one at the end; a multistep step adds one (active counts). */
+#ifndef CB200_FORCE_STEP_CUH
+#define CB200_FORCE_STEP_CUH
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+/* ------------------------------------------------------------------ NCCL */
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int *) = nullptr;
+};
+static NcclApi *nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    /* an NCCL already in the process (a host that links one, torch's bundled copy) is found by its soname */
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) {
+      fprintf(stderr, "changa_b200: multi-GPU requested but libnccl.so.2 cannot be loaded (%s)\n", dlerror());
+      abort();
+    }
+    auto sym = [&](const char *name) {
+      void *p = dlsym(api.handle, name);
+      if (!p) { fprintf(stderr, "changa_b200: %s missing from libnccl\n", name); abort(); }
+      return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+  });
+  return &api;
+}
+#define ncclChk(call)                                                                               \
+  do {                                                                                              \
+    ncclResult_t r_ = (call);                                                                       \
+    if (r_ != ncclSuccess) {                                                                        \
+      fprintf(stderr, "Fatal NCCL Error %s at %s:%d\n", nccl_api()->GetErrorString(r_), __FILE__, __LINE__); \
+      abort();                                                                                      \
+    }                                                                                               \
+  } while (0)
+
+struct cb200_comm {
+  ncclComm_t comm;
+  int rank, world;
+};
+
+/* ----------------------------------------------------------------- kernels */
+/* EwaldInit on the device (Ewald.cpp:285-375; ewald_setup.cuh is shared with the host build):
+ * thread 0 completes the root moments, then one thread per h-vector fills its table row. */
+__global__ void ewald_setup_kernel(const double *__restrict__ mom64, double L, double fEwCut, int nReps, int nEwh,
+                                   const int *__restrict__ hxyz, int first, int last, EwaldParams *__restrict__ out) {
+  __shared__ double comp[125];
+  __shared__ double momc[32];
+  if (threadIdx.x == 0) {
+    ewald_complete_moments(mom64, comp, momc);
+    EwaldReadOnlyData &ro = out->ro;
+    ro.mm.totalMass = (real)mom64[2];
+    ro.mm.cmx = (real)mom64[3]; ro.mm.cmy = (real)mom64[4]; ro.mm.cmz = (real)mom64[5];
+    real *q = reinterpret_cast<real *>(&ro.momcRoot);
+    for (int i = 0; i < 32; ++i) q[i] = (real)momc[i];
+    const double alpha = 2.0 / L;
+    ro.n = last - first + 1; ro.nReps = nReps; ro.nEwReps = (int)ceil(fEwCut); ro.nEwhLoop = nEwh;
+    ro.L = (real)L; ro.fEwCut = (real)fEwCut; ro.alpha = (real)alpha; ro.alpha2 = (real)(alpha * alpha);
+    ro.k1 = (real)(3.14159265358979323846 / (alpha * alpha * L * L * L));
+    ro.ka = (real)(2.0 * alpha / sqrt(3.14159265358979323846));
+    ro.fEwCut2 = (real)(fEwCut * fEwCut * L * L);
+    ro.fInner2 = (real)(1.1e-2 * L * L); /* Ewald.cpp:516 (not used by ewald_kernel) */
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nEwh; i += blockDim.x) {
+    double row[5];
+    ewald_h_row(comp, mom64[2], L, hxyz[3 * i], hxyz[3 * i + 1], hxyz[3 * i + 2], row);
+    EwtData &e = out->ewt[i];
+    e.hx = (real)row[0]; e.hy = (real)row[1]; e.hz = (real)row[2]; e.hCfac = (real)row[3]; e.hSfac = (real)row[4];
+  }
+}
+
+/* pair interactions of buckets [b0, b1), counted like Compute.cpp:1643-1651 (list length x bucket
+ * size): out[0] = p-c, out[1] = p-p (+ softened cells) */
+__global__ void step_pairs_kernel(const int *__restrict__ cellMarkers, const int *__restrict__ partMarkers,
+                                  const int *__restrict__ softMarkers, const int *__restrict__ sizes, int b0, int b1,
+                                  unsigned long long *__restrict__ out) {
+  unsigned long long pc = 0, pp = 0;
+  for (int b = b0 + blockIdx.x * blockDim.x + threadIdx.x; b < b1; b += gridDim.x * blockDim.x) {
+    const unsigned long long z = (unsigned long long)sizes[b];
+    pc += z * (unsigned long long)(cellMarkers[b + 1] - cellMarkers[b]);
+    pp += z * (unsigned long long)((partMarkers[b + 1] - partMarkers[b]) + (softMarkers[b + 1] - softMarkers[b]));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    pc += __shfl_xor_sync(0xffffffffu, pc, o);
+    pp += __shfl_xor_sync(0xffffffffu, pp, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, pc); atomicAdd(out + 1, pp); }
+}
+
+/* results back to the caller's particle order: out[order[i]] = vars[i] (single GPU), or the rank's own
+ * rows [p0, p1) with the caller index each belongs to */
+__global__ void step_scatter_kernel(const VariablePartData *__restrict__ vars, const int *__restrict__ order, int n,
+                                    VariablePartData *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[order[i]] = vars[i];
+}
+
+/* multistep rank boundaries: boundary r = first bucket starting at or after the particle that holds
+ * active marker at[r] (changa_b200.multigpu.bucket_range_by_active) */
+__global__ void step_active_cuts_kernel(const int *__restrict__ markers, const int *__restrict__ at, int nCuts,
+                                        const int *__restrict__ bucketStarts, int nb, int n, int *__restrict__ cuts) {
+  const int r = threadIdx.x;
+  if (r >= nCuts) return;
+  const int want = markers[at[r]];
+  int a = 0, b = nb;
+  while (a < b) {
+    const int mid = a + ((b - a) >> 1);
+    if (bucketStarts[mid] < want) a = mid + 1; else b = mid;
+  }
+  cuts[2 * r] = a;
+  cuts[2 * r + 1] = a < nb ? bucketStarts[a] : n;
+}
+/* out[k] = number of markers below p0 (k = 0) / p1 (k = 1): the slice of the ascending marker array in [p0, p1) */
+__global__ void step_marker_range_kernel(const int *__restrict__ markers, int nAct, int p0, int p1, int *__restrict__ out) {
+  const int want = threadIdx.x == 0 ? p0 : p1;
+  int a = 0, b = nAct;
+  while (a < b) {
+    const int mid = a + ((b - a) >> 1);
+    if (markers[mid] < want) a = mid + 1; else b = mid;
+  }
+  out[threadIdx.x] = a;
+}
+
+/* ------------------------------------------------------------------- step */
+enum { PH_H2D = 0, PH_GATHER, PH_TREE, PH_MOMENTS, PH_EWALD, PH_WALK, PH_PC, PH_PP, PH_FINISH, PH_TOTAL, PH_N };
+
+struct cb200_step {
+  cb200_comm *comm = nullptr;
+  cb200_step_config cfg;
+  int rank = 0, world = 1, device = 0;
+  long long n = 0;
+  int chunk = 0;
+  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaEvent_t ev[PH_N + 2], evFork = nullptr, evJoin = nullptr;
+  int ewaldSlot = 0;
+  int nEwh = 0;
+  int *d_hxyz = nullptr;
+  EwaldParams *d_ewald = nullptr;
+  double *d_rec = nullptr, *d_all = nullptr;       /* my slice / the gathered box */
+  unsigned char *d_rung = nullptr, *d_rungAll = nullptr;
+  VariablePartData *d_vars = nullptr, *d_out = nullptr;
+  unsigned long long *d_counts = nullptr;
+  /* node-sized arrays follow the tree */
+  int nodeCap = 0;
+  double *d_mom64 = nullptr;
+  PackedCell *d_pkMom = nullptr;
+  real *d_mom32 = nullptr;
+  int bucketCap = 0;
+  unsigned char *d_bucketActive = nullptr;
+  int *d_markers = nullptr;
+  /* what the last run left for inspection (tests; cb200_step_tree / _lists) */
+  cb200_tree tree;
+  cb200_lists lists;
+  bool haveTree = false, haveLists = false;
+  /* cost feedback: last step's particle cuts and the cost every rank measured between them */
+  std::vector<double> prevCost;
+  std::vector<long long> prevCut;
+};
+
+static std::atomic<int> g_nextEwaldSlot{0};
+
+static void step_release_products(cb200_step *st) {
+  cudaStream_t s = st->stream;
+  if (st->haveLists) { cb200_lists_free(&st->lists, s); st->haveLists = false; }
+  if (st->haveTree) { cb200_tree_free(&st->tree, s); st->haveTree = false; }
+}
+
+/* New particle targets of the rank boundaries from last step's measured costs: the cost is taken as
+ * uniform inside each old range, the cumulative cost is inverted at k/N of its total (never splits
+ * a bucket: the device snaps each target to the next bucket start).  Pure host arithmetic on values
+ * every rank holds identically, so all ranks cut alike. */
+static void cost_targets(const std::vector<long long> &cut, const std::vector<double> &cost, int world, long long n,
+                         int *targets) {
+  double total = 0.0;
+  for (double c : cost) total += c;
+  int seg = 0;
+  double before = 0.0;
+  for (int r = 1; r < world; ++r) {
+    const double want = total * r / world;
+    while (seg < world - 1 && before + cost[seg] < want) { before += cost[seg]; ++seg; }
+    const double span = (double)(cut[seg + 1] - cut[seg]);
+    const double frac = cost[seg] > 0.0 ? (want - before) / cost[seg] : 0.0;
+    long long p = cut[seg] + (long long)(frac * span + 0.5);
+    if (p < 0) p = 0;
+    if (p > n) p = n;
+    targets[r] = (int)p;
+  }
+  targets[0] = 0;
+  targets[world] = (int)n;
+}
+
+extern "C" {
+
+/* ---- communicator ---- */
+size_t cb200_comm_id_bytes(void) { return sizeof(ncclUniqueId); }
+void cb200_comm_unique_id(void *id) {
+  ncclUniqueId u;
+  ncclChk(nccl_api()->GetUniqueId(&u));
+  memcpy(id, &u, sizeof u);
+}
+cb200_comm *cb200_comm_init(int rank, int world, const void *id) {
+  device_info();
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof u);
+  cb200_comm *c = new cb200_comm;
+  c->rank = rank; c->world = world;
+  ncclChk(nccl_api()->CommInitRank(&c->comm, world, u, rank));
+  return c;
+}
+void cb200_comm_destroy(cb200_comm *c) {
+  if (!c) return;
+  ncclChk(nccl_api()->CommDestroy(c->comm));
+  delete c;
+}
+int cb200_comm_rank(const cb200_comm *c) { return c ? c->rank : 0; }
+int cb200_comm_world(const cb200_comm *c) { return c ? c->world : 1; }
+int cb200_comm_nccl_version(void) {
+  int v = 0;
+  ncclChk(nccl_api()->GetVersion(&v));
+  return v;
+}
+/* element-wise reduction of n host doubles over the ranks (op: 0 sum, 1 max, 2 min); blocking.
+ * With one rank (comm NULL) the values stay as they are. */
+void cb200_comm_allreduce_f64(cb200_comm *c, double *h_values, int n, int op, void *stream) {
+  if (!c || c->world == 1 || n <= 0) return;
+  cudaStream_t s = (cudaStream_t)stream;
+  double *d = (double *)pool_alloc((size_t)n * sizeof(double), s);
+  cudaChk(cudaMemcpyAsync(d, h_values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  ncclChk(nccl_api()->AllReduce(d, d, (size_t)n, ncclDouble, op == 1 ? ncclMax : (op == 2 ? ncclMin : ncclSum), c->comm, s));
+  cudaChk(cudaMemcpyAsync(h_values, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaStreamSynchronize(s));
+  pool_free(d, s);
+}
+void cb200_comm_barrier(cb200_comm *c, void *stream) {
+  double one = 1.0;
+  cb200_comm_allreduce_f64(c, &one, 1, 0, stream);
+  cudaChk(cudaStreamSynchronize((cudaStream_t)stream));
+}
+/* replicate equal slices: every rank contributes sendBytes at d_send, d_recv gets world x sendBytes in rank order */
+void cb200_comm_allgather(cb200_comm *c, const void *d_send, void *d_recv, size_t sendBytes, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!c || c->world == 1) {
+    if (d_send != d_recv && sendBytes) cudaChk(cudaMemcpyAsync(d_recv, d_send, sendBytes, cudaMemcpyDeviceToDevice, s));
+    return;
+  }
+  ncclChk(nccl_api()->AllGather(d_send, d_recv, sendBytes, ncclChar, c->comm, s));
+}
+
+/* the cut rule of costCuts as a plain host function (prevCut: world + 1 particle indices, prevCost: world
+ * costs; targets: world + 1 particle indices out) */
+void cb200_cost_targets(const long long *prevCut, const double *prevCost, int world, long long n, int *targets) {
+  cost_targets(std::vector<long long>(prevCut, prevCut + world + 1), std::vector<double>(prevCost, prevCost + world), world, n,
+               targets);
+}
+
+/* ---- step ---- */
+cb200_step *cb200_step_create(cb200_comm *comm, const cb200_step_config *cfg) {
+  device_info();
+  cb200_step *st = new cb200_step;
+  st->comm = comm;
+  st->cfg = *cfg;
+  st->rank = comm ? comm->rank : 0;
+  st->world = comm ? comm->world : 1;
+  cudaChk(cudaGetDevice(&st->device));
+  st->n = cfg->numParticles;
+  if (st->n <= 0 || st->n > 0x7fffffffLL || st->world > 17) {
+    fprintf(stderr, "cb200_step_create: %lld particles on %d ranks is outside what one step handles (int32 particle "
+                    "indices as in the reference's ABI; at most 17 ranks)\n", st->n, st->world);
+    abort();
+  }
+  st->chunk = (int)((st->n + st->world - 1) / st->world);
+  cudaChk(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+  cudaChk(cudaStreamCreateWithFlags(&st->aux, cudaStreamNonBlocking));
+  for (cudaEvent_t &e : st->ev) cudaChk(cudaEventCreate(&e));
+  cudaChk(cudaEventCreateWithFlags(&st->evFork, cudaEventDisableTiming));
+  cudaChk(cudaEventCreateWithFlags(&st->evJoin, cudaEventDisableTiming));
+  const size_t n = (size_t)st->n, chunk = (size_t)st->chunk;
+  cudaChk(cudaMalloc((void **)&st->d_rec, chunk * 5 * sizeof(double)));
+  if (st->world > 1) cudaChk(cudaMalloc((void **)&st->d_all, chunk * st->world * 5 * sizeof(double)));
+  cudaChk(cudaMalloc((void **)&st->d_vars, n * sizeof(VariablePartData)));
+  if (st->world == 1) cudaChk(cudaMalloc((void **)&st->d_out, n * sizeof(VariablePartData)));
+  cudaChk(cudaMalloc((void **)&st->d_counts, 64));
+  if (cfg->activeRung > 0) {
+    cudaChk(cudaMalloc((void **)&st->d_rung, chunk));
+    if (st->world > 1) cudaChk(cudaMalloc((void **)&st->d_rungAll, chunk * st->world));
+    cudaChk(cudaMalloc((void **)&st->d_markers, n * sizeof(int)));
+  }
+  if (cfg->ewald) {
+    std::vector<int> h(3 * 4096);
+    st->nEwh = ewald_h_vectors(cfg->dEwhCut, h.data(), 4096);
+    if (st->nEwh > NEWH) { /* HostCUDA.cu:1923 */
+      fprintf(stderr, "cb200_step_create: dEwhCut = %g gives %d h-vectors, the table holds %d\n", cfg->dEwhCut, st->nEwh, NEWH);
+      abort();
+    }
+    cudaChk(cudaMalloc((void **)&st->d_hxyz, (size_t)(st->nEwh > 0 ? st->nEwh : 1) * 3 * sizeof(int)));
+    cudaChk(cudaMemcpy(st->d_hxyz, h.data(), (size_t)st->nEwh * 3 * sizeof(int), cudaMemcpyHostToDevice));
+    cudaChk(cudaMalloc((void **)&st->d_ewald, sizeof(EwaldParams)));
+    cudaChk(cudaMemset(st->d_ewald, 0, sizeof(EwaldParams)));
+    st->ewaldSlot = g_nextEwaldSlot.fetch_add(1) % kEwaldSlots;
+  }
+  memset(&st->tree, 0, sizeof st->tree);
+  memset(&st->lists, 0, sizeof st->lists);
+  stream_counter(st->stream); /* made here, not inside a launch */
+  return st;
+}
+
+void cb200_step_destroy(cb200_step *st) {
+  if (!st) return;
+  cudaChk(cudaStreamSynchronize(st->stream));
+  step_release_products(st);
+  cudaChk(cudaStreamSynchronize(st->stream));
+  for (void *p : {(void *)st->d_rec, (void *)st->d_all, (void *)st->d_vars, (void *)st->d_out, (void *)st->d_counts,
+                  (void *)st->d_rung, (void *)st->d_rungAll, (void *)st->d_markers, (void *)st->d_hxyz, (void *)st->d_ewald,
+                  (void *)st->d_mom64, (void *)st->d_pkMom, (void *)st->d_mom32, (void *)st->d_bucketActive})
+    if (p) cudaChk(cudaFree(p));
+  for (cudaEvent_t &e : st->ev) cudaEventDestroy(e);
+  cudaEventDestroy(st->evFork); cudaEventDestroy(st->evJoin);
+  pool_forget_stream(st->stream); pool_forget_stream(st->aux);
+  drop_companion(st->stream); drop_stream_counter(st->stream);
+  drop_companion(st->aux); drop_stream_counter(st->aux);
+  cudaStreamDestroy(st->stream); cudaStreamDestroy(st->aux);
+  delete st;
+}
+
+int cb200_step_chunk_rows(const cb200_step *st) { return st->chunk; }
+void *cb200_step_stream(const cb200_step *st) { return (void *)st->stream; }
+/* device buffer of this rank's chunk_rows x {x, y, z, mass, soft} doubles (and rung bytes): a caller that
+ * keeps its particles on the device writes them here and calls cb200_step_run with h_records = NULL */
+double *cb200_step_device_records(const cb200_step *st) { return st->d_rec; }
+unsigned char *cb200_step_device_rungs(const cb200_step *st) { return st->d_rung; }
+/* the tree / lists / moments / accumulators of the last run (valid until the next run or destroy) */
+const cb200_tree *cb200_step_tree(const cb200_step *st) { return st->haveTree ? &st->tree : nullptr; }
+const cb200_lists *cb200_step_lists(const cb200_step *st) { return st->haveLists ? &st->lists : nullptr; }
+const double *cb200_step_moments_f64(const cb200_step *st) { return st->d_mom64; }
+const void *cb200_step_packed_moments(const cb200_step *st) { return st->d_pkMom; }
+const void *cb200_step_vars(const cb200_step *st) { return st->d_vars; }
+const int *cb200_step_markers(const cb200_step *st) { return st->d_markers; }
+
+/* One force step.  h_records: this rank's chunk_rows x 5 doubles in (pinned) host memory, or NULL when the
+ * caller already wrote cb200_step_device_records().  h_rungs: chunk_rows bytes (multistep steps only).
+ * h_out: accelerations, potential and dtGrav as VariablePartData rows -- world == 1: numParticles rows in the
+ * CALLER'S particle order; world > 1: this rank's result->rows rows (its SFC range) with the caller index of
+ * each row in h_index; outCapacityRows = rows h_out / h_index can hold (cb200_step_out_capacity()).  h_out NULL: results stay on the device
+ * (cb200_step_vars, tree order).  Blocking: returns when the results are in h_out.  keepLists: leave the
+ * interaction lists on the device for inspection (cb200_step_lists). */
+void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char *h_rungs, void *h_out, int *h_index,
+                    int outCapacityRows, int keepLists, cb200_step_result *res) {
+  cudaChk(cudaSetDevice(st->device));
+  cudaStream_t s = st->stream;
+  const cb200_step_config &cfg = st->cfg;
+  const int n = (int)st->n, world = st->world, rank = st->rank, chunk = st->chunk;
+  const bool multistep = cfg.activeRung > 0;
+  memset(res, 0, sizeof *res);
+  step_release_products(st);
+  nvtx_push("cb200_step_run");
+
+  cudaChk(cudaEventRecord(st->ev[0], s));
+  nvtx_push("CUDA_XFER_LOCAL");
+  if (h_records) {
+    cudaChk(cudaMemcpyAsync(st->d_rec, h_records, (size_t)chunk * 5 * sizeof(double), cudaMemcpyHostToDevice, s));
+    res->h2dBytes += (long long)chunk * 5 * (long long)sizeof(double);
+    if (multistep && h_rungs) {
+      cudaChk(cudaMemcpyAsync(st->d_rung, h_rungs, (size_t)chunk, cudaMemcpyHostToDevice, s));
+      res->h2dBytes += chunk;
+    }
+  }
+  nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_H2D + 1], s));
+
+  /* the one exchange of the step: every rank's slice of the 40-byte records */
+  nvtx_push("all-gather");
+  const double *box = st->d_rec;
+  const unsigned char *rungs = st->d_rung;
+  if (world > 1) {
+    ncclChk(nccl_api()->AllGather(st->d_rec, st->d_all, (size_t)chunk * 5, ncclDouble, st->comm->comm, s));
+    box = st->d_all;
+    if (multistep) {
+      ncclChk(nccl_api()->AllGather(st->d_rung, st->d_rungAll, (size_t)chunk, ncclChar, st->comm->comm, s));
+      rungs = st->d_rungAll;
+    }
+  }
+  nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_GATHER + 1], s));
+
+  /* tree; the rank boundaries ride back with its one synchronisation */
+  nvtx_push("CUDA_SER_TREE");
+  int targets[18], cuts[36];
+  const bool byCost = cfg.costCuts && !multistep && (int)st->prevCost.size() == world && world > 1;
+  if (byCost) cost_targets(st->prevCut, st->prevCost, world, n, targets);
+  else for (int r = 0; r <= world; ++r) targets[r] = (int)((long long)r * n / world);
+  TreeInput in;
+  in.pos = box; in.mass = box + 3; in.soft = box + 4; in.posStride = 5; in.attrStride = 5;
+  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, targets, world + 1, cuts, s);
+  st->haveTree = true;
+  cb200_tree &tr = st->tree;
+  nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_TREE + 1], s));
+  res->numNodes = tr.numNodes; res->numBuckets = tr.numBuckets; res->numLevels = tr.numLevels;
+  if (tr.error) { res->error = 10 + tr.error; nvtx_pop(); return; }
+  const int nn = tr.numNodes, nb = tr.numBuckets;
+
+  /* moments */
+  nvtx_push("CUDA_SER_TREE moments");
+  if (nn > st->nodeCap) {
+    for (void *p : {(void *)st->d_mom64, (void *)st->d_pkMom, (void *)st->d_mom32}) if (p) cudaChk(cudaFree(p));
+    st->nodeCap = nn + nn / 16 + 1024;
+    cudaChk(cudaMalloc((void **)&st->d_mom64, (size_t)st->nodeCap * 27 * sizeof(double)));
+    cudaChk(cudaMalloc((void **)&st->d_mom32, (size_t)st->nodeCap * 27 * sizeof(real)));
+    cudaChk(cudaMalloc((void **)&st->d_pkMom, (size_t)st->nodeCap * sizeof(PackedCell)));
+  }
+  cb200_build_moments(tr.d_pos, tr.d_mass, tr.d_soft, n, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last, tr.d_geolo,
+                      tr.d_geohi, tr.d_boxlo, tr.d_boxhi, tr.levelStart, tr.numLevels, nn, st->d_mom32, st->d_mom64, s);
+  repack_cells(st->d_mom32, st->d_pkMom, nn, s);
+  cudaChk(cudaMemsetAsync(st->d_vars, 0, (size_t)n * sizeof(VariablePartData), s));
+  nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_MOMENTS + 1], s));
+
+  /* my share: buckets [b0, b1) = particles [p0, p1) */
+  int b0 = cuts[2 * rank], p0 = cuts[2 * rank + 1], b1 = cuts[2 * rank + 2], p1 = cuts[2 * rank + 3];
+  if (rank == 0) { b0 = 0; p0 = 0; }
+  if (rank == world - 1) { b1 = nb; p1 = n; }
+  const unsigned char *bucketActive = nullptr;
+  int nAct = n;
+  if (multistep) {
+    if (nb > st->bucketCap) {
+      if (st->d_bucketActive) cudaChk(cudaFree(st->d_bucketActive));
+      st->bucketCap = nb + nb / 16 + 1024;
+      cudaChk(cudaMalloc((void **)&st->d_bucketActive, (size_t)st->bucketCap));
+    }
+    int counts[2] = {0, 0};
+    cb200_active_sets_device(rungs, tr.d_order, n, tr.d_bucketStarts, tr.d_bucketSizes, nb, cfg.activeRung,
+                             st->d_bucketActive, st->d_markers, counts, s);
+    bucketActive = st->d_bucketActive;
+    nAct = counts[1];
+    res->activeBuckets = counts[0]; res->activeParticles = counts[1];
+    if (world > 1 && nAct > 0) {
+      /* equal ACTIVE particle counts (changa_b200.multigpu.bucket_range_by_active): the boundaries are the
+       * particles holding markers r * nAct / world, snapped to bucket starts */
+      int at[18];
+      for (int r = 0; r <= world; ++r) { long long a = (long long)r * nAct / world; at[r] = (int)(a < nAct ? a : nAct - 1); }
+      int *d_at = (int *)pool_alloc(18 * sizeof(int), s);
+      int *d_cut = (int *)pool_alloc(36 * sizeof(int), s);
+      cudaChk(cudaMemcpyAsync(d_at, at, (size_t)(world + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+      step_active_cuts_kernel<<<1, 32, 0, s>>>(st->d_markers, d_at, world + 1, tr.d_bucketStarts, nb, n, d_cut);
+      cudaChk(cudaMemcpyAsync(cuts, d_cut, (size_t)(2 * world + 2) * sizeof(int), cudaMemcpyDeviceToHost, s));
+      cudaChk(cudaStreamSynchronize(s));
+      pool_free(d_at, s); pool_free(d_cut, s);
+      b0 = rank == 0 ? 0 : cuts[2 * rank]; p0 = rank == 0 ? 0 : cuts[2 * rank + 1];
+      b1 = rank == world - 1 ? nb : cuts[2 * rank + 2]; p1 = rank == world - 1 ? n : cuts[2 * rank + 3];
+    }
+  }
+  res->bucketLo = b0; res->bucketHi = b1; res->partLo = p0; res->partHi = p1;
+
+  /* Ewald needs the particles and the root moments only: it runs on a second stream under the walk
+   * (the walk is latency-bound, the Ewald kernel issue-bound; both leave room for the other) */
+  const real fper = (real)((cfg.nReplicas || cfg.ewald) ? cfg.period : 0.0);
+  cudaStream_t es = cfg.overlapEwald ? st->aux : s;
+  if (cfg.ewald && p1 > p0) {
+    nvtx_push("CUDA_EWALD");
+    if (cfg.overlapEwald) {
+      cudaChk(cudaEventRecord(st->evFork, s));
+      cudaChk(cudaStreamWaitEvent(es, st->evFork, 0));
+    }
+    ewald_setup_kernel<<<1, 128, 0, es>>>(st->d_mom64, cfg.period, cfg.dEwCut, cfg.nReplicas, st->nEwh, st->d_hxyz, p0, p1 - 1,
+                                          st->d_ewald);
+    cudaChk(cudaPeekAtLastError());
+    cudaChk(cudaMemcpyToSymbolAsync(c_ewaldSlot, st->d_ewald, sizeof(EwaldParams), (size_t)st->ewaldSlot * sizeof(EwaldParams),
+                                    cudaMemcpyDeviceToDevice, es));
+    const int *mk = nullptr;
+    int first = p0, last = p1 - 1, count = p1 - p0;
+    if (multistep) { /* large-phase form: the markers of my particle range (ascending: a binary search on the host copy is not needed) */
+      int range[2] = {0, 0};
+      int *d_range = (int *)pool_alloc(2 * sizeof(int), es);
+      step_marker_range_kernel<<<1, 2, 0, es>>>(st->d_markers, nAct, p0, p1, d_range);
+      cudaChk(cudaMemcpyAsync(range, d_range, sizeof range, cudaMemcpyDeviceToHost, es));
+      cudaChk(cudaStreamSynchronize(es));
+      pool_free(d_range, es);
+      mk = st->d_markers + range[0];
+      first = 0; count = range[1] - range[0]; last = count - 1;
+    }
+    if (count > 0) {
+      TapScope tap(TAP_EWALD, es);
+      ewald_slot_kernel<<<(count + kEwaldThreads - 1) / kEwaldThreads, kEwaldThreads, 0, es>>>(
+          (const PackedPart *)tr.d_packedParts, st->d_vars, mk, first, last, st->ewaldSlot);
+      cudaChk(cudaPeekAtLastError());
+    }
+    if (cfg.overlapEwald) cudaChk(cudaEventRecord(st->evJoin, es));
+    nvtx_pop();
+  }
+  /* with the overlap the Ewald kernel's time is inside the walk phase (which ends after the join) */
+  cudaChk(cudaEventRecord(st->ev[PH_EWALD + 1], s));
+
+  /* interaction lists of my buckets */
+  nvtx_push("CUDA_SER_LIST");
+  cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
+                           tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
+                           cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
+  st->haveLists = true;
+  cb200_lists &li = st->lists;
+  nvtx_pop();
+  if (cfg.overlapEwald && cfg.ewald && p1 > p0) cudaChk(cudaStreamWaitEvent(s, st->evJoin, 0));
+  cudaChk(cudaEventRecord(st->ev[PH_WALK + 1], s));
+  res->nCell = li.nCell; res->nSoft = li.nSoft; res->nPart = li.nPart;
+  if (li.error) { res->error = 20 + li.error; nvtx_pop(); return; }
+
+  /* forces */
+  const PackedPart *P = (const PackedPart *)tr.d_packedParts;
+  unsigned *counter = stream_counter(s);
+  nvtx_push("CUDA_GRAV_LOCAL");
+  dispatch_cell_list(cfg.maxBucket, P, st->d_vars, st->d_pkMom, li.d_cell, li.d_cellMarkers, li.d_starts, li.d_sizes, nb, fper,
+                     counter, s);
+  nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_PC + 1], s));
+  nvtx_push("CUDA_PART_GRAV_LOCAL");
+  dispatch_part_list(cfg.maxBucket, P, st->d_vars, P, li.d_part, li.d_partMarkers, li.d_starts, li.d_sizes, nb, fper, counter, s);
+  if (li.nSoft)
+    dispatch_part_list(cfg.maxBucket, P, st->d_vars, (const PackedPart *)li.d_nodeParticles, li.d_soft, li.d_softMarkers,
+                       li.d_starts, li.d_sizes, nb, fper, counter, s);
+  nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_PP + 1], s));
+
+  /* pair counts (the metric) and results */
+  nvtx_push("CUDA_XFER_BACK");
+  cudaChk(cudaMemsetAsync(st->d_counts, 0, 64, s));
+  if (b1 > b0) {
+    step_pairs_kernel<<<device_info().sms, 256, 0, s>>>(li.d_cellMarkers, li.d_partMarkers, li.d_softMarkers, li.d_sizes, b0, b1,
+                                                       st->d_counts);
+    cudaChk(cudaPeekAtLastError());
+  }
+  unsigned long long pairs[2] = {0, 0};
+  cudaChk(cudaMemcpyAsync(pairs, st->d_counts, sizeof pairs, cudaMemcpyDeviceToHost, s));
+  if (world == 1) {
+    res->rows = n;
+    if (h_out && n > outCapacityRows) {
+      res->error = 30;
+    } else if (h_out) {
+      step_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(st->d_vars, tr.d_order, n, st->d_out);
+      cudaChk(cudaPeekAtLastError());
+      cudaChk(cudaMemcpyAsync(h_out, st->d_out, (size_t)n * sizeof(VariablePartData), cudaMemcpyDeviceToHost, s));
+      res->d2hBytes += (long long)n * (long long)sizeof(VariablePartData);
+    }
+  } else {
+    res->rows = p1 - p0;
+    if (h_out && p1 - p0 > outCapacityRows) {
+      res->error = 30; /* the rank's share outgrew the caller's result buffer */
+    } else if (h_out && p1 > p0) {
+      cudaChk(cudaMemcpyAsync(h_out, st->d_vars + p0, (size_t)(p1 - p0) * sizeof(VariablePartData), cudaMemcpyDeviceToHost, s));
+      cudaChk(cudaMemcpyAsync(h_index, tr.d_order + p0, (size_t)(p1 - p0) * sizeof(int), cudaMemcpyDeviceToHost, s));
+      res->d2hBytes += (long long)(p1 - p0) * (long long)(sizeof(VariablePartData) + sizeof(int));
+    }
+  }
+  g_launches.fetch_add(3);
+  nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_FINISH + 1], s));
+  if (!keepLists) { cb200_lists_free(&st->lists, s); st->haveLists = false; }
+  cudaChk(cudaStreamSynchronize(s));
+  res->pcPairs = (long long)pairs[0]; res->ppPairs = (long long)pairs[1];
+  res->cost = 198.0 * (double)pairs[0] + 30.0 * (double)pairs[1];
+  for (int k = 0; k < PH_FINISH + 1; ++k) cudaChk(cudaEventElapsedTime(&res->ms[k], st->ev[k], st->ev[k + 1]));
+  cudaChk(cudaEventElapsedTime(&res->ms[PH_TOTAL], st->ev[0], st->ev[PH_FINISH + 1]));
+
+  /* cost feedback for the next step's cuts: every rank learns every rank's cost and range */
+  if (world > 1 && cfg.costCuts && !multistep) {
+    std::vector<double> v(2 * (size_t)world, 0.0);
+    v[rank] = res->cost; v[world + rank] = (double)p0;
+    cb200_comm_allreduce_f64(st->comm, v.data(), 2 * world, 0, s);
+    st->prevCost.assign(v.begin(), v.begin() + world);
+    st->prevCut.resize((size_t)world + 1);
+    for (int r = 0; r < world; ++r) st->prevCut[r] = (long long)v[world + r];
+    st->prevCut[world] = n;
+  }
+  nvtx_pop();
+}
+
+/* rows a caller should provide for h_out / h_index: the whole box on one GPU; with several, three equal
+ * shares (cost-balanced cuts give a rank in a void more particles than n / world) */
+int cb200_step_out_capacity(const cb200_step *st) {
+  const long long want = st->world == 1 ? st->n : 3LL * st->chunk + 64;
+  return (int)(want < st->n ? want : st->n);
+}
+
+} /* extern "C" */
+#endif

@@ -1337,10 +1337,9 @@ __device__ __forceinline__ real ewald_series(real x) {
  * __grid_constant__ argument (constant bank, uniform reads) instead of the
  * reference's process-global __constant__ symbols, so concurrent requests on
  * different streams cannot race.  Adds to acc/pot, never touches dtGrav. */
-__global__ void __launch_bounds__(kEwaldThreads)
-ewald_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
-             const int *__restrict__ markers, int first, int last,
-             const __grid_constant__ EwaldParams P) {
+__device__ __forceinline__ void ewald_particle(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
+                                               const int *__restrict__ markers, int first, int last,
+                                               const EwaldParams &P) {
   int id = blockIdx.x * kEwaldThreads + threadIdx.x;
   if (markers) {
     if (id > last) return;
@@ -1475,6 +1474,25 @@ ewald_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict_
   VariablePartData *v = vars + id;
   v->a.x += ax; v->a.y += ay; v->a.z += az;
   v->potential += fPot;
+}
+
+__global__ void __launch_bounds__(kEwaldThreads)
+ewald_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
+             const int *__restrict__ markers, int first, int last,
+             const __grid_constant__ EwaldParams P) {
+  ewald_particle(parts, vars, markers, first, last, P);
+}
+
+/* The same kernel for a force step that builds its Ewald tables ON THE DEVICE (ewald_setup_kernel,
+ * hostcuda.cu): the parameters sit in one of a few __constant__ slots, filled by a stream-ordered
+ * device-to-device copy, so the root moments never travel to the host and the step needs no
+ * synchronisation in front of the Ewald launch.  A slot belongs to one step object at a time. */
+constexpr int kEwaldSlots = 4;
+__constant__ EwaldParams c_ewaldSlot[kEwaldSlots];
+__global__ void __launch_bounds__(kEwaldThreads)
+ewald_slot_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
+                  const int *__restrict__ markers, int first, int last, int slot) {
+  ewald_particle(parts, vars, markers, first, last, c_ewaldSlot[slot]);
 }
 
 

@@ -35,6 +35,8 @@
 #include "moments_build.cuh"
 #include "walk_kernels.cuh"
 #include "tree_kernels.cuh"
+#include "ewald_setup.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
@@ -55,6 +57,18 @@ static inline void cb200_cuda_assert(cudaError_t code, const char *file, int lin
     abort();
   }
 }
+
+/* ------------------------------------------------------------ NVTX ranges */
+/* host-side ranges around what each entry point enqueues, named after the reference's HAPI trace
+ * ids (cuda_typedef.h:27-47): CUDA_XFER_LOCAL, CUDA_GRAV_LOCAL, ..., CUDA_EWALD, CUDA_SER_TREE /
+ * CUDA_SER_LIST for the tree and list generation the device path does itself.  nvtx3 is header-only
+ * and costs a null check when no tool is attached. */
+static inline void nvtx_push(const char *name) { nvtxRangePushA(name); }
+static inline void nvtx_pop() { nvtxRangePop(); }
+struct NvtxScope {
+  explicit NvtxScope(const char *name) { nvtxRangePushA(name); }
+  ~NvtxScope() { nvtxRangePop(); }
+};
 
 /* ------------------------------------------------------- completion callbacks */
 static std::atomic<cb200_callback_fn> g_handler{nullptr};
@@ -565,6 +579,7 @@ void DataManagerTransferLocalTree(void *moments, size_t sMoments, void *compactP
                                   size_t sCompactParts, void *varParts, size_t sVarParts,
                                   void **d_localMoments, void **d_compactParts, void **d_varParts,
                                   cudaStream_t stream, int numParticles, void *callback) {
+  NvtxScope range("CUDA_XFER_LOCAL");
   const size_t nCells = sMoments / sizeof(CudaMultipoleMoments);
   const size_t nParts = sCompactParts / sizeof(CompactPartData);
   *d_localMoments = pool_alloc(nCells * sizeof(PackedCell), stream);
@@ -587,6 +602,7 @@ void DataManagerTransferLocalTree(void *moments, size_t sMoments, void *compactP
 void DataManagerTransferRemoteChunk(void *moments, size_t sMoments, void *remoteParts,
                                     size_t sRemoteParts, void **d_remoteMoments,
                                     void **d_remoteParts, cudaStream_t stream, void *callback) {
+  NvtxScope range("CUDA_XFER_REMOTE");
   const size_t nCells = sMoments / sizeof(CudaMultipoleMoments);
   const size_t nParts = sRemoteParts / sizeof(CompactPartData);
   *d_remoteMoments = pool_alloc(nCells * sizeof(PackedCell), stream);
@@ -598,6 +614,7 @@ void DataManagerTransferRemoteChunk(void *moments, size_t sMoments, void *remote
 
 void TransferParticleVarsBack(VariablePartData *hostBuffer, size_t size, void *d_varParts,
                               cudaStream_t stream, void *cb) {
+  NvtxScope range("CUDA_XFER_BACK");
   if (size) cudaChk(cudaMemcpyAsync(hostBuffer, d_varParts, size, cudaMemcpyDeviceToHost, stream));
   hapiAddCallback(stream, cb);
 }
@@ -655,6 +672,7 @@ static RequestScratch stage_request(CudaRequest *data, size_t missedPackedBytes,
 enum Gather { G_LOCAL, G_REMOTE, G_MISSED };
 
 static void cell_list_request(CudaRequest *data, Gather g) {
+  NvtxScope range(g == G_LOCAL ? "CUDA_GRAV_LOCAL" : (g == G_REMOTE ? "CUDA_GRAV_REMOTE" : "CUDA_REMOTE_RESUME"));
   cudaStream_t stream = data->stream;
   const int nb = data->numBucketsPlusOne - 1;
   if (nb <= 0) { hapiAddCallback(stream, data->cb); return; }
@@ -677,6 +695,8 @@ static void cell_list_request(CudaRequest *data, Gather g) {
 }
 
 static void part_list_request(CudaRequest *data, Gather g, const CompactPartData *h_small, int nSmall) {
+  NvtxScope range(g == G_LOCAL ? "CUDA_PART_GRAV_LOCAL" : (g == G_REMOTE ? "CUDA_PART_GRAV_REMOTE"
+                  : (h_small ? "CUDA_PART_GRAV_LOCAL_SMALL" : "CUDA_REMOTE_RESUME")));
   cudaStream_t stream = data->stream;
   const int nb = data->numBucketsPlusOne - 1;
   if (nb <= 0) { hapiAddCallback(stream, data->cb); return; }
@@ -770,6 +790,7 @@ static void launch_ewald(const PackedPart *parts, VariablePartData *vars, const 
 
 void EwaldHost(CompactPartData *d_localParts, VariablePartData *d_localVars, EwaldData *h_idata,
                cudaStream_t stream, void *cb, int myIndex, int largephase) {
+  NvtxScope range("CUDA_EWALD");
   (void)myIndex;
   const int n = h_idata->cachedData->n;
   int *d_markers = nullptr;
@@ -962,9 +983,40 @@ void cb200_build_moments(const double *d_pos_xyz, const double *d_mass, const do
 }
 
 /* ---- tree topology on the device ---- */
-void cb200_build_tree(const double *d_pos_xyz, const double *d_mass, const double *d_soft, int n, int maxBucket,
-                      const double *rootlo, const double *roothi, cb200_tree *out, void *stream) {
-  cudaStream_t s = (cudaStream_t)stream;
+static int tree_level_grid() {
+  static CtaCache cache;
+  int dev = 0;
+  cudaChk(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache.n[dev].load(std::memory_order_acquire);
+  if (n > 0) return n;
+  int per = 0;
+  cudaChk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, tree_levels_kernel, kTreeLevelThreads, 0));
+  n = device_info().sms * (per > 4 ? 4 : (per > 0 ? per : 1)); /* co-resident by construction: cooperative launch */
+  cache.n[dev].store(n, std::memory_order_release);
+  return n;
+}
+
+/* Rank boundaries on the sorted particle array: boundary r sits at the first bucket that starts at or
+ * after particle target[r] (never splits a bucket; changa_b200.multigpu.bucket_range_by_starts is the
+ * host statement).  rank[p] = number of bucket starts in [0, p). */
+__global__ void tree_cuts_kernel(const int *__restrict__ flag, const int *__restrict__ rank, int n, const int *__restrict__ targets,
+                                 int nCuts, TreeMeta *meta) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nCuts) return;
+  int p = targets[r];
+  if (p > n) p = n;
+  while (p < n && !flag[p]) ++p; /* at most maxBucket steps */
+  meta->cuts[2 * r] = rank[p];
+  meta->cuts[2 * r + 1] = p;
+}
+__global__ void tree_set_buckets_kernel(const int *__restrict__ rank, int n, TreeMeta *meta) { meta->numBuckets = rank[n]; }
+
+/* the build; input as three arrays or one record array (TreeInput).  h_targets (optional, nCuts <= 17 particle
+ * indices, host): rank boundaries looked up on the device and returned in cuts[2r] (bucket) / cuts[2r+1]
+ * (particle).  ONE stream synchronisation (the node / bucket / level counts size everything downstream). */
+static void build_tree_impl(const TreeInput &in, int n, int maxBucket, const double *rootlo, const double *roothi,
+                            cb200_tree *out, const int *h_targets, int nCuts, int *h_cuts, cudaStream_t s) {
   memset(out, 0, sizeof *out);
   out->numParticles = n;
   if (n <= 0) return;
@@ -976,7 +1028,7 @@ void cb200_build_tree(const double *d_pos_xyz, const double *d_mass, const doubl
   unsigned long long *keys = (unsigned long long *)pool_alloc((size_t)n * 8, s);
   int *idxIn = (int *)pool_alloc((size_t)n * 4, s);
   out->d_order = (int *)pool_alloc((size_t)n * 4, s);
-  tree_keys_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(d_pos_xyz, n, box, keysIn, idxIn);
+  tree_keys_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(in, n, box, keysIn, idxIn);
   cudaChk(cudaPeekAtLastError());
   size_t tmpBytes = 0;
   cudaChk(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keysIn, keys, idxIn, out->d_order, n, 0, kTreeKeyBits, s));
@@ -987,13 +1039,13 @@ void cb200_build_tree(const double *d_pos_xyz, const double *d_mass, const doubl
   out->d_mass = (double *)pool_alloc((size_t)n * 8, s);
   out->d_soft = (double *)pool_alloc((size_t)n * 8, s);
   out->d_packedParts = pool_alloc((size_t)n * sizeof(PackedPart), s);
-  tree_gather_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(d_pos_xyz, d_mass, d_soft, out->d_order, n, out->d_pos,
-                                                      out->d_mass, out->d_soft, (PackedPart *)out->d_packedParts);
+  tree_gather_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(in, out->d_order, n, out->d_pos, out->d_mass, out->d_soft,
+                                                      (PackedPart *)out->d_packedParts);
   cudaChk(cudaPeekAtLastError());
   g_launches.fetch_add(5);
 
-  /* nodes, level by level; capacity: a node holds at least one particle, chains of single
-   * children are the only way past ~n/3 nodes */
+  /* nodes, level by level inside one cooperative kernel; capacity: a node holds at least one
+   * particle, chains of single children are the only way past ~n/3 nodes */
   const int cap = n + n / 2 + 4096;
   TreeArrays t;
   t.child0 = out->d_child0 = (int *)pool_alloc((size_t)cap * 4, s);
@@ -1003,78 +1055,80 @@ void cb200_build_tree(const double *d_pos_xyz, const double *d_mass, const doubl
   t.last = out->d_last = (int *)pool_alloc((size_t)cap * 4, s);
   t.geolo = out->d_geolo = (double *)pool_alloc((size_t)cap * 24, s);
   t.geohi = out->d_geohi = (double *)pool_alloc((size_t)cap * 24, s);
-  int *err = (int *)pool_alloc(4, s);
-  cudaChk(cudaMemsetAsync(err, 0, 4, s));
+  TreeMeta *meta = (TreeMeta *)pool_alloc(sizeof(TreeMeta), s);
+  cudaChk(cudaMemsetAsync(meta, 0, sizeof(TreeMeta), s));
   tree_root_kernel<<<1, 1, 0, s>>>(t, n, box, roothi[0], roothi[1], roothi[2]);
   int *split = (int *)pool_alloc((size_t)(n + 1) * 4, s); /* a level has at most n nodes */
-  int *nkids = (int *)pool_alloc((size_t)(n + 1) * 4, s);
   int *slot = (int *)pool_alloc((size_t)(n + 1) * 4, s);
-  size_t scanBytes = 0;
-  cudaChk(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, nkids, slot, n + 1, s));
-  void *scanTmp = pool_alloc(scanBytes, s);
-  int lo = 0, hi = 1, level = 0;
-  out->levelStart[0] = 0;
-  while (lo < hi && level < kTreeMaxLevels) {
-    const int cnt = hi - lo;
-    out->levelStart[level + 1] = hi;
-    tree_split_kernel<<<(cnt + 1 + tb - 1) / tb, tb, 0, s>>>(t, keys, lo, cnt, level, maxBucket, split, nkids);
-    cudaChk(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, nkids, slot, cnt + 1, s));
-    int total = 0;
-    cudaChk(cudaMemcpyAsync(&total, slot + cnt, 4, cudaMemcpyDeviceToHost, s));
-    cudaChk(cudaStreamSynchronize(s)); /* the size of the next level decides the next launch */
-    g_launches.fetch_add(2);
-    if (total > 0) {
-      if (hi + total > cap) { out->error = 1; break; }
-      tree_emit_kernel<<<(cnt + tb - 1) / tb, tb, 0, s>>>(t, lo, cnt, level, split, slot, hi, cap, err);
-      cudaChk(cudaPeekAtLastError());
-      g_launches.fetch_add(1);
-    }
-    lo = hi;
-    hi += total;
-    ++level;
+  const int grid = tree_level_grid();
+  int *blockSums = (int *)pool_alloc((size_t)grid * 4, s);
+  {
+    const unsigned long long *ckeys = keys;
+    int mb = maxBucket, cp = cap;
+    void *args[] = {&t, &ckeys, &mb, &cp, &split, &slot, &blockSums, &meta};
+    cudaChk(cudaLaunchCooperativeKernel((void *)tree_levels_kernel, dim3(grid), dim3(kTreeLevelThreads), args, 0, s));
   }
-  out->numLevels = level;
-  out->numNodes = hi;
-  const int nn = hi;
-
-  /* buckets in particle order; first bucket / bucket count of every node */
+  /* buckets in particle order: flags at bucket starts, their exclusive scan */
   int *flag = (int *)pool_alloc((size_t)(n + 1) * 4, s);
   int *rank = (int *)pool_alloc((size_t)(n + 1) * 4, s);
   int *leafAt = (int *)pool_alloc((size_t)n * 4, s);
   cudaChk(cudaMemsetAsync(flag, 0, (size_t)(n + 1) * 4, s));
-  tree_leaf_flags_kernel<<<(nn + tb - 1) / tb, tb, 0, s>>>(t, nn, flag, leafAt);
+  tree_leaf_flags_kernel<<<(cap + tb - 1) / tb, tb, 0, s>>>(t, meta, flag, leafAt); /* node count read on the device */
+  size_t scanBytes = 0;
+  cudaChk(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, flag, rank, n + 1, s));
+  void *scanTmp = pool_alloc(scanBytes, s);
   cudaChk(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, flag, rank, n + 1, s));
-  int nb = 0;
-  cudaChk(cudaMemcpyAsync(&nb, rank + n, 4, cudaMemcpyDeviceToHost, s));
-  cudaChk(cudaStreamSynchronize(s));
-  out->numBuckets = nb;
-  out->d_bucketNode = (int *)pool_alloc((size_t)nb * 4, s);
-  out->d_bucketStarts = (int *)pool_alloc((size_t)nb * 4, s);
-  out->d_bucketSizes = (int *)pool_alloc((size_t)nb * 4, s);
-  out->d_bucketFirst = (int *)pool_alloc((size_t)nn * 4, s);
-  out->d_bucketCount = (int *)pool_alloc((size_t)nn * 4, s);
-  const int m = nn > n ? nn : n;
-  tree_buckets_kernel<<<(m + tb - 1) / tb, tb, 0, s>>>(t, nn, n, flag, rank, leafAt, out->d_bucketNode,
-                                                     out->d_bucketFirst, out->d_bucketCount, out->d_bucketStarts,
-                                                     out->d_bucketSizes);
-  cudaChk(cudaPeekAtLastError());
-  /* tight bounding boxes, bottom-up */
-  out->d_boxlo = (double *)pool_alloc((size_t)nn * 24, s);
-  out->d_boxhi = (double *)pool_alloc((size_t)nn * 24, s);
-  for (int lvl = out->numLevels - 1; lvl >= 0; --lvl) {
-    const int l0 = out->levelStart[lvl], cnt = out->levelStart[lvl + 1] - l0;
-    if (cnt <= 0) continue;
-    tree_boxes_level_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(t, out->d_pos, l0, cnt, out->d_boxlo, out->d_boxhi);
+  tree_set_buckets_kernel<<<1, 1, 0, s>>>(rank, n, meta);
+  int *d_targets = nullptr;
+  if (nCuts > 0) {
+    d_targets = (int *)pool_alloc((size_t)nCuts * 4, s);
+    cudaChk(cudaMemcpyAsync(d_targets, h_targets, (size_t)nCuts * 4, cudaMemcpyHostToDevice, s));
+    tree_cuts_kernel<<<1, 32, 0, s>>>(flag, rank, n, d_targets, nCuts, meta);
+  }
+  g_launches.fetch_add(6);
+  TreeMeta hm;
+  cudaChk(cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaStreamSynchronize(s)); /* the only one: node, bucket and level counts size what follows */
+  out->numLevels = hm.numLevels;
+  out->numNodes = hm.numNodes;
+  out->numBuckets = hm.numBuckets;
+  out->error = hm.error;
+  for (int l = 0; l <= hm.numLevels && l < 66; ++l) out->levelStart[l] = hm.levelStart[l];
+  for (int r = 0; r < 2 * nCuts; ++r) h_cuts[r] = hm.cuts[r];
+  const int nn = hm.numNodes, nb = hm.numBuckets;
+  if (!out->error) {
+    out->d_bucketNode = (int *)pool_alloc((size_t)nb * 4, s);
+    out->d_bucketStarts = (int *)pool_alloc((size_t)nb * 4, s);
+    out->d_bucketSizes = (int *)pool_alloc((size_t)nb * 4, s);
+    out->d_bucketFirst = (int *)pool_alloc((size_t)nn * 4, s);
+    out->d_bucketCount = (int *)pool_alloc((size_t)nn * 4, s);
+    const int m = nn > n ? nn : n;
+    tree_buckets_kernel<<<(m + tb - 1) / tb, tb, 0, s>>>(t, nn, n, flag, rank, leafAt, out->d_bucketNode,
+                                                       out->d_bucketFirst, out->d_bucketCount, out->d_bucketStarts,
+                                                       out->d_bucketSizes);
     cudaChk(cudaPeekAtLastError());
+    /* tight bounding boxes, bottom-up */
+    out->d_boxlo = (double *)pool_alloc((size_t)nn * 24, s);
+    out->d_boxhi = (double *)pool_alloc((size_t)nn * 24, s);
+    for (int lvl = out->numLevels - 1; lvl >= 0; --lvl) {
+      const int l0 = out->levelStart[lvl], cnt = out->levelStart[lvl + 1] - l0;
+      if (cnt <= 0) continue;
+      tree_boxes_level_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(t, out->d_pos, l0, cnt, out->d_boxlo, out->d_boxhi);
+      cudaChk(cudaPeekAtLastError());
+      g_launches.fetch_add(1);
+    }
     g_launches.fetch_add(1);
   }
-  g_launches.fetch_add(3);
-  int herr = 0;
-  cudaChk(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, s));
-  cudaChk(cudaStreamSynchronize(s));
-  if (herr) out->error = herr;
-  pool_free(flag, s); pool_free(rank, s); pool_free(leafAt, s); pool_free(scanTmp, s);
-  pool_free(split, s); pool_free(nkids, s); pool_free(slot, s); pool_free(err, s); pool_free(keys, s);
+  pool_free(flag, s); pool_free(rank, s); pool_free(leafAt, s); pool_free(scanTmp, s); pool_free(d_targets, s);
+  pool_free(split, s); pool_free(slot, s); pool_free(blockSums, s); pool_free(meta, s); pool_free(keys, s);
+}
+
+void cb200_build_tree(const double *d_pos_xyz, const double *d_mass, const double *d_soft, int n, int maxBucket,
+                      const double *rootlo, const double *roothi, cb200_tree *out, void *stream) {
+  TreeInput in;
+  in.pos = d_pos_xyz; in.mass = d_mass; in.soft = d_soft;
+  in.posStride = 3; in.attrStride = 1;
+  build_tree_impl(in, n, maxBucket, rootlo, roothi, out, nullptr, 0, nullptr, (cudaStream_t)stream);
 }
 
 void cb200_tree_free(cb200_tree *t, void *stream) {
@@ -1288,3 +1342,5 @@ void cb200_partition_buckets(const double *cost, int numBuckets, int nRanks, int
 }
 
 } /* extern "C" */
+
+#include "force_step.cuh"

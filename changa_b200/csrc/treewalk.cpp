@@ -46,6 +46,7 @@
 #endif
 
 #include "moments_build.cuh"
+#include "ewald_setup.cuh"
 
 using cb200::MomentNode;
 
@@ -598,63 +599,12 @@ void cb200h_expand_part_list(const int *part, const long long *partMark, int num
  * integer wave vector: hCfac = -(g0 M + g2 T2:hh/2 + g4 T4::hhhh/24), hSfac = -(g3 T3:.hhh/6),
  * g_k = g0 (2 pi/L)^k with signs (+,+,-,-,+,+).  Returns the number of rows (<= cap written). */
 int cb200h_ewald_tables(const double *root, double L, double dEwhCut, double *momc, double *ewt, int cap) {
-  /* index of component (a,b[,c[,d]]) with a<=b<=c<=d in x<y<z among the stored reduced ones, or -1 */
-  static const char *names2[] = {"xx", "xy", "xz", "yy", "yz"};
-  static const char *names3[] = {"xxx", "xyy", "xxy", "yyy", "xxz", "yyz", "xyz"};
-  static const char *names4[] = {"xxxx", "xyyy", "xxxy", "yyyy", "xxxz", "yyyz", "xxyy", "xxyz", "xyyz"};
-  auto key = [](const int *idx, int n) { int c[3] = {0, 0, 0}; for (int i = 0; i < n; ++i) c[idx[i]]++; return c[0] * 25 + c[1] * 5 + c[2]; };
-  auto keyOf = [](const char *nm) { int c[3] = {0, 0, 0}; for (const char *p = nm; *p; ++p) c[*p - 'x']++; return c[0] * 25 + c[1] * 5 + c[2]; };
   double comp[125];
-  bool have[125] = {false};
-  const double r = root[0];
-  for (int i = 0; i < 5; ++i) { comp[keyOf(names2[i])] = root[6 + i] * r * r; have[keyOf(names2[i])] = true; }
-  for (int i = 0; i < 7; ++i) { comp[keyOf(names3[i])] = root[11 + i] * r * r * r; have[keyOf(names3[i])] = true; }
-  for (int i = 0; i < 9; ++i) { comp[keyOf(names4[i])] = root[18 + i] * r * r * r * r; have[keyOf(names4[i])] = true; }
-  /* trace-free completion: T[..zz] = -(T[..xx] + T[..yy]), fewest z first */
-  for (int order = 2; order <= 4; ++order)
-    for (int nz = 2; nz <= order; ++nz)
-      for (int nx = 0; nx <= order - nz; ++nx) {
-        const int ny = order - nz - nx, k = nx * 25 + ny * 5 + nz;
-        if (have[k]) continue;
-        comp[k] = -(comp[(nx + 2) * 25 + ny * 5 + (nz - 2)] + comp[nx * 25 + (ny + 2) * 5 + (nz - 2)]);
-        have[k] = true;
-      }
-  static const char *momcNames[] = {"xx", "yy", "xy", "xz", "yz", "xxx", "xyy", "xxy", "yyy", "xxz", "yyz", "xyz",
-                                    "xxxx", "xyyy", "xxxy", "yyyy", "xxxz", "yyyz", "xxyy", "xxyz", "xyyz", "zz",
-                                    "xzz", "yzz", "zzz", "xxzz", "xyzz", "xzzz", "yyzz", "yzzz", "zzzz"};
-  const double M = root[2];
-  momc[0] = M;
-  for (int i = 0; i < 31; ++i) momc[1 + i] = comp[keyOf(momcNames[i])];
-  const int hreps = (int)std::ceil(dEwhCut);
-  const double alpha = 2.0 / L, k4 = M_PI * M_PI / (alpha * alpha * L * L), c = 2.0 * M_PI / L;
-  int n = 0;
-  for (int hx = -hreps; hx <= hreps; ++hx)
-    for (int hy = -hreps; hy <= hreps; ++hy)
-      for (int hz = -hreps; hz <= hreps; ++hz) {
-        const int h2 = hx * hx + hy * hy + hz * hz;
-        if (h2 == 0 || h2 > dEwhCut * dEwhCut) continue;
-        const double h[3] = {(double)hx, (double)hy, (double)hz};
-        double q2 = 0, q3 = 0, q4 = 0;
-        int idx[4];
-        for (idx[0] = 0; idx[0] < 3; ++idx[0])
-          for (idx[1] = 0; idx[1] < 3; ++idx[1]) {
-            q2 += comp[key(idx, 2)] * h[idx[0]] * h[idx[1]];
-            for (idx[2] = 0; idx[2] < 3; ++idx[2]) {
-              q3 += comp[key(idx, 3)] * h[idx[0]] * h[idx[1]] * h[idx[2]];
-              for (idx[3] = 0; idx[3] < 3; ++idx[3])
-                q4 += comp[key(idx, 4)] * h[idx[0]] * h[idx[1]] * h[idx[2]] * h[idx[3]];
-            }
-          }
-        const double g0 = std::exp(-k4 * h2) / (M_PI * h2 * L);
-        const double g2 = -c * c * g0, g3 = -c * c * c * g0, g4 = c * c * c * c * g0;
-        if (n < cap) {
-          double *row = ewt + 5 * (size_t)n;
-          row[0] = c * hx; row[1] = c * hy; row[2] = c * hz;
-          row[3] = -(g0 * M + g2 * q2 / 2.0 + g4 * q4 / 24.0);
-          row[4] = -(g3 * q3 / 6.0);
-        }
-        ++n;
-      }
+  cb200::ewald_complete_moments(root, comp, momc); /* ewald_setup.cuh: shared with the device set-up kernel */
+  std::vector<int> h(3 * (size_t)(cap > 0 ? cap : 1));
+  const int n = cb200::ewald_h_vectors(dEwhCut, h.data(), cap);
+  for (int i = 0; i < n && i < cap; ++i)
+    cb200::ewald_h_row(comp, root[2], L, h[3 * i], h[3 * i + 1], h[3 * i + 2], ewt + 5 * (size_t)i);
   return n;
 }
 

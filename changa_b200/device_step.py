@@ -177,268 +177,59 @@ class DeviceTreeStep:
 class RawParticleStep:
     """The whole force step from UNSORTED particles (SURVEY f1 + f2): per step the host hands over
     positions, masses and softenings (40 bytes per particle) and gets accelerations back in its
-    own particle order; keys, sort, tree topology, boxes, moments, interaction lists, forces and
-    the Ewald sum all run on the device (cb200_build_tree, cb200_build_moments,
-    cb200_walk_device, cb200_*_list_device_ex, cb200_EwaldHost)."""
+    own particle order.  A thin view of the in-library step (changa_b200.step.NativeStep ->
+    cb200_step_run): upload, NCCL all-gather, keys, sort, tree, moments, lists, forces, Ewald and the
+    copy back all happen inside libchanga_b200.so; no torch on this path."""
 
     def __init__(self, hc, pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, ewald=None, max_bucket=12,
-                 root_lo=(-0.5, -0.5, -0.5), root_hi=(0.5, 0.5, 0.5), dist=None, rank=0, world=1,
-                 rung=None, active_rung=0):
+                 root_lo=(-0.5, -0.5, -0.5), root_hi=(0.5, 0.5, 0.5), comm=None, rung=None, active_rung=0,
+                 overlap_ewald=True, cost_cuts=True):
         """rung (one byte per particle, caller order) + active_rung: a multistep force step
          -- only buckets holding a particle with rung >= active_rung get lists and
         forces (Compute.cpp:1278,1574), only particles with rung >= active_rung get the Ewald sum
-        (Ewald.cpp:416-437); the sets are made on the device (cb200_active_sets_device) and the
-        walk is cb200_walk_device_active.  Rows of inactive buckets come back zero.
+        (Ewald.cpp:416-437).  Rows of inactive buckets come back zero.
 
-        world > 1 (one process per GPU, torch.distributed `dist`): every rank holds rows
-        [rank*chunk, (rank+1)*chunk) of the particle set on its host; ONE all-gather per step
+        comm (changa_b200.step.Comm, world > 1): one process per GPU; every rank holds rows
+        [rank*chunk, (rank+1)*chunk) of the particle set on its host, ONE all-gather per step
         replicates the 40-byte records, every rank builds the same tree and moments, then walks,
-        evaluates and returns only its own contiguous SFC range of buckets (equal particle counts;
-        accelerations never leave the owning GPU).  run() then returns (caller indices, rows)."""
-        import torch
-        assert hc.L.cb200_real_bytes() == 4, "RawParticleStep holds float32 device buffers: use the float build"
-        self.torch, self.hc = torch, hc
-        self.dist, self.rank, self.world = dist, int(rank), int(world)
-        self.theta, self.nrep, self.period = float(theta), int(n_replicas), float(period)
-        self.ewald, self.max_bucket = ewald, int(max_bucket)
-        self.lo = np.ascontiguousarray(root_lo, dtype=np.float64)
-        self.hi = np.ascontiguousarray(root_hi, dtype=np.float64)
-        self.ext = torch.cuda.Stream()
-        self.stream = self.ext.cuda_stream
-        n = len(pos)
-        self.n = n
-        # {x, y, z, mass, soft}: the 40-byte record that crosses PCIe and NVLink; only this rank's rows
-        self.chunk = -(-n // self.world)
-        mine = np.zeros((self.chunk, 5))
-        mine[:, 4] = 1.0
-        # pad rows (only when world does not divide n) never reach the tree: the gathered array is
-        # cut back to n rows
-        lo_r = self.rank * self.chunk
-        hi_r = min(n, lo_r + self.chunk)
-        k = max(0, hi_r - lo_r)
-        mine[:k, :3] = np.asarray(pos)[lo_r:hi_r]
-        mine[:k, 3] = np.broadcast_to(mass, (n,))[lo_r:hi_r]
-        mine[:k, 4] = np.broadcast_to(soft, (n,))[lo_r:hi_r]
-        self.h = {"rec": torch.from_numpy(mine).pin_memory()}
-        self.h2d_bytes = self.h["rec"].numel() * 8
-        self.active_rung = int(active_rung)
-        if rung is not None:
-            r = np.zeros(self.chunk, dtype=np.uint8)
-            r[:k] = np.asarray(rung, dtype=np.uint8)[lo_r:hi_r]
-            self.h["rung"] = torch.from_numpy(r).pin_memory()
-            self.h2d_bytes += self.chunk
-        rows = n if self.world == 1 else 2 * self.chunk + 64
-        self.out = torch.zeros((rows, 5), dtype=torch.float32).pin_memory()
-        self.out_idx = torch.zeros(rows, dtype=torch.int32).pin_memory()
-        self.d2h_bytes = self.out.numel() * 4
-        self.dev = None
+        evaluates and returns only its own contiguous SFC range of buckets.  run() then returns
+        (caller indices, rows)."""
+        from .step import NativeStep
+        self.hc = hc
+        self.n = len(pos)
+        self.st = NativeStep(hc, self.n, theta=theta, n_replicas=n_replicas, period=period, ewald=ewald,
+                             max_bucket=max_bucket, root_lo=root_lo, root_hi=root_hi, comm=comm,
+                             active_rung=active_rung if rung is not None else 0, overlap_ewald=overlap_ewald,
+                             cost_cuts=cost_cuts)
+        self.world, self.rank = self.st.world, self.st.rank
+        self.st.set_particles(pos, mass, soft, rung)
         self.info = None
-        self._ew = None
+        self.h2d_bytes = self.d2h_bytes = 0
 
     def update_positions(self, pos):
-        """new positions (caller order) for the next run(): an integrator's drift.  world == 1 only."""
-        assert self.world == 1
-        self.h["rec"][: self.n, :3] = self.torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float64))
+        """new positions (caller order) for the next run(): an integrator's drift"""
+        lo, hi = self.st.my_rows()
+        self.st.rec.array[: hi - lo, :3] = np.asarray(pos, dtype=np.float64)[lo:hi]
 
-    def run(self, phases=None, keep_tree=False, count_pairs=False):
-        """count_pairs: also leave {pc_pairs, pp_pairs} (sum over buckets of list length x bucket
-        size, as Compute.cpp:1643-1651 counts interactions) in self.info"""
-        torch, hc, L, s, n = self.torch, self.hc, self.hc.L, self.stream, self.n
-        marks = []
-
-        def mark(name):
-            if phases is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(self.ext)
-                marks.append((name, e))
-
-        with torch.cuda.stream(self.ext):
-            if self.dev is None:
-                self.dev = {"rec": torch.empty_like(self.h["rec"], device="cuda"),
-                            "all": torch.empty((self.chunk * self.world, 5), dtype=torch.float64, device="cuda"),
-                            "pos": torch.empty((n, 3), dtype=torch.float64, device="cuda"),
-                            "mass": torch.empty(n, dtype=torch.float64, device="cuda"),
-                            "soft": torch.empty(n, dtype=torch.float64, device="cuda"),
-                            "vars": torch.empty((n, 5), dtype=torch.float32, device="cuda")}
-                if self.world == 1:
-                    self.dev["out"] = torch.empty((n, 5), dtype=torch.float32, device="cuda")
-            d = self.dev
-            multistep = "rung" in self.h
-            if multistep and "rung" not in d:
-                d["rung"] = torch.empty_like(self.h["rung"], device="cuda")
-                d["rung_all"] = torch.empty(self.chunk * self.world, dtype=torch.uint8, device="cuda")
-                d["markers"] = torch.empty(n, dtype=torch.int32, device="cuda")
-            mark("start")
-            d["rec"].copy_(self.h["rec"], non_blocking=True)
-            if multistep:
-                d["rung"].copy_(self.h["rung"], non_blocking=True)
-            mark("h2d")
-            if self.world > 1:
-                self.dist.all_gather_into_tensor(d["all"], d["rec"])
-                full = d["all"]
-                if multistep:
-                    self.dist.all_gather_into_tensor(d["rung_all"], d["rung"])
-            else:
-                full = d["rec"]
-                if multistep:
-                    d["rung_all"] = d["rung"]
-            d["pos"].copy_(full[:n, :3])
-            d["mass"].copy_(full[:n, 3])
-            d["soft"].copy_(full[:n, 4])
-            mark("gather")
-            tr = hc.T.DevTree()
-            L.cb200_build_tree(d["pos"].data_ptr(), d["mass"].data_ptr(), d["soft"].data_ptr(), n, self.max_bucket,
-                               self.lo.ctypes.data, self.hi.ctypes.data, C.byref(tr), s)
-            if tr.error:
-                raise RuntimeError("device tree build: node capacity exceeded")
-            mark("tree")
-            nn, nb = tr.numNodes, tr.numBuckets
-            key = (nn,)
-            if d.get("key") != key:  # node-sized buffers follow the tree
-                d["mom32"] = torch.empty((nn, 27), dtype=torch.float32, device="cuda")
-                d["mom64"] = torch.empty((nn, 27), dtype=torch.float64, device="cuda")
-                d["pk_mom"] = torch.empty(nn * L.cb200_packed_moment_bytes(), dtype=torch.uint8, device="cuda")
-                d["key"] = key
-            mom32, mom64 = d["mom32"], d["mom64"]
-            lvl = C.addressof(tr) + hc.T.DevTree.levelStart.offset
-            L.cb200_build_moments(tr.d_pos, tr.d_mass, tr.d_soft, n, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last,
-                                  tr.d_geolo, tr.d_geohi, tr.d_boxlo, tr.d_boxhi, lvl, tr.numLevels, nn,
-                                  mom32.data_ptr(), mom64.data_ptr(), s)
-            mark("moments")
-            b0, b1, p0, p1 = 0, nb, 0, n
-            active_ptr, n_act = None, n
-            if multistep:
-                if d.get("nb") != nb:
-                    d["bucket_active"] = torch.empty(nb, dtype=torch.uint8, device="cuda")
-                    d["nb"] = nb
-                counts = (C.c_int * 2)()
-                L.cb200_active_sets_device(d["rung_all"].data_ptr(), tr.d_order, n, tr.d_bucketStarts,
-                                           tr.d_bucketSizes, nb, self.active_rung, d["bucket_active"].data_ptr(),
-                                           d["markers"].data_ptr(), counts, s)
-                active_ptr, n_act = d["bucket_active"].data_ptr(), int(counts[1])
-                self.active = {"buckets": int(counts[0]), "particles": n_act}
-            if self.world > 1:  # my contiguous SFC range of buckets: equal particle counts, never splits a bucket
-                starts = torch.empty(nb, dtype=torch.int32, device="cuda")
-                L.cb200_copy_device(starts.data_ptr(), tr.d_bucketStarts, nb * 4, s)
-                want = torch.tensor([self.rank * n // self.world, (self.rank + 1) * n // self.world],
-                                    dtype=torch.int32, device="cuda")
-                if multistep and n_act > 0:  # equal ACTIVE particle counts
-                    at = [min(n_act - 1, self.rank * n_act // self.world),
-                          min(n_act - 1, (self.rank + 1) * n_act // self.world)]
-                    want = d["markers"][at]
-                cut = torch.searchsorted(starts, want, right=False).tolist()
-                b0 = 0 if self.rank == 0 else int(cut[0])
-                b1 = nb if self.rank == self.world - 1 else int(cut[1])
-                edge = starts[[min(b0, nb - 1), min(b1, nb - 1)]].tolist()
-                p0 = int(edge[0]) if b0 < nb else n
-                p1 = int(edge[1]) if b1 < nb else n
-            self.range = (b0, b1, p0, p1)
-            lists = hc.T.Lists()
-            L.cb200_walk_device_active(nn, nb, tr.numLevels, lvl, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first,
-                                       tr.d_last, tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo,
-                                       tr.d_boxhi, mom64.data_ptr(), self.theta, self.nrep, self.period, b0, b1,
-                                       active_ptr, C.byref(lists), s)
-            if lists.error:
-                raise RuntimeError(f"device walk: per-node capacity exceeded (error {lists.error})")
-            mark("walk")
-            L.cb200_pack_moments_device(mom32.data_ptr(), d["pk_mom"].data_ptr(), nn, s)
-            vars_ = d["vars"]
-            L.cb200_zero_vars_device(vars_.data_ptr(), n, s)
-            P, V, M = tr.d_packedParts, vars_.data_ptr(), d["pk_mom"].data_ptr()
-            fper = self.period if (self.nrep or self.ewald is not None) else 0.0
-            mark("pack")
-            if self.ewald is not None:
-                from .tree import ewald_tables_fast as ewald_tables
-                hc.stream_synchronize(s)
-                root = mom64[0].cpu().numpy()
-                momc, ewt = ewald_tables(root, self.period, self.ewald.get("dEwhCut", 2.8))
-                if self._ew is None:
-                    self._ew = hc.EwaldHostMemorySetup(1, len(ewt), 0)
-                if p1 > p0:
-                    hc.fill_ewald(self._ew, root, momc, ewt, self.period, float(self.ewald.get("dEwCut", 2.6)),
-                                  self.nrep, active=None, first=p0, last=p1 - 1)
-                    if multistep:  # large-phase form: the markers of my particle range, already on the device
-                        mk = d["markers"][:n_act]
-                        i0, i1 = torch.searchsorted(mk, torch.tensor([p0, p1], dtype=torch.int32, device="cuda")).tolist()
-                        if i1 > i0:
-                            L.cb200_ewald_device(P, V, mk.data_ptr() + 4 * i0, i1 - i0, self._ew.cachedData,
-                                                 self._ew.ewt, s)
-                    else:
-                        L.cb200_EwaldHost(P, V, C.byref(self._ew), s, None, 0, 0)
-            mark("ewald")
-            mx = self.max_bucket
-            L.cb200_cell_list_device_ex(P, V, M, lists.d_cell, lists.d_cellMarkers, lists.d_starts, lists.d_sizes,
-                                        nb, fper, mx, s)
-            L.cb200_part_list_device_ex(P, V, P, lists.d_part, lists.d_partMarkers, lists.d_starts, lists.d_sizes,
-                                        nb, fper, mx, s)
-            if lists.nSoft:
-                L.cb200_part_list_device_ex(P, V, lists.d_nodeParticles, lists.d_soft, lists.d_softMarkers,
-                                            lists.d_starts, lists.d_sizes, nb, fper, mx, s)
-            mark("forces")
-            # back to the caller's particle order: out[order[i]] = vars[i]
-            order = torch.empty(n, dtype=torch.int32, device="cuda")
-            L.cb200_copy_device(order.data_ptr(), tr.d_order, n * 4, s)
-            if self.world == 1:
-                d["out"].index_copy_(0, order.long(), vars_)
-                self.out.copy_(d["out"], non_blocking=True)
-            else:  # my rows only, with the caller indices they belong to
-                if p1 - p0 > self.out.shape[0]:
-                    raise RuntimeError("bucket range larger than the result buffer")
-                self.out[: p1 - p0].copy_(vars_[p0:p1], non_blocking=True)
-                self.out_idx[: p1 - p0].copy_(order[p0:p1], non_blocking=True)
-            mark("d2h")
-            self.info = {"nodes": nn, "buckets": nb, "levels": tr.numLevels, "nCell": int(lists.nCell),
-                         "nSoft": int(lists.nSoft), "nPart": int(lists.nPart)}
-            if keep_tree:
-                self.kept_tree = self._download_tree(tr)
-            if count_pairs:
-                def dev_i32(ptr, count):
-                    t = torch.empty(count, dtype=torch.int32, device="cuda")
-                    L.cb200_copy_device(t.data_ptr(), ptr, count * 4, s)
-                    return t.long()
-                sizes = dev_i32(lists.d_sizes, nb)
-                pairs = [int((torch.diff(dev_i32(m, nb + 1)) * sizes).sum().item())
-                         for m in (lists.d_cellMarkers, lists.d_partMarkers, lists.d_softMarkers)]
-                self.info.update(pc_pairs=pairs[0], pp_pairs=pairs[1] + pairs[2])
-            L.cb200_lists_free(C.byref(lists), s)
-            L.cb200_tree_free(C.byref(tr), s)
-            hc.stream_synchronize(s)
+    def run(self, phases=None, keep_tree=False, count_pairs=False, keep_lists=False):
+        """phases: optional dict, the milliseconds of each phase are ADDED to it (CUDA events on the step's
+        stream).  keep_tree: leave the downloaded tree arrays in self.kept_tree."""
+        res = self.st.run(keep_lists=keep_lists)
         if phases is not None:
-            for (_, a), (name, b) in zip(marks, marks[1:]):
-                phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
+            for k, v in self.st.phases().items():
+                phases[k] = phases.get(k, 0.0) + v
+        self.range = (res.bucketLo, res.bucketHi, res.partLo, res.partHi)
+        self.info = {"nodes": res.numNodes, "buckets": res.numBuckets, "levels": res.numLevels, "nCell": int(res.nCell),
+                     "nSoft": int(res.nSoft), "nPart": int(res.nPart), "pc_pairs": int(res.pcPairs),
+                     "pp_pairs": int(res.ppPairs)}
+        if self.st.cfg.activeRung > 0:
+            self.active = {"buckets": res.activeBuckets, "particles": res.activeParticles}
+        self.h2d_bytes, self.d2h_bytes = int(res.h2dBytes), int(res.d2hBytes)
+        if keep_tree:
+            self.kept_tree = self.st.tree()
         if self.world > 1:
-            k = self.range[3] - self.range[2]
-            self.d2h_bytes = k * 24  # 5 floats + the caller index per row
-            return self.out_idx.numpy()[:k], self.out.numpy()[:k]
-        return self.out.numpy()
-
-    def _download_tree(self, tr):
-        torch, L, s = self.torch, self.hc.L, self.stream
-
-        def arr(ptr, count, dtype):
-            t = torch.empty(count, dtype=dtype, device="cuda")
-            if count:
-                L.cb200_copy_device(t.data_ptr(), ptr, count * t.element_size(), s)
-            self.hc.stream_synchronize(s)
-            return t.cpu().numpy()
-        n, nn, nb = tr.numParticles, tr.numNodes, tr.numBuckets
-        i32, f64 = torch.int32, torch.float64
-        out = {"order": arr(tr.d_order, n, i32), "pos": arr(tr.d_pos, 3 * n, f64).reshape(n, 3),
-               "mass": arr(tr.d_mass, n, f64), "soft": arr(tr.d_soft, n, f64),
-               "level_start": np.array(tr.levelStart[:tr.numLevels + 1], dtype=np.int32)}
-        for name, ptr in (("child0", tr.d_child0), ("child1", tr.d_child1), ("parent", tr.d_parent),
-                          ("first", tr.d_first), ("last", tr.d_last), ("bucket_first", tr.d_bucketFirst),
-                          ("bucket_count", tr.d_bucketCount)):
-            out[name] = arr(ptr, nn, i32)
-        for name, ptr in (("geolo", tr.d_geolo), ("geohi", tr.d_geohi), ("boxlo", tr.d_boxlo), ("boxhi", tr.d_boxhi)):
-            out[name] = arr(ptr, 3 * nn, f64).reshape(nn, 3)
-        for name, ptr in (("bucket_node", tr.d_bucketNode), ("bucket_starts", tr.d_bucketStarts),
-                          ("bucket_sizes", tr.d_bucketSizes)):
-            out[name] = arr(ptr, nb, i32)
-        return out
+            return self.st.idx.array[: res.rows], self.st.out.array[: res.rows]
+        return self.st.out.array[: self.n]
 
     def free(self):
-        if self._ew is not None:
-            self.hc.EwaldHostMemoryFree(self._ew, 0)
-            self._ew = None
-        self.h = self.out = self.dev = None
+        self.st.free()

@@ -124,6 +124,13 @@ C_ABI_SYMBOLS = [
     "cb200_build_moments", "cb200_partition_buckets", "cb200_walk_device", "cb200_lists_free",
     "cb200_walk_device_active", "cb200_active_sets_device",
     "cb200_build_tree", "cb200_tree_free",
+    "cb200_comm_id_bytes", "cb200_comm_unique_id", "cb200_comm_init", "cb200_comm_destroy", "cb200_comm_rank",
+    "cb200_comm_world", "cb200_comm_nccl_version", "cb200_comm_allreduce_f64", "cb200_comm_barrier",
+    "cb200_comm_allgather", "cb200_cost_targets",
+    "cb200_step_create", "cb200_step_destroy", "cb200_step_chunk_rows", "cb200_step_out_capacity",
+    "cb200_step_stream", "cb200_step_device_records", "cb200_step_device_rungs", "cb200_step_run",
+    "cb200_step_tree", "cb200_step_lists", "cb200_step_moments_f64", "cb200_step_packed_moments",
+    "cb200_step_vars", "cb200_step_markers",
 ]
 
 CALLBACK_FN = C.CFUNCTYPE(None, C.c_void_p)

@@ -279,6 +279,89 @@ void cb200_lists_free(cb200_lists *lists, void *stream);
 void cb200_partition_buckets(const double *cost, int numBuckets, int nRanks,
                              int *cuts);
 
+/* --- new: one communicator per process, the whole force step in the library -------------- */
+/* One process per GPU (one logical node per device, DataManager.h:329-337).  The host program makes a
+ * 128-byte id on one rank (cb200_comm_unique_id), hands it to the others by its own means (a Charm++
+ * broadcast, MPI, a file) and every rank calls cb200_comm_init after cb200_set_device.  NCCL is loaded
+ * with dlopen("libnccl.so.2") on first use: single-GPU hosts do not need it. */
+typedef struct cb200_comm cb200_comm;
+size_t cb200_comm_id_bytes(void);                 /* sizeof(ncclUniqueId) = 128 */
+void cb200_comm_unique_id(void *id);              /* ncclGetUniqueId */
+cb200_comm *cb200_comm_init(int rank, int world, const void *id);
+void cb200_comm_destroy(cb200_comm *comm);
+int cb200_comm_rank(const cb200_comm *comm);      /* 0 for NULL */
+int cb200_comm_world(const cb200_comm *comm);     /* 1 for NULL */
+int cb200_comm_nccl_version(void);
+/* element-wise reduction of n HOST doubles over the ranks (op 0 sum, 1 max, 2 min); blocking */
+void cb200_comm_allreduce_f64(cb200_comm *comm, double *h_values, int n, int op, void *stream);
+void cb200_comm_barrier(cb200_comm *comm, void *stream);
+/* ncclAllGather of equal byte slices: d_recv gets world x sendBytes in rank order */
+void cb200_comm_allgather(cb200_comm *comm, const void *d_send, void *d_recv, size_t sendBytes, void *stream);
+
+/* The force step from UNSORTED particles (SURVEY f1 + f2 + 8e).  Every rank holds rows
+ * [rank * chunk, (rank + 1) * chunk) of the box's {x, y, z, mass, soft} records (doubles, caller order;
+ * chunk = ceil(numParticles / world), the tail of the last rank is padding).  Per step: upload of the
+ * slice, ONE ncclAllGather of the records, then on every rank keys, sort, tree, boxes, moments (all
+ * replicated), and for the rank's own contiguous SFC range of buckets the interaction lists, p-c, p-p,
+ * softened cells and the Ewald sum; the rank's rows come back with the caller indices they belong to.
+ * Bucket ranges: equal particle counts, or (costCuts) equal cost as measured by the previous step
+ * (198 x p-c pairs + 30 x p-p pairs; never splits a bucket).  Multistep: see
+ * cb200_active_sets_device; ranks are then cut by active-particle count. */
+typedef struct cb200_step_config {
+  long long numParticles;   /* the whole box, all ranks */
+  int maxBucket;            /* 12 */
+  int nReplicas;            /* periodic replicas of the walk (0: isolated) */
+  int ewald;                /* 1: add the Ewald correction (periodic boxes) */
+  int activeRung;           /* > 0: multistep step, rung bytes are uploaded with the records */
+  int overlapEwald;         /* 1: the Ewald kernel runs on a second stream under the tree walk */
+  int costCuts;             /* 1: cut ranks by last step's measured cost */
+  double theta, period, dEwCut, dEwhCut;
+  double rootlo[3], roothi[3];
+} cb200_step_config;
+
+enum { CB200_PH_H2D = 0, CB200_PH_GATHER, CB200_PH_TREE, CB200_PH_MOMENTS, CB200_PH_EWALD, CB200_PH_WALK,
+       CB200_PH_PC, CB200_PH_PP, CB200_PH_FINISH, CB200_PH_TOTAL, CB200_PH_COUNT };
+
+typedef struct cb200_step_result {
+  int error;                /* 0 ok; 11: node capacity; 21-23: walk (see cb200_lists); 30: result buffer too small */
+  int numNodes, numBuckets, numLevels;
+  int bucketLo, bucketHi, partLo, partHi; /* this rank's share (tree order) */
+  int activeBuckets, activeParticles;     /* multistep */
+  int rows;                               /* result rows of this rank */
+  long long nCell, nSoft, nPart;          /* list entries of this rank */
+  long long pcPairs, ppPairs;             /* pair interactions of this rank (Compute.cpp:1643-1651) */
+  long long h2dBytes, d2hBytes;
+  double cost;                            /* 198 pcPairs + 30 ppPairs */
+  float ms[CB200_PH_COUNT];               /* CUDA events on the step's stream; with overlapEwald the Ewald
+                                             kernel's time lies inside the walk phase */
+} cb200_step_result;
+
+/* the costCuts rule on the host: last step's boundaries prevCut[0..world] (particle indices) and the cost
+ * each rank measured between them -> targets[0..world] for the next step (cost taken as uniform inside
+ * each old range; the device snaps every target to the next bucket start) */
+void cb200_cost_targets(const long long *prevCut, const double *prevCost, int world, long long numParticles, int *targets);
+
+typedef struct cb200_step cb200_step;
+cb200_step *cb200_step_create(cb200_comm *comm /* NULL: one GPU */, const cb200_step_config *cfg);
+void cb200_step_destroy(cb200_step *step);
+int cb200_step_chunk_rows(const cb200_step *step);
+int cb200_step_out_capacity(const cb200_step *step);
+void *cb200_step_stream(const cb200_step *step);
+double *cb200_step_device_records(const cb200_step *step);
+unsigned char *cb200_step_device_rungs(const cb200_step *step);
+/* h_records NULL: the records are already in cb200_step_device_records().  h_out NULL: results stay on the
+ * device.  world == 1: h_out gets numParticles VariablePartData rows in the caller's order (h_index unused);
+ * world > 1: result->rows rows of this rank's SFC range, caller indices in h_index.  Blocking. */
+void cb200_step_run(cb200_step *step, const double *h_records, const unsigned char *h_rungs, void *h_out, int *h_index,
+                    int outCapacityRows, int keepLists, cb200_step_result *result);
+/* products of the last run, valid until the next run / destroy (tests, parity sampling) */
+const cb200_tree *cb200_step_tree(const cb200_step *step);
+const cb200_lists *cb200_step_lists(const cb200_step *step);     /* only after keepLists = 1 */
+const double *cb200_step_moments_f64(const cb200_step *step);    /* 27 doubles per node */
+const void *cb200_step_packed_moments(const cb200_step *step);
+const void *cb200_step_vars(const cb200_step *step);             /* VariablePartData, tree order */
+const int *cb200_step_markers(const cb200_step *step);           /* multistep: active particles, tree order */
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -14,8 +14,9 @@
  *     and softening) into a per-warp two-stage ring one chunk ahead; a lane copies and later
  *     reads only its OWN rows, so the chunk needs no __syncwarp and no register is held while the
  *     rows are in flight;
- *   - the tile loop is instantiated per number of target pairs (1..PB/2): no bound test or
- *     branch between the bodies, which are independent and interleave freely;
+ *   - the two bodies that share a target pair (sources A and B of the lane) sit in one basic block
+ *     and interleave; pairs are guarded by a warp-uniform test (one copy of the code: see the note at
+ *     the chunk loop about the instruction cache);
  *   - the Newtonian body has no select on coincidence: a half inside the softening sphere OR at
  *     zero distance reads rsqrt(+inf) = 0 (one FSETP + one FSEL per half), and the rare lanes
  *     that met one redo exactly those halves with the scalar spline afterwards;
@@ -260,67 +261,63 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
       for (int j = 0; j < NP; ++j) { ax[j] = ay[j] = az[j] = pot[j] = 0ull; idt[2 * j] = idt[2 * j + 1] = 0.0f; }
       bool dirty = false; /* the scratch holds spline contributions of this pass */
 
-      /* the chunk loop, instantiated for NPR target pairs */
-      auto run = [&](auto npr_tag) {
-        constexpr int NPR = decltype(npr_tag)::value;
-        for (int c = 0; c < nchunks; ++c) {
-          const unsigned st = c & 1;
-          if (c + 1 < nchunks) gather(st ^ 1, nxtA.index, nxtB.index);
-          if (lastPass && c == nchunks - 1) { /* the next bucket's first loads ride under this chunk */
-            prefetch_bucket(mn);
-            prefetched = true;
-          }
-          cp_async_commit();
-          ILCell nnA = none, nnB = none;
-          const int e2 = (c + 2) * kPpChunk + lane;
-          if (e2 < len) nnA = mylist[e2];
-          if (e2 + 32 < len) nnB = mylist[e2 + 32];
-          cp_async_wait<1>();
+      /* The chunk loop.  ONE copy of the bodies, guarded per target pair by a warp-uniform test: a first
+       * version instantiated the loop per pair count (no guards, 12 copies, 4768 SASS instructions = 76 KB)
+       * and ran at 13.6 no-instruction stalls per issue -- the 16 resident warps of an SM sat in different
+       * copies and thrashed the instruction cache (profiles/r02b_ncu_part_list_stream_icache.json). */
+      for (int c = 0; c < nchunks; ++c) {
+        const unsigned st = c & 1;
+        if (c + 1 < nchunks) gather(st ^ 1, nxtA.index, nxtB.index);
+        if (lastPass && c == nchunks - 1) { /* the next bucket's first loads ride under this chunk */
+          prefetch_bucket(mn);
+          prefetched = true;
+        }
+        cp_async_commit();
+        ILCell nnA = none, nnB = none;
+        const int e2 = (c + 2) * kPpChunk + lane;
+        if (e2 < len) nnA = mylist[e2];
+        if (e2 + 32 < len) nnB = mylist[e2 + 32];
+        cp_async_wait<1>();
 
-          SrcReg sa = load_src(st, 0, curA);
-          const bool hasB = c * kPpChunk + 32 < len; /* warp-uniform */
-          SrcReg sb = nowhere;
-          if (hasB) sb = load_src(st, 1, curB);
-          const int away = ((curA.offsetID >> 22) ^ kHomeBox) | ((curB.offsetID >> 22) ^ kHomeBox);
-          if (__any_sync(kFull, (away & 0x1ff) != 0)) {
-            shift_src(sa, curA.offsetID);
-            shift_src(sb, curB.offsetID);
-          }
-          unsigned slowA = 0, slowB = 0;
-          if (hasB) {
+        SrcReg sa = load_src(st, 0, curA);
+        const bool hasB = c * kPpChunk + 32 < len; /* warp-uniform */
+        SrcReg sb = nowhere;
+        if (hasB) sb = load_src(st, 1, curB);
+        const int away = ((curA.offsetID >> 22) ^ kHomeBox) | ((curB.offsetID >> 22) ^ kHomeBox);
+        if (__any_sync(kFull, (away & 0x1ff) != 0)) {
+          shift_src(sa, curA.offsetID);
+          shift_src(sb, curB.offsetID);
+        }
+        unsigned slowA = 0, slowB = 0;
+        if (hasB) {
 #pragma unroll
-            for (int j = 0; j < NPR; ++j) {
+          for (int j = 0; j < NP; ++j) {
+            if (j < npairs) { /* two independent bodies on one read of the target pair */
               const TargetSoftPair p = lds_target_soft_pair(tgtAddr + j * 48u);
               pp_body(sa, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1], slowA);
               pp_body(sb, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1], slowB);
             }
-          } else {
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < NPR; ++j) {
+          for (int j = 0; j < NP; ++j) {
+            if (j < npairs) {
               const TargetSoftPair p = lds_target_soft_pair(tgtAddr + j * 48u);
               pp_body(sa, p, ax[j], ay[j], az[j], pot[j], idt[2 * j], idt[2 * j + 1], slowA);
             }
           }
-          if (__any_sync(kFull, (slowA | slowB) != 0)) { /* rare: a pair inside the softening length */
-            if (!dirty) {
-              for (int r = 0; r < 10 * npairs; ++r)
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(redCol + r * kRedPitch), "f"(0.0f) : "memory");
-              dirty = true;
-            }
-            if (slowA) pp_near_lane(sa.x, sa.y, sa.z, sa.m, sa.soft, npairs, tgtAddr, redCol);
-            if (slowB) pp_near_lane(sb.x, sb.y, sb.z, sb.m, sb.soft, npairs, tgtAddr, redCol);
-          }
-          curA = nxtA; curB = nxtB;
-          nxtA = nnA; nxtB = nnB;
         }
-      };
-      switch (npairs) {
-        case 1: run(std::integral_constant<int, 1>()); break;
-        case 2: run(std::integral_constant<int, (NP >= 2 ? 2 : NP)>()); break;
-        case 3: run(std::integral_constant<int, (NP >= 3 ? 3 : NP)>()); break;
-        case 4: run(std::integral_constant<int, (NP >= 4 ? 4 : NP)>()); break;
-        case 5: run(std::integral_constant<int, (NP >= 5 ? 5 : NP)>()); break;
-        default: run(std::integral_constant<int, NP>()); break;
+        if (__any_sync(kFull, (slowA | slowB) != 0)) { /* rare: a pair inside the softening length */
+          if (!dirty) {
+            for (int r = 0; r < 10 * npairs; ++r)
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(redCol + r * kRedPitch), "f"(0.0f) : "memory");
+            dirty = true;
+          }
+          if (slowA) pp_near_lane(sa.x, sa.y, sa.z, sa.m, sa.soft, npairs, tgtAddr, redCol);
+          if (slowB) pp_near_lane(sb.x, sb.y, sb.z, sb.m, sb.soft, npairs, tgtAddr, redCol);
+        }
+        curA = nxtA; curB = nxtB;
+        nxtA = nnA; nxtB = nnB;
       }
 
       /* park partial sums: row (particle*5 + component), column lane */

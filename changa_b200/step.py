@@ -197,6 +197,18 @@ class NativeStep:
         if rung is not None and self.rung is not None:
             self.rung.array[:k] = np.asarray(rung, dtype=np.uint8)[lo:hi]
 
+    def set_rows(self, pos_rows, mass, soft, rung_rows=None):
+        """the same from this rank's OWN rows (my_rows()): what a host that holds only its share passes"""
+        lo, hi = self.my_rows()
+        k = max(0, hi - lo)
+        assert len(pos_rows) == k
+        r = self.rec.array
+        r[:k, :3] = pos_rows
+        r[:k, 3] = mass
+        r[:k, 4] = soft
+        if rung_rows is not None and self.rung is not None:
+            self.rung.array[:k] = np.asarray(rung_rows, dtype=np.uint8)
+
     def upload(self):
         """records to the device once (then run(resident=True) times the step without the host copies)"""
         d = self.L.cb200_step_device_records(self.handle)

@@ -161,19 +161,19 @@ def test_tree_workloads_match_oracle(hc, name, n):
 
 
 def test_resident_path_equals_abi_path(hc):
-    """device-pointer entry points (bench.py's resident step) give the same bits as the
+    """device-pointer entry points (changa_b200.resident.ResidentStep) give the same bits as the
     host-buffer entry points"""
     import torch
     from changa_b200.hostcuda import ForceStep
     from changa_b200.workloads import config_workload
-    import bench
+    from changa_b200.resident import ResidentStep
     wl = config_workload("cube300", n=12 ** 3)
     step = ForceStep(hc, wl)
     try:
         a = step.run().copy()
     finally:
         step.free()
-    rs = bench.ResidentStep(hc, wl, torch, None, 0, 1)
+    rs = ResidentStep(hc, wl, torch)
     with torch.cuda.stream(rs.ext):
         rs.step()
     torch.cuda.synchronize()
@@ -188,7 +188,7 @@ def test_resident_steps_share_one_self_resetting_counter(hc):
     import torch
     from changa_b200.hostcuda import ForceStep
     from changa_b200.workloads import config_workload, random_workload
-    import bench
+    from changa_b200.resident import ResidentStep
     wls = [config_workload("cube300", n=10 ** 3), random_workload(seed=11, n_buckets=37, max_bucket=12),
            random_workload(seed=12, n_buckets=700, max_bucket=8)]
     want = []
@@ -198,7 +198,7 @@ def test_resident_steps_share_one_self_resetting_counter(hc):
             want.append(step.run().copy())
         finally:
             step.free()
-    steps = [bench.ResidentStep(hc, wl, torch, None, 0, 1) for wl in wls]
+    steps = [ResidentStep(hc, wl, torch) for wl in wls]
     for rs in steps[1:]:  # all on the first one's stream
         rs.stream, rs.ext = steps[0].stream, steps[0].ext
     with torch.cuda.stream(steps[0].ext):

@@ -256,7 +256,13 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     const double rmMax = 2.0 * __longlong_as_double((long long)*t.softMaxBits);
     int head = 0, tail = 0, nc = 0, nl = 0, nu = 0;
     int myParts = 0, myFlagged = 0; /* per lane; summed over the warp at the end */
-    /* initial checklist: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757) */
+    /* initial checklist: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757).
+     * The parent's list is read where it lies (its slice of the undecided pool): FIFO entries
+     * [0, nInit) come from there, everything this node appends lives in the warp's ring `chk` --
+     * copying the slice into the ring first cost a global read-write pass per node (12% of the
+     * level kernel's stall samples sat on those stores, profiles/r02c_ncu_walk_level.json) */
+    const WalkEntry *init = chk;
+    int nInit = 0;
     if (par < 0) {
       const int side = 2 * p.nReplicas + 1, total = side * side * side;
       for (int i = lane; i < total; i += 32) {
@@ -266,11 +272,13 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       tail = total;
     } else {
       const NodeLists pl = lists[par];
-      for (int i = lane; i < pl.uLen; i += 32) chk[i] = pools.undlist[pl.uOff + i];
+      init = pools.undlist + pl.uOff;
+      nInit = pl.uLen;
       tail = pl.uLen;
     }
     if (tail > kWalkCap) { if (lane == 0) *pools.error = 1; tail = kWalkCap; }
     __syncwarp();
+    auto fifo = [&](int i) -> WalkEntry { return i < nInit ? init[i] : chk[(i - nInit) & (kWalkCap - 1)]; };
 
     /* Source records are gathered cooperatively: four lanes fetch the four 16-byte pieces of one
      * 64-byte record with ONE cp.async instruction per 8 records, into an 80-byte-pitch row of
@@ -291,7 +299,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
      * tested (entries already in the checklist), the ones this batch appends right after it */
     int buf = 0;
     WalkEntry eN = {-1, 0};
-    if (lane < tail) eN = chk[lane];
+    if (lane < tail) eN = fifo(lane);
     stage(rows, eN.node);
     while (head < tail) {
       const int i = head + lane;
@@ -310,7 +318,7 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       const bool early = iN < oldTail;
       eN.node = -1;
       if (head + batch < oldTail) { /* warp-uniform */
-        if (early) eN = chk[iN & (kWalkCap - 1)];
+        if (early) eN = fifo(iN);
         stage(rows + (buf ^ 1) * (32 * 5), eN.node);
       }
       int open = 0;
@@ -361,15 +369,15 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       if (tail - head - batch + totalKids > kWalkCap) { if (lane == 0) *pools.error = 1; break; }
       int pos = tail + __popc(k0 & below) + __popc(k1 & below);
       if (expand) {
-        if (c0 >= 0) chk[(pos++) & (kWalkCap - 1)] = {c0, e.offsetID};
-        if (c1 >= 0) chk[pos & (kWalkCap - 1)] = {c1, e.offsetID};
+        if (c0 >= 0) chk[((pos++) - nInit) & (kWalkCap - 1)] = {c0, e.offsetID};
+        if (c1 >= 0) chk[(pos - nInit) & (kWalkCap - 1)] = {c1, e.offsetID};
       }
       head += batch;
       tail += totalKids;
       __syncwarp();
       if (tail > oldTail && oldTail < head + 32) { /* warp-uniform: this batch appended entries of the next one */
         int late = -1;
-        if (!early && iN < tail) { eN = chk[iN & (kWalkCap - 1)]; late = eN.node; }
+        if (!early && iN < tail) { eN = fifo(iN); late = eN.node; }
         stage(rows + (buf ^ 1) * (32 * 5), late);
       }
       buf ^= 1;

@@ -3,5 +3,5 @@
 # parity of a variant: CB200_PC64_VARIANT=4 python -m pytest tests -m gpu -q -k "double or collapse"
 for v in "$@"; do
   echo "== variant $v"
-  CB200_PC64_VARIANT=$v timeout 300 python bench.py --double --steps 50 --warmup 5 --no-cpu-baseline --e2e-steps 3 --large-n 0 | python -c "import json,sys; j=json.loads(sys.stdin.read()); print(json.dumps({'ms':round(j['ms_per_step'],4),'pc_ms':round(j['kernels']['pc_ms'],4),'pp_ms':round(j['kernels']['pp_ms'],4),'ew_ms':round(j['kernels']['ewald_ms'],4),'frac':round(j['roofline']['frac'],4)}))"
+  CB200_PC64_VARIANT=$v timeout 300 python tools/resident_probe.py --workload cube300 --double --steps 30 | python -c "import json,sys; j=json.loads(sys.stdin.read()); print(json.dumps({k: (round(j[k],4) if isinstance(j[k],float) else j[k]) for k in ('resident_step_ms','pc_ms','pp_ms','ewald_ms','pc_frac_of_fma_peak')}))"
 done

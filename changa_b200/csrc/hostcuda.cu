@@ -1226,13 +1226,25 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   cudaChk(cudaPeekAtLastError());
   g_launches.fetch_add(1);
   t.rec = rec;
-  const int walkCtas = sms * 8; /* 64 registers: 32 resident warps per SM; the walk is latency-bound */
+  /* 4 CTAs of 4 warps per SM: what the kernel's registers (113) and its 50 KB of shared memory
+   * (the heads of the per-node lists) both allow; the walk is latency-bound */
+  const int walkCtas = sms * 4;
+  {
+    static CtaCache attrSet;
+    int dev = 0;
+    cudaChk(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (attrSet.n[dev].load(std::memory_order_acquire) == 0) {
+      cudaChk(cudaFuncSetAttribute(walk_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmemBytes));
+      attrSet.n[dev].store(1, std::memory_order_release);
+    }
+  }
   WalkEntry *scratch = (WalkEntry *)pool_alloc((size_t)walkCtas * kWalkWarps * 4 * kWalkCap * sizeof(WalkEntry), s);
   for (int lvl = 0; lvl < numLevels; ++lvl) {
     const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
     if (n <= 0) continue;
     const int need = (n + kWalkWarps - 1) / kWalkWarps;
-    walk_level_kernel<<<need < walkCtas ? need : walkCtas, kWalkWarps * 32, 0, s>>>(t, p, lo, n, lists, pools, scratch);
+    walk_level_kernel<<<need < walkCtas ? need : walkCtas, kWalkWarps * 32, kWalkSmemBytes, s>>>(t, p, lo, n, lists, pools, scratch);
     cudaChk(cudaPeekAtLastError());
     g_launches.fetch_add(1);
   }

@@ -35,6 +35,13 @@ namespace cb200 {
 
 constexpr int kWalkCap = 2048;          /* entries per node list / checklist (host walk: max ~640) */
 constexpr int kWalkWarps = 4;           /* warps per CTA */
+/* The head of every per-node list lives in shared memory; what does not fit spills to the warp's
+ * slice of the global scratch at the same index.  Sizes cover the typical node (host walk: ~110
+ * accepted cells, ~45 undecided, ~12 buckets, ~300 appended checklist entries at the leaves). */
+constexpr int kWalkRingS = 512, kWalkClS = 256, kWalkUnS = 128, kWalkLpS = 64;
+constexpr int kWalkRowBytes = 2 * 32 * 5 * 16;                                   /* two buffers of 32 records, 80-byte pitch */
+constexpr int kWalkWarpSmem = kWalkRowBytes + 8 * (kWalkRingS + kWalkClS + kWalkUnS + kWalkLpS);
+constexpr int kWalkSmemBytes = kWalkWarps * kWalkWarpSmem;
 constexpr int kWalkOffsetMask = 0x1ff << 22;
 constexpr int kWalkBucketMask = (1 << 22) - 1;
 
@@ -227,7 +234,11 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
   const int lane = threadIdx.x & 31;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int totalWarps = (gridDim.x * blockDim.x) >> 5;
-  __shared__ __align__(16) uint4 recRows[kWalkWarps * 2 * 32 * 5];
+  extern __shared__ __align__(16) unsigned char walkSmem[];
+  unsigned char *wsm = walkSmem + (size_t)(threadIdx.x >> 5) * kWalkWarpSmem;
+  uint4 *rows = reinterpret_cast<uint4 *>(wsm);
+  WalkEntry *sring = reinterpret_cast<WalkEntry *>(wsm + kWalkRowBytes);
+  WalkEntry *scl = sring + kWalkRingS, *sund = scl + kWalkClS, *slp = sund + kWalkUnS;
   WalkEntry *chk = scratch + (size_t)warpGlobal * 4 * kWalkCap;
   WalkEntry *cl = chk + kWalkCap, *lp = cl + kWalkCap, *und = lp + kWalkCap;
 
@@ -267,7 +278,9 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       const int side = 2 * p.nReplicas + 1, total = side * side * side;
       for (int i = lane; i < total; i += 32) {
         const int x = i / (side * side) - p.nReplicas, y = (i / side) % side - p.nReplicas, z = i % side - p.nReplicas;
-        if (i < kWalkCap) chk[i] = {0, (((x + 3) | ((y + 3) << 3) | ((z + 3) << 6)) << 22)};
+        const WalkEntry r0 = {0, (((x + 3) | ((y + 3) << 3) | ((z + 3) << 6)) << 22)};
+        if (i < kWalkRingS) sring[i] = r0;
+        else if (i < kWalkCap) chk[i] = r0;
       }
       tail = total;
     } else {
@@ -278,14 +291,23 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     }
     if (tail > kWalkCap) { if (lane == 0) *pools.error = 1; tail = kWalkCap; }
     __syncwarp();
-    auto fifo = [&](int i) -> WalkEntry { return i < nInit ? init[i] : chk[(i - nInit) & (kWalkCap - 1)]; };
+    /* FIFO entry i: the parent's slice, then what this node appended (shared ring, global beyond it) */
+    auto fifo = [&](int i) -> WalkEntry {
+      if (i < nInit) return init[i];
+      const int r = i - nInit;
+      return r < kWalkRingS ? sring[r] : chk[r & (kWalkCap - 1)];
+    };
+    auto fifo_put = [&](int i, WalkEntry v) {
+      const int r = i - nInit;
+      if (r < kWalkRingS) sring[r] = v;
+      else chk[r & (kWalkCap - 1)] = v;
+    };
 
     /* Source records are gathered cooperatively: four lanes fetch the four 16-byte pieces of one
      * 64-byte record with ONE cp.async instruction per 8 records, into an 80-byte-pitch row of
      * shared memory (conflict-free 128-bit reads), and every lane then reads its own row.  A
      * per-lane gather costs one L1 tag lookup per lane and load instruction (five instructions x 32
      * lines per batch: the L1 was the busiest unit, 74%); this way it is 32 lookups per batch. */
-    uint4 *rows = recRows + (size_t)(threadIdx.x >> 5) * (2 * 32 * 5);
     auto stage = [&](uint4 *dstRows, int node) {
       const int sub = lane >> 2, piece = lane & 3;
 #pragma unroll
@@ -358,7 +380,8 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
                      bU = __ballot_sync(0xffffffffu, toU);
       if (toC | toL | toU) {
         const int pos = toC ? nc + __popc(bC & below) : (toL ? nl + __popc(bL & below) : nu + __popc(bU & below));
-        WalkEntry *dst = toC ? cl : (toL ? lp : und);
+        const int capS = toC ? kWalkClS : (toL ? kWalkLpS : kWalkUnS);
+        WalkEntry *dst = pos < capS ? (toC ? scl : (toL ? slp : sund)) : (toC ? cl : (toL ? lp : und));
         if (pos < kWalkCap) dst[pos] = e;
         else *pools.error = 1;
       }
@@ -369,8 +392,8 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
       if (tail - head - batch + totalKids > kWalkCap) { if (lane == 0) *pools.error = 1; break; }
       int pos = tail + __popc(k0 & below) + __popc(k1 & below);
       if (expand) {
-        if (c0 >= 0) chk[((pos++) - nInit) & (kWalkCap - 1)] = {c0, e.offsetID};
-        if (c1 >= 0) chk[(pos - nInit) & (kWalkCap - 1)] = {c1, e.offsetID};
+        if (c0 >= 0) fifo_put(pos++, {c0, e.offsetID});
+        if (c1 >= 0) fifo_put(pos, {c1, e.offsetID});
       }
       head += batch;
       tail += totalKids;
@@ -393,9 +416,9 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     }
     oc = __shfl_sync(0xffffffffu, oc, 0); ol = __shfl_sync(0xffffffffu, ol, 0); ou = __shfl_sync(0xffffffffu, ou, 0);
     nc = __shfl_sync(0xffffffffu, nc, 0); nl = __shfl_sync(0xffffffffu, nl, 0); nu = __shfl_sync(0xffffffffu, nu, 0);
-    for (int i = lane; i < nc; i += 32) pools.clist[oc + i] = cl[i];
-    for (int i = lane; i < nl; i += 32) pools.lplist[ol + i] = lp[i];
-    for (int i = lane; i < nu; i += 32) pools.undlist[ou + i] = und[i];
+    for (int i = lane; i < nc; i += 32) pools.clist[oc + i] = i < kWalkClS ? scl[i] : cl[i];
+    for (int i = lane; i < nl; i += 32) pools.lplist[ol + i] = i < kWalkLpS ? slp[i] : lp[i];
+    for (int i = lane; i < nu; i += 32) pools.undlist[ou + i] = i < kWalkUnS ? sund[i] : und[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       myParts += __shfl_xor_sync(0xffffffffu, myParts, o);

@@ -442,15 +442,15 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   /* moments */
   nvtx_push("CUDA_SER_TREE moments");
   if (nn > st->nodeCap) {
-    for (void *p : {(void *)st->d_mom64, (void *)st->d_pkMom, (void *)st->d_mom32}) if (p) cudaChk(cudaFree(p));
+    for (void *p : {(void *)st->d_mom64, (void *)st->d_pkMom}) if (p) cudaChk(cudaFree(p));
     st->nodeCap = nn + nn / 16 + 1024;
     cudaChk(cudaMalloc((void **)&st->d_mom64, (size_t)st->nodeCap * 27 * sizeof(double)));
-    cudaChk(cudaMalloc((void **)&st->d_mom32, (size_t)st->nodeCap * 27 * sizeof(real)));
     cudaChk(cudaMalloc((void **)&st->d_pkMom, (size_t)st->nodeCap * sizeof(PackedCell)));
   }
-  cb200_build_moments(tr.d_pos, tr.d_mass, tr.d_soft, n, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last, tr.d_geolo,
-                      tr.d_geohi, tr.d_boxlo, tr.d_boxhi, tr.levelStart, tr.numLevels, nn, st->d_mom32, st->d_mom64, s);
-  repack_cells(st->d_mom32, st->d_pkMom, nn, s);
+  /* the double records (walk, Ewald set-up) and the packed rows of the force kernels straight from the
+   * build: no float AoS copy, no repack pass */
+  build_moments_impl(tr.d_pos, tr.d_mass, tr.d_soft, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last, tr.d_geolo,
+                     tr.d_geohi, tr.d_boxlo, tr.d_boxhi, tr.levelStart, tr.numLevels, nn, nullptr, st->d_mom64, st->d_pkMom, s);
   cudaChk(cudaMemsetAsync(st->d_vars, 0, (size_t)n * sizeof(VariablePartData), s));
   nvtx_pop();
   cudaChk(cudaEventRecord(st->ev[PH_MOMENTS + 1], s));

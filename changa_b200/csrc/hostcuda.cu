@@ -451,14 +451,16 @@ static void dispatch_cell_list(int maxBucket, const PackedPart *parts, VariableP
     launch_cell_list<12, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   else if (variant == 3)
     launch_cell_list<4, 3>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-  else if (variant == 4) /* 4-6: two targets per basic block (not measured yet) */
+  else if (variant == 4) /* 4-6: two targets per basic block */
     launch_cell_list<4, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   else if (variant == 5)
     launch_cell_list<6, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
   else if (variant == 6)
     launch_cell_list<8, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
-  else
+  else if (variant == 7) /* the round-1 default */
     launch_cell_list<8, 2>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
+  else /* measured (profiles/r02f_f64_pc_variants.log): 0.4225 ms on cube300 against 0.4308 for <8,2> */
+    launch_cell_list<6, 2, true>(parts, vars, cells, list, markers, starts, sizes, nBuckets, fperiod, counter, stream);
 #else
   static const bool scalar = getenv("CB200_PC_SCALAR") != nullptr; /* A/B switch: the pre-FFMA2 kernel */
   if (scalar) {
@@ -960,6 +962,35 @@ void cb200_timing_read(double out[6]) {
 long long cb200_kernel_launches(void) { return g_launches.load(); }
 
 /* ---- device moment build ---- */
+static void build_moments_impl(const double *d_pos_xyz, const double *d_mass, const double *d_soft, const int *d_child0,
+                               const int *d_child1, const int *d_firstPart, const int *d_lastPart,
+                               const double *d_geolo_xyz, const double *d_geohi_xyz, const double *d_boxlo_xyz,
+                               const double *d_boxhi_xyz, const int *h_levelStart, int numLevels, int numNodes,
+                               real *d_moments_out, double *d_moments_f64_out, PackedCell *d_packed_out, cudaStream_t s) {
+  if (numNodes <= 0) return;
+  MomentNode *work = (MomentNode *)pool_alloc((size_t)numNodes * sizeof(MomentNode), s);
+  /* CB200_MOM_VARIANT: resident CTAs (of 64 threads) per SM the kernel is compiled for -- default 8
+   * (128 registers, some spills: 0.886 ms at 4 M particles), 4: no bound (192 registers, no spills:
+   * 1.043 ms), 3: 5 (168: 0.915), 2: 10 (96: 1.039) -- the FP64 chains want warps more than registers */
+  static const int variant = getenv("CB200_MOM_VARIANT") ? atoi(getenv("CB200_MOM_VARIANT")) : 0;
+  for (int lvl = numLevels - 1; lvl >= 0; --lvl) { /* bottom-up: children are on deeper levels */
+    const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
+    if (n <= 0) continue;
+#define CB200_MOM_LAUNCH(MINB)                                                                                     \
+  build_moments_level_kernel<MINB><<<(n + kMomThreads - 1) / kMomThreads, kMomThreads, 0, s>>>(                     \
+      d_pos_xyz, d_mass, d_soft, d_child0, d_child1, d_firstPart, d_lastPart, d_geolo_xyz, d_geohi_xyz, d_boxlo_xyz, \
+      d_boxhi_xyz, lo, n, numNodes, work, d_moments_out, d_moments_f64_out, d_packed_out)
+    if (variant == 4) CB200_MOM_LAUNCH(1);
+    else if (variant == 2) CB200_MOM_LAUNCH(10);
+    else if (variant == 3) CB200_MOM_LAUNCH(5);
+    else CB200_MOM_LAUNCH(8);
+#undef CB200_MOM_LAUNCH
+    cudaChk(cudaPeekAtLastError());
+    g_launches.fetch_add(1);
+  }
+  pool_free(work, s);
+}
+
 void cb200_build_moments(const double *d_pos_xyz, const double *d_mass, const double *d_soft,
                          int numParticles, const int *d_child0, const int *d_child1,
                          const int *d_firstPart, const int *d_lastPart, const double *d_geolo_xyz,
@@ -967,19 +998,9 @@ void cb200_build_moments(const double *d_pos_xyz, const double *d_mass, const do
                          const int *h_levelStart, int numLevels, int numNodes, void *d_moments_out,
                          double *d_moments_f64_out, void *stream) {
   (void)numParticles;
-  if (numNodes <= 0) return;
-  cudaStream_t s = (cudaStream_t)stream;
-  MomentNode *work = (MomentNode *)pool_alloc((size_t)numNodes * sizeof(MomentNode), s);
-  for (int lvl = numLevels - 1; lvl >= 0; --lvl) { /* bottom-up: children are on deeper levels */
-    const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
-    if (n <= 0) continue;
-    build_moments_level_kernel<<<(n + 63) / 64, 64, 0, s>>>(
-        d_pos_xyz, d_mass, d_soft, d_child0, d_child1, d_firstPart, d_lastPart, d_geolo_xyz, d_geohi_xyz,
-        d_boxlo_xyz, d_boxhi_xyz, lo, n, numNodes, work, (real *)d_moments_out, d_moments_f64_out);
-    cudaChk(cudaPeekAtLastError());
-    g_launches.fetch_add(1);
-  }
-  pool_free(work, s);
+  build_moments_impl(d_pos_xyz, d_mass, d_soft, d_child0, d_child1, d_firstPart, d_lastPart, d_geolo_xyz, d_geohi_xyz,
+                     d_boxlo_xyz, d_boxhi_xyz, h_levelStart, numLevels, numNodes, (real *)d_moments_out, d_moments_f64_out,
+                     nullptr, (cudaStream_t)stream);
 }
 
 /* ---- tree topology on the device ---- */

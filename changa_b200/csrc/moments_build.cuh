@@ -253,52 +253,104 @@ __host__ __device__ inline void node_export(const MomentNode &n, T *o) {
 }
 
 #ifdef __CUDACC__
+/* CudaMultipoleMoments record (27 reals) -> the 32 slots of a PackedCell: what repack_cells_kernel
+ * (gravity_kernels.cuh) does at upload time, on the values already rounded to `real` */
+__device__ __forceinline__ void pack_cell_slots(const real *m, real *v) {
+  const real xx = 3 * m[6], xy = 3 * m[7], xz = 3 * m[8], yy = 3 * m[9], yz = 3 * m[10];
+  const real xxx = 15 * m[11], xyy = 15 * m[12], xxy = 15 * m[13], yyy = 15 * m[14], xxz = 15 * m[15],
+             yyz = 15 * m[16], xyz = 15 * m[17];
+  const real xxxx = 105 * m[18], xyyy = 105 * m[19], xxxy = 105 * m[20], yyyy = 105 * m[21],
+             xxxz = 105 * m[22], yyyz = 105 * m[23], xxyy = 105 * m[24], xxyz = 105 * m[25], xyyz = 105 * m[26];
+  v[PK_CX] = m[3]; v[PK_CY] = m[4]; v[PK_CZ] = m[5]; v[PK_RADIUS] = m[0];
+  v[PK_MASS] = m[2]; v[PK_XX] = xx; v[PK_XY] = xy; v[PK_XZ] = xz;
+  v[PK_YY] = yy; v[PK_YZ] = yz; v[PK_ZZ] = -(xx + yy); v[PK_XXX] = xxx;
+  v[PK_XYY] = xyy; v[PK_XXY] = xxy; v[PK_YYY] = yyy; v[PK_XXZ] = xxz;
+  v[PK_YYZ] = yyz; v[PK_XYZ] = xyz; v[PK_XZZ] = -(xxx + xyy); v[PK_YZZ] = -(xxy + yyy);
+  v[PK_XXXX] = xxxx; v[PK_XYYY] = xyyy; v[PK_XXXY] = xxxy; v[PK_YYYY] = yyyy;
+  v[PK_XXXZ] = xxxz; v[PK_YYYZ] = yyyz; v[PK_XXYY] = xxyy; v[PK_XXYZ] = xxyz;
+  v[PK_XYYZ] = xyyz; v[PK_XY3S] = xyyy + xxxy; v[PK_SOFT] = m[1]; v[PK_PAD] = 0;
+}
+
 /* one tree level: nodes [lo, lo+n).  Children live on deeper levels and are
- * already in `work`.  Writes the cudatype record (what the force kernels'
- * upload path consumes) and, when asked, a double copy for checking. */
-__global__ void build_moments_level_kernel(const double *__restrict__ pos, const double *__restrict__ mass,
-                                           const double *__restrict__ soft, const int *__restrict__ child0,
-                                           const int *__restrict__ child1, const int *__restrict__ firstPart,
-                                           const int *__restrict__ lastPart, const double *__restrict__ geolo,
-                                           const double *__restrict__ geohi, const double *__restrict__ boxlo,
-                                           const double *__restrict__ boxhi, int lo, int n, int numNodes,
-                                           MomentNode *__restrict__ work, real *__restrict__ out,
-                                           double *__restrict__ out64) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const int i = lo + t;
+ * already in `work`.  Outputs (each optional): `out` CudaMultipoleMoments records in `real`
+ * (what the upload path of the force kernels consumes), `out64` the same 27 values in double
+ * (the walk, the Ewald set-up), `packed` the PackedCell rows of the force kernels directly.
+ *
+ * The records of a block's 64 nodes are consecutive in every output array, so they are laid out
+ * in shared memory and written by the whole block with consecutive stores: a thread writing its
+ * own 27-value record is 27 stores of 32 different sectors each -- the first version spent most of
+ * its time in those (10 GB of L2 write transactions for 1.3 GB of records at 256^3). */
+constexpr int kMomThreads = 64;
+template <int MINB>
+__global__ void __launch_bounds__(kMomThreads, MINB)
+build_moments_level_kernel(const double *__restrict__ pos, const double *__restrict__ mass,
+                           const double *__restrict__ soft, const int *__restrict__ child0,
+                           const int *__restrict__ child1, const int *__restrict__ firstPart,
+                           const int *__restrict__ lastPart, const double *__restrict__ geolo,
+                           const double *__restrict__ geohi, const double *__restrict__ boxlo,
+                           const double *__restrict__ boxhi, int lo, int n, int numNodes,
+                           MomentNode *__restrict__ work, real *__restrict__ out,
+                           double *__restrict__ out64, PackedCell *__restrict__ packed) {
+  __shared__ __align__(16) double stage[kMomThreads * 32]; /* 27 doubles per record; 32 reals per packed row */
+  const int base = blockIdx.x * kMomThreads;
+  const int t = base + threadIdx.x;
+  const int valid = min(kMomThreads, n - base);
   /* the per-node work records are kept component-major (work[k * numNodes + node]): neighbouring
    * threads own neighbouring nodes and their children are neighbours one level down, so every
    * load and store of a component is a run of consecutive doubles instead of a 224-byte stride */
   double *w = reinterpret_cast<double *>(work);
   constexpr int kWords = (int)(sizeof(MomentNode) / sizeof(double));
   MomentNode m;
-  const int c0 = child0[i], c1 = child1[i];
-  if (c0 < 0 && c1 < 0) {
-    node_make_bucket(m, pos, mass, soft, firstPart[i], lastPart[i], geolo + 3 * i, geohi + 3 * i);
-  } else {
-    node_clear(m);
-    MomentNode o;
-    double *po = reinterpret_cast<double *>(&o);
-    if (c0 >= 0) {
+  if (t < n) {
+    const int i = lo + t;
+    const int c0 = child0[i], c1 = child1[i];
+    if (c0 < 0 && c1 < 0) {
+      node_make_bucket(m, pos, mass, soft, firstPart[i], lastPart[i], geolo + 3 * i, geohi + 3 * i);
+    } else {
+      node_clear(m);
+      MomentNode o;
+      double *po = reinterpret_cast<double *>(&o);
+      if (c0 >= 0) {
 #pragma unroll
-      for (int k = 0; k < kWords; ++k) po[k] = w[(size_t)k * numNodes + c0];
-      node_add_node(m, o);
+        for (int k = 0; k < kWords; ++k) po[k] = w[(size_t)k * numNodes + c0];
+        node_add_node(m, o);
+      }
+      if (c1 >= 0) {
+#pragma unroll
+        for (int k = 0; k < kWords; ++k) po[k] = w[(size_t)k * numNodes + c1];
+        node_add_node(m, o);
+      }
+      node_radius_from_box(m, boxlo + 3 * i, boxhi + 3 * i);
     }
-    if (c1 >= 0) {
+    {
+      const double *pm = reinterpret_cast<const double *>(&m);
 #pragma unroll
-      for (int k = 0; k < kWords; ++k) po[k] = w[(size_t)k * numNodes + c1];
-      node_add_node(m, o);
+      for (int k = 0; k < kWords; ++k) w[(size_t)k * numNodes + i] = pm[k];
     }
-    node_radius_from_box(m, boxlo + 3 * i, boxhi + 3 * i);
+    node_export(m, stage + threadIdx.x * 27);
   }
-  {
-    const double *pm = reinterpret_cast<const double *>(&m);
+  __syncthreads();
+  const size_t first = (size_t)(lo + base);
+  if (out64)
+    for (int k = threadIdx.x; k < valid * 27; k += kMomThreads) out64[first * 27 + k] = stage[k];
+  if (out)
+    for (int k = threadIdx.x; k < valid * 27; k += kMomThreads) out[first * 27 + k] = (real)stage[k];
+  if (packed) {
+    /* rows in `real`, through the same staging area (the double records are not needed any more) */
+    real rec[27];
+    if (t < n) {
 #pragma unroll
-    for (int k = 0; k < kWords; ++k) w[(size_t)k * numNodes + i] = pm[k];
+      for (int k = 0; k < 27; ++k) rec[k] = (real)stage[threadIdx.x * 27 + k];
+    }
+    __syncthreads();
+    real *rows = reinterpret_cast<real *>(stage);
+    static_assert(kCellReals * sizeof(real) <= 32 * sizeof(double), "a packed row fits in a record's staging slot");
+    if (t < n) pack_cell_slots(rec, rows + threadIdx.x * kCellReals);
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(packed + first);
+    const uint4 *src = reinterpret_cast<const uint4 *>(rows);
+    for (int k = threadIdx.x; k < valid * kCellPieces; k += kMomThreads) dst[k] = src[k];
   }
-  if (out) node_export(m, out + (size_t)i * 27);
-  if (out64) node_export(m, out64 + (size_t)i * 27);
 }
 #endif
 

@@ -320,25 +320,37 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
         nxtA = nnA; nxtB = nnB;
       }
 
-      /* park partial sums: row (particle*5 + component), column lane */
+      /* park partial sums: row (particle*5 + component), column lane.  When the spline fix-up wrote into
+       * the scratch (rare, warp-uniform) the sums are combined with what it left there. */
       auto lds = [](unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
-      auto park = [&](unsigned a, float v, bool isMax) {
-        if (dirty) { /* warp-uniform */
-          const float prev = lds(a);
-          v = isMax ? fmaxf(prev, v) : prev + v;
-        }
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
-      };
+      auto sts = [](unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
+      if (!dirty) {
 #pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        if (j < npairs) {
-          float a0, a1, b0, b1, c0, c1, e0, e1;
-          unpk2(ax[j], a0, a1); unpk2(ay[j], b0, b1); unpk2(az[j], c0, c1); unpk2(pot[j], e0, e1);
-          const unsigned r0 = redCol + (2 * j) * 5 * kRedPitch;
-          park(r0, a0, false); park(r0 + kRedPitch, b0, false); park(r0 + 2 * kRedPitch, c0, false);
-          park(r0 + 3 * kRedPitch, e0, false); park(r0 + 4 * kRedPitch, idt[2 * j], true);
-          park(r0 + 5 * kRedPitch, a1, false); park(r0 + 6 * kRedPitch, b1, false); park(r0 + 7 * kRedPitch, c1, false);
-          park(r0 + 8 * kRedPitch, e1, false); park(r0 + 9 * kRedPitch, idt[2 * j + 1], true);
+        for (int j = 0; j < NP; ++j) {
+          if (j < npairs) {
+            float a0, a1, b0, b1, c0, c1, e0, e1;
+            unpk2(ax[j], a0, a1); unpk2(ay[j], b0, b1); unpk2(az[j], c0, c1); unpk2(pot[j], e0, e1);
+            const unsigned r0 = redCol + (2 * j) * 5 * kRedPitch;
+            sts(r0, a0); sts(r0 + kRedPitch, b0); sts(r0 + 2 * kRedPitch, c0); sts(r0 + 3 * kRedPitch, e0);
+            sts(r0 + 4 * kRedPitch, idt[2 * j]);
+            sts(r0 + 5 * kRedPitch, a1); sts(r0 + 6 * kRedPitch, b1); sts(r0 + 7 * kRedPitch, c1); sts(r0 + 8 * kRedPitch, e1);
+            sts(r0 + 9 * kRedPitch, idt[2 * j + 1]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          if (j < npairs) {
+            float v[10];
+            unpk2(ax[j], v[0], v[5]); unpk2(ay[j], v[1], v[6]); unpk2(az[j], v[2], v[7]); unpk2(pot[j], v[3], v[8]);
+            v[4] = idt[2 * j]; v[9] = idt[2 * j + 1];
+            const unsigned r0 = redCol + (2 * j) * 5 * kRedPitch;
+#pragma unroll
+            for (int q = 0; q < 10; ++q) {
+              const float prev = lds(r0 + q * kRedPitch);
+              sts(r0 + q * kRedPitch, (q % 5) == 4 ? fmaxf(prev, v[q]) : prev + v[q]);
+            }
+          }
         }
       }
       float *out = reinterpret_cast<float *>(vars + m.first + p0);

@@ -502,6 +502,38 @@ __global__ void walk_totals_kernel(const int *__restrict__ counts, int nb1, unsi
   }
 }
 
+/* 32 source buckets -> their particles, one ILCell per particle (GenericList<ILPart>::serialize,
+ * Compute.cpp:1174-1187).  Every lane holds one source bucket (first particle f, count cnt, replica
+ * code); `incl` is the inclusive scan of cnt.  The runs are laid out in shared memory and copied out
+ * with full-warp, consecutive 8-byte stores: writing each lane's run straight to global memory is 32
+ * strided stores per instruction (a quarter of every 32-byte sector), and the particle lists are 40%
+ * of all list bytes. */
+constexpr int kEmitStage = 512;
+__device__ __forceinline__ void emit_expand(ILCell *__restrict__ dst, ILCell *stage, int f, int cnt, int code, int incl,
+                                            int lane) {
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total <= kEmitStage) {
+    ILCell *mine = stage + (incl - cnt);
+    for (int j = 0; j < cnt; ++j) {
+      ILCell o;
+      o.index = f + j; o.offsetID = code;
+      mine[j] = o;
+    }
+    __syncwarp();
+    long long *d64 = reinterpret_cast<long long *>(dst);
+    const long long *s64 = reinterpret_cast<const long long *>(stage);
+    for (int o = lane; o < total; o += 32) d64[o] = s64[o];
+    __syncwarp();
+  } else {
+    ILCell *mine = dst + (incl - cnt);
+    for (int j = 0; j < cnt; ++j) {
+      ILCell o;
+      o.index = f + j; o.offsetID = code;
+      mine[j] = o;
+    }
+  }
+}
+
 /* markers are exclusive prefix sums of the counts (numBuckets + 1 entries each) */
 __global__ void __launch_bounds__(kWalkWarps * 32)
 emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, WalkPools pools,
@@ -509,6 +541,8 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
                  ILCell *__restrict__ cellOut, ILCell *__restrict__ softOut, ILCell *__restrict__ partOut) {
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ __align__(16) ILCell stageAll[kWalkWarps * kEmitStage];
+  ILCell *stage = stageAll + (threadIdx.x >> 5) * kEmitStage;
   if (b >= t.numBuckets || !walk_bucket_active(p, b)) return;
   const int bn = t.bucketNode[b];
   if (lists[bn].pathFlagged == 0) {
@@ -546,12 +580,7 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
           const int u = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += u;
         }
-        ILCell *dst = partOut + wp + (incl - cnt);
-        for (int j = 0; j < cnt; ++j) {
-          ILCell o;
-          o.index = f + j; o.offsetID = code;
-          dst[j] = o;
-        }
+        emit_expand(partOut + wp, stage, f, cnt, code, incl, lane);
         wp += __shfl_sync(0xffffffffu, incl, 31);
       }
       }
@@ -614,12 +643,7 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
       }
-      ILCell *dst = partOut + wp + (incl - cnt);
-      for (int j = 0; j < cnt; ++j) {
-        ILCell o;
-        o.index = f + j; o.offsetID = code;
-        dst[j] = o;
-      }
+      emit_expand(partOut + wp, stage, f, cnt, code, incl, lane);
       wp += __shfl_sync(0xffffffffu, incl, 31);
     }
   }

@@ -426,11 +426,19 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   nvtx_push("CUDA_SER_TREE");
   int targets[18], cuts[36];
   const bool byCost = cfg.costCuts && !multistep && (int)st->prevCost.size() == world && world > 1;
+  /* profiling aid: CB200_EMULATE_RANK="r/N" makes a single-GPU step do the work of rank r of N (its bucket
+   * range only; tree and moments whole, as on every rank), so that ncu can look at one rank's share */
+  int cutWorld = world, cutRank = rank;
+  if (world == 1 && !multistep)
+    if (const char *em = getenv("CB200_EMULATE_RANK")) {
+      int r = 0, w = 1;
+      if (sscanf(em, "%d/%d", &r, &w) == 2 && w >= 1 && w <= 17 && r >= 0 && r < w) { cutWorld = w; cutRank = r; }
+    }
   if (byCost) cost_targets(st->prevCut, st->prevCost, world, n, targets);
-  else for (int r = 0; r <= world; ++r) targets[r] = (int)((long long)r * n / world);
+  else for (int r = 0; r <= cutWorld; ++r) targets[r] = (int)((long long)r * n / cutWorld);
   TreeInput in;
   in.pos = box; in.mass = box + 3; in.soft = box + 4; in.posStride = 5; in.attrStride = 5;
-  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, targets, world + 1, cuts, s);
+  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, targets, cutWorld + 1, cuts, s);
   st->haveTree = true;
   cb200_tree &tr = st->tree;
   nvtx_pop();
@@ -456,9 +464,9 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   cudaChk(cudaEventRecord(st->ev[PH_MOMENTS + 1], s));
 
   /* my share: buckets [b0, b1) = particles [p0, p1) */
-  int b0 = cuts[2 * rank], p0 = cuts[2 * rank + 1], b1 = cuts[2 * rank + 2], p1 = cuts[2 * rank + 3];
-  if (rank == 0) { b0 = 0; p0 = 0; }
-  if (rank == world - 1) { b1 = nb; p1 = n; }
+  int b0 = cuts[2 * cutRank], p0 = cuts[2 * cutRank + 1], b1 = cuts[2 * cutRank + 2], p1 = cuts[2 * cutRank + 3];
+  if (cutRank == 0) { b0 = 0; p0 = 0; }
+  if (cutRank == cutWorld - 1) { b1 = nb; p1 = n; }
   const unsigned char *bucketActive = nullptr;
   int nAct = n;
   if (multistep) {

@@ -670,6 +670,105 @@ __device__ __forceinline__ BucketMeta load_bucket_meta(const int *__restrict__ m
   return m;
 }
 
+/* ---- the bucket pipeline of the packed list kernels -------------------------------------------
+ * A warp works on bucket k while it already holds k1 (the next one: its first list entries and targets
+ * are prefetched under k's last tile) and, on launches with many buckets per warp, while the atomic
+ * that draws k2 is in flight.  ncu of the 256^3 step (profiles/r02j_ncu_part_list_stream_256.json):
+ * 13.6 % of the p-p kernel's stall samples sat on the shuffle that broadcasts the atomic's result and
+ * on the first use of the bucket's markers -- both at the top of a bucket, with nothing to overlap. */
+__device__ __forceinline__ unsigned grab_bucket_raw(unsigned int *nextBucket, int nBuckets, int lane) {
+  unsigned int k = 0;
+  if (lane == 0) {
+    k = atomicAdd(nextBucket, 1u);
+    if (k == (unsigned int)nBuckets + gridDim.x * kListWarps - 1u) *nextBucket = 0u;
+  }
+  return k;
+}
+/* markers / start / size of a bucket, loaded through asm so that ptxas does not treat the values as
+ * warp-uniform: a uniform value is moved to the uniform register file at once (R2UR right behind the
+ * load = a full memory round trip at the top of every bucket); these stay in flight until the bucket
+ * is started, when bucket_meta_uniform broadcasts them */
+struct RawMeta { int begin, end, first, count; };
+__device__ __forceinline__ RawMeta load_bucket_meta_raw(const int *__restrict__ markers, const int *__restrict__ starts,
+                                                        const int *__restrict__ sizes, int k) {
+  RawMeta r;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r.begin) : "l"(markers + k));
+  asm volatile("ld.global.nc.s32 %0, [%1+4];" : "=r"(r.end) : "l"(markers + k));
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r.first) : "l"(starts + k));
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r.count) : "l"(sizes + k));
+  return r;
+}
+__device__ __forceinline__ BucketMeta bucket_meta_uniform(const RawMeta &r) {
+  BucketMeta m;
+  m.begin = __shfl_sync(kFull, r.begin, 0);
+  m.len = __shfl_sync(kFull, r.end, 0) - m.begin;
+  m.first = __shfl_sync(kFull, r.first, 0);
+  m.count = __shfl_sync(kFull, r.count, 0);
+  return m;
+}
+/* launches with fewer buckets per warp than this keep one bucket in reserve instead of two: what a warp
+ * holds and has not started is idle at the tail of the launch (13 k buckets over 1776 warps on cube300) */
+constexpr int kDeepPipeBuckets = 32;
+
+/* ---- per-bucket reduction of the packed list kernels ---------------------------------------------
+ * Every lane holds, per target PAIR j, the packed partial sums {ax, ay, az, pot} (two targets per
+ * register pair) and two dtGrav maxima.  Sums: the lane parks its 4 * npairs packed values as 8-byte
+ * column `lane` of a [4 * npairs][32] array (row pitch 272 B: STS.64 and LDS.128 both conflict-free),
+ * lane v then adds up row v with 16 LDS.128 and packed adds -- one pass for a bucket of up to 16
+ * particles -- and adds both halves to the bucket's VariablePartData rows with RED.ADD.F32 (no load of
+ * the old value, nothing to wait for; one warp owns a bucket, so the order of additions to an address
+ * is the launch order on the stream: bitwise reproducible).  dtGrav: a non-negative float orders like
+ * its bit pattern, so the maximum over the lanes is one REDUX.MAX.U32 per target and the store one
+ * RED.MAX.U32.  Replaces parking 5 * np scalar rows and two divergent 32-element row sums (sum rows
+ * and max rows interleaved): 290 -> ~130 instructions per bucket, 18 % of the p-p kernel's stall
+ * samples at 256^3 (profiles/r02j_ncu_part_list_stream_256.json). */
+constexpr int kRed2Pitch = 272;
+__device__ __forceinline__ void sts64(unsigned a, f32x2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ f32x2 lds64(unsigned a) { f32x2 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void red_add_f32(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_max_u32(float *p, unsigned v) { asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <int NP>
+__device__ __forceinline__ void bucket_reduce_store(const f32x2 (&ax)[NP], const f32x2 (&ay)[NP], const f32x2 (&az)[NP],
+                                                    const f32x2 (&pot)[NP], const float (&idt)[2 * NP], int np, int npairs,
+                                                    unsigned redBase, int lane, float *__restrict__ out) {
+  const unsigned col = redBase + lane * 8;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    if (j < npairs) {
+      const unsigned r0 = col + (4 * j) * kRed2Pitch;
+      sts64(r0, ax[j]); sts64(r0 + kRed2Pitch, ay[j]); sts64(r0 + 2 * kRed2Pitch, az[j]); sts64(r0 + 3 * kRed2Pitch, pot[j]);
+    }
+  }
+  /* dtGrav while the stores land */
+  unsigned myMax = 0u;
+#pragma unroll
+  for (int i = 0; i < 2 * NP; ++i) { /* unguarded: slots past np hold zeros (or an odd bucket's unused half) and are not stored */
+    const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(idt[i]));
+    if (lane == i) myMax = mx;
+  }
+  __syncwarp();
+  if (lane < 4 * npairs) {
+    const unsigned row = redBase + lane * kRed2Pitch;
+    f32x2 acc0 = 0ull, acc1 = 0ull;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      f32x2 e0, e1;
+      asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(e0), "=l"(e1) : "r"(row + i * 16));
+      acc0 = add2(acc0, e0);
+      acc1 = add2(acc1, e1);
+    }
+    float s0, s1;
+    unpk2(add2(acc0, acc1), s0, s1);
+    /* accumulate, never overwrite (HostCUDA.cu:1196-1200, 1749-1751) */
+    const int t0 = 2 * (lane >> 2), comp = lane & 3;
+    red_add_f32(out + t0 * 5 + comp, s0);
+    if (t0 + 1 < np) red_add_f32(out + (t0 + 1) * 5 + comp, s1);
+  }
+  if (lane < np) red_max_u32(out + lane * 5 + 4, myMax); /* dtGrav is a running max */
+  __syncwarp();
+}
+
 template <int PB, int MINB>
 __global__ void __launch_bounds__(kListWarps * 32, MINB)
 cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__restrict__ vars,
@@ -677,8 +776,8 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
                     const int *__restrict__ markers, const int *__restrict__ starts,
                     const int *__restrict__ sizes, int nBuckets, float fperiod,
                     unsigned int *__restrict__ nextBucket) {
-  static_assert(PB % 2 == 0 && 5 * PB <= 64, "two reduction rows per lane at most");
-  static_assert(5 * PB * kRedPitch <= 2 * kTileBytes, "reduction scratch fits in the cell tiles");
+  static_assert(PB % 2 == 0 && 2 * PB <= 32, "one packed sum row per lane (bucket_reduce_store)");
+  static_assert(4 * (PB / 2) * kRed2Pitch <= 2 * kTileBytes, "reduction scratch fits in the cell tiles");
   static_assert(kCellPieces == 8, "float build");
   constexpr int NP = PB / 2;
   typedef CellWarpSmem<PB> S;
@@ -691,13 +790,10 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
   /* lane-constant addresses */
   const unsigned rowAddr = pin_u32(tbase + lane * kCellBytes + (lane & 7) * 16);          /* my row of tile 0: piece j at ^ (j << 4) */
   const unsigned dstAddr = pin_u32(tbase + (lane & ~7) * kCellBytes + (lane & 7) * 16);   /* row 8g + i, piece q at ^ (i * 144)      */
-  const unsigned redRow = tbase + lane * kRedPitch;                                       /* reduction: my row / my column           */
-  const unsigned redCol = tbase + lane * 4;
   const unsigned tgtAddr = pin_u32(wbase + S::targets);
   const char *srcBase; /* piece q of row 0, pinned: one IMAD.WIDE per gathered row */
   asm volatile("mov.u64 %0, %1;" : "=l"(srcBase) : "l"(reinterpret_cast<const char *>(cells) + (lane & 7) * 16));
 
-  auto grab = [&]() { return grab_bucket(nextBucket, nBuckets, lane); };
   /* rows 8g .. 8g+7 of a tile are fetched by lane group g (8 lanes = 8 pieces of one row) */
   auto stage = [&](unsigned dst, int index) {
     /* lanes without an entry re-fetch the tile's first row (never read): no predicate per row,
@@ -718,28 +814,34 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
     }
   };
   /* first two list tiles and the targets of bucket b -> staging area */
-  auto prefetch_bucket = [&](const BucketMeta &b) {
+  auto prefetch_bucket = [&](const RawMeta &b) { /* per-lane values: nothing here needs them uniform */
     const ILCell *nl = list + b.begin;
-    if (lane < b.len) cp_async8_s(wbase + S::preList + lane * 8, nl + lane);
-    if (32 + lane < b.len) cp_async8_s(wbase + S::preList + 256 + lane * 8, nl + 32 + lane);
+    const int blen = b.end - b.begin;
+    if (lane < blen) cp_async8_s(wbase + S::preList + lane * 8, nl + lane);
+    if (32 + lane < blen) cp_async8_s(wbase + S::preList + 256 + lane * 8, nl + 32 + lane);
     if (lane < min(PB, b.count)) cp_async16_s(wbase + S::preTargets + lane * 16, parts + b.first + lane);
   };
   const ILCell none = {-1, 0};
 
-  int k = grab();
+  /* the bucket pipeline (see grab_bucket_raw): k in work, k1 held, k2's atomic in flight */
+  const bool deep = nBuckets >= kDeepPipeBuckets * (int)(gridDim.x * kListWarps);
+  int k = __shfl_sync(kFull, grab_bucket_raw(nextBucket, nBuckets, lane), 0);
+  int k1 = k;
+  if (k < nBuckets) k1 = __shfl_sync(kFull, grab_bucket_raw(nextBucket, nBuckets, lane), 0);
   BucketMeta m = {0, 0, 0, 0};
   if (k < nBuckets) {
-    m = load_bucket_meta(markers, starts, sizes, k);
-    prefetch_bucket(m);
+    const RawMeta r = load_bucket_meta_raw(markers, starts, sizes, k);
+    prefetch_bucket(r);
+    m = bucket_meta_uniform(r);
   }
   cp_async_commit();
 
   while (k < nBuckets) {
-    /* one bucket ahead only: reserving further ahead costs more at the tail (a warp sits on
-     * buckets it has not started) than the atomic's round trip costs here -- measured */
-    const int kn = grab();
-    BucketMeta mn = {0, 0, 0, 0};
-    if (kn < nBuckets) mn = load_bucket_meta(markers, starts, sizes, kn);
+    /* a warp draws exactly one index >= nBuckets (the self-resetting counter counts on it) */
+    unsigned k2raw = (unsigned)k1;
+    if (deep && k1 < nBuckets) k2raw = grab_bucket_raw(nextBucket, nBuckets, lane);
+    RawMeta mn = {0, 0, 0, 0};
+    if (k1 < nBuckets) mn = load_bucket_meta_raw(markers, starts, sizes, k1);
     bool prefetched = false;
 
     const ILCell *__restrict__ mylist = list + m.begin;
@@ -817,6 +919,9 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
             }
           }
 #else
+          /* (requesting the next pair's targets before this pair is evaluated -- the first FADD2 of a body
+           * waits on its own LDS, 9 % of the stall samples -- was measured: 27.61 ms against 27.19 at 256^3,
+           * the 12 extra registers cost more than the wait; profiles/r02k) */
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
             if (j < npairs) {
@@ -833,49 +938,15 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
       /* every tile has landed (wait<1> of the last iteration); only the staging-area
        * prefetch may still be in flight, and it does not touch the tiles */
 
-      /* park partial sums: row (particle*5 + component), column lane */
-      auto sts = [](unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
-      auto lds = [](unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
-#pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        if (j < npairs) {
-          float a0, a1, b0, b1, c0, c1, e0, e1;
-          unpk2(ax[j], a0, a1); unpk2(ay[j], b0, b1); unpk2(az[j], c0, c1); unpk2(pot[j], e0, e1);
-          const unsigned r0 = redCol + (2 * j) * 5 * kRedPitch;
-          sts(r0, a0); sts(r0 + kRedPitch, b0); sts(r0 + 2 * kRedPitch, c0); sts(r0 + 3 * kRedPitch, e0);
-          sts(r0 + 4 * kRedPitch, idt[2 * j]);
-          sts(r0 + 5 * kRedPitch, a1); sts(r0 + 6 * kRedPitch, b1); sts(r0 + 7 * kRedPitch, c1); sts(r0 + 8 * kRedPitch, e1);
-          sts(r0 + 9 * kRedPitch, idt[2 * j + 1]);
-        }
-      }
-      float *out = reinterpret_cast<float *>(vars + m.first + p0);
-      float old[2]; /* the accumulators' current values: loaded under the shared-memory reduction */
-#pragma unroll
-      for (int h = 0; h < 2; ++h) old[h] = (lane + 32 * h < 5 * np) ? out[lane + 32 * h] : 0.0f;
-      __syncwarp();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int v = lane + 32 * h;
-        if (v < 5 * np) {
-          const unsigned row = redRow + h * 32 * kRedPitch; /* row v: bank (v + i) % 32 for element i */
-          const bool isMax = (v % 5) == 4;
-          float acc = 0.0f;
-          if (isMax) { /* dtGrav rows */
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc = fmaxf(acc, lds(row + i * 4));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc += lds(row + i * 4);
-          }
-          /* accumulate, never overwrite (HostCUDA.cu:1196-1200); dtGrav is a running max */
-          out[v] = isMax ? fmaxf(old[h], acc) : old[h] + acc;
-        }
-      }
-      __syncwarp();
+      bucket_reduce_store<NP>(ax, ay, az, pot, idt, np, npairs, tbase, lane,
+                              reinterpret_cast<float *>(vars + m.first + p0));
     }
     if (!prefetched) prefetch_bucket(mn); /* empty list: nothing rode under a tile */
     cp_async_commit();
-    k = kn; m = mn;
+    if (!deep && k1 < nBuckets) k2raw = grab_bucket_raw(nextBucket, nBuckets, lane);
+    k = k1;
+    k1 = (int)__shfl_sync(kFull, k2raw, 0);
+    m = bucket_meta_uniform(mn);
   }
   cp_async_wait<0>();
 }

@@ -1307,9 +1307,23 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
     out->d_cell = (ILCell *)pool_alloc((size_t)(totals[0] > 0 ? totals[0] : 1) * sizeof(ILCell), s);
     out->d_soft = (ILCell *)pool_alloc((size_t)(totals[1] > 0 ? totals[1] : 1) * sizeof(ILCell), s);
     out->d_part = (ILCell *)pool_alloc((size_t)(totals[2] > 0 ? totals[2] : 1) * sizeof(ILCell), s);
-    emit_fill_kernel<<<emitGrid, kWalkWarps * 32, 0, s>>>(t, p, lists, pools, out->d_cellMarkers, out->d_softMarkers,
-                                                        out->d_partMarkers, out->d_cell, out->d_soft, out->d_part);
-    cudaChk(cudaPeekAtLastError());
+    /* the path table (walk_paths_kernel): one row of numLevels node indices per bucket of the range */
+    static const bool oldEmit = getenv("CB200_EMIT_CLIMB") != nullptr; /* A/B switch: the parent-link climb */
+    const int nRange = p.bucketHi > p.bucketLo ? p.bucketHi - p.bucketLo : 0;
+    int *path = nullptr;
+    if (!oldEmit && nRange > 0) {
+      path = (int *)pool_alloc((size_t)nRange * numLevels * sizeof(int), s);
+      walk_paths_kernel<<<(nRange + 127) / 128, 128, 0, s>>>(t, p.bucketLo, p.bucketHi, numLevels, path);
+      cudaChk(cudaPeekAtLastError());
+      g_launches.fetch_add(1);
+    }
+    if (nRange > 0) {
+      emit_fill_kernel<<<(nRange + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, s>>>(
+          t, p, lists, pools, out->d_cellMarkers, out->d_softMarkers, out->d_partMarkers, out->d_cell, out->d_soft, out->d_part,
+          path, numLevels);
+      cudaChk(cudaPeekAtLastError());
+    }
+    pool_free(path, s);
     out->d_nodeParticles = pool_alloc((size_t)numNodes * sizeof(PackedPart), s);
     nodes_as_particles_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(d_moments_f64, (PackedPart *)out->d_nodeParticles,
                                                                     numNodes);

@@ -47,8 +47,9 @@ struct PartWarpSmem {
   static constexpr int preList = ring + 2 * stageBytes;           /* first 128 list entries of the NEXT bucket */
   static constexpr int preTargets = preList + 2 * kPpChunk * 8;   /* its target rows (PackedPart) */
   static constexpr int targets = preTargets + PB * 32;            /* PB/2 TargetSoftPair */
-  static constexpr int red = targets + (PB / 2) * 48;             /* reduction scratch: 5*PB rows of 33 floats */
-  static constexpr int bytes = (red + 5 * PB * kRedPitch + 15) & ~15;
+  static constexpr int red = targets + (PB / 2) * 48;             /* reduction scratch: per target pair 4 packed sum rows, then
+                                                                     one packed dtGrav row per pair (spline fix-up only) */
+  static constexpr int bytes = (red + 5 * (PB / 2) * kRed2Pitch + 15) & ~15;
 };
 template <int PB>
 constexpr size_t part_list_stream_smem_bytes() {
@@ -109,10 +110,11 @@ __device__ __forceinline__ void pp_body(const SrcReg &s, const TargetSoftPair &p
 
 /* The halves pp_body left out, with the scalar spline (gravity.h:147-182; same near test, bit for
  * bit).  Rare, so it is kept out of the unrolled bodies: one routine, a plain loop over the bucket's
- * target pairs, adding into THIS lane's column of the bucket's reduction scratch (rows = particle*5 +
- * component, zeroed by the caller on first use), which the final reduction sums anyway. */
+ * target pairs, adding into THIS lane's 8-byte column of the bucket's reduction scratch (rows 4 * pair +
+ * component hold {half 0, half 1}; rows 4 * NP + pair the two dtGrav maxima; zeroed by the caller on
+ * first use), which the lane folds into its registers before the reduction. */
 __device__ __noinline__ void pp_near_lane(float sx, float sy, float sz, float sm, float ssoft, int npairs,
-                                          unsigned tgtAddr, unsigned redCol) {
+                                          unsigned tgtAddr, unsigned redCol, int maxRow0) {
   for (int j = 0; j < npairs; ++j) {
     const TargetSoftPair p = lds_target_soft_pair(tgtAddr + j * 48u);
     float x[2], y[2], z[2], m[2], h[2];
@@ -127,11 +129,12 @@ __device__ __noinline__ void pp_near_lane(float sx, float sy, float sz, float sm
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
         const real4 tp = {x[e], y[e], z[e], m[e]};
         pp_pair(sx, sy, sz, sm, ssoft, tp, h[e], a0, a1, a2, a3, a4);
-        const unsigned r0 = redCol + (unsigned)((2 * j + e) * 5) * kRedPitch;
+        const unsigned r0 = redCol + (unsigned)(4 * j) * kRed2Pitch + e * 4;
         float *c = reinterpret_cast<float *>(__cvta_shared_to_generic(r0));
-        constexpr int pitch = kRedPitch / 4;
+        constexpr int pitch = kRed2Pitch / 4;
         c[0] += a0; c[pitch] += a1; c[2 * pitch] += a2; c[3 * pitch] += a3;
-        c[4 * pitch] = fmaxf(c[4 * pitch], a4);
+        float *mx = reinterpret_cast<float *>(__cvta_shared_to_generic(redCol + (unsigned)(maxRow0 + j) * kRed2Pitch + e * 4));
+        *mx = fmaxf(*mx, a4);
       }
     }
   }
@@ -144,7 +147,7 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
                         const int *__restrict__ markers, const int *__restrict__ starts,
                         const int *__restrict__ sizes, int nBuckets, float fperiod,
                         unsigned int *__restrict__ nextBucket) {
-  static_assert(PB % 2 == 0 && 5 * PB <= 64, "two reduction rows per lane at most");
+  static_assert(PB % 2 == 0 && 2 * PB <= 32, "one packed sum row per lane (bucket_reduce_store)");
   constexpr int NP = PB / 2;
   typedef PartWarpSmem<PB> S;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,12 +157,11 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
   const unsigned posAddr = pin_u32(wbase + S::ring + lane * 16);            /* my first row; second at +512 */
   const unsigned softAddr = pin_u32(wbase + S::ring + kPpChunk * 16 + lane * 4);
   const unsigned tgtAddr = pin_u32(wbase + S::targets);
-  const unsigned redRow = wbase + S::red + lane * kRedPitch;
-  const unsigned redCol = wbase + S::red + lane * 4;
+  const unsigned redBase = wbase + S::red;
+  const unsigned redCol = redBase + lane * 8;
   const ILCell none = {-1, kHomeBox << 22};
   const SrcReg nowhere = {1e18f, 1e18f, 1e18f, 0.0f, 0.0f};
 
-  auto grab = [&]() { return grab_bucket(nextBucket, nBuckets, lane); };
   /* rows of my two entries of a chunk -> ring stage `st` */
   auto gather = [&](unsigned st, int ia, int ib) {
     const unsigned o = st * S::stageBytes;
@@ -174,11 +176,12 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
       cp_async4_s(softAddr + o + 128, &q->soft);
     }
   };
-  auto prefetch_bucket = [&](const BucketMeta &b) {
+  auto prefetch_bucket = [&](const RawMeta &b) { /* per-lane values: nothing here needs them uniform */
     const ILCell *nl = list + b.begin;
+    const int blen = b.end - b.begin;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (32 * i + lane < b.len) cp_async8_s(wbase + S::preList + (32 * i + lane) * 8, nl + 32 * i + lane);
+      if (32 * i + lane < blen) cp_async8_s(wbase + S::preList + (32 * i + lane) * 8, nl + 32 * i + lane);
     if (lane < min(PB, b.count)) {
       const PackedPart *q = parts + b.first + lane;
       cp_async16_s(wbase + S::preTargets + lane * 32, q);
@@ -200,18 +203,24 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
     s.z = fmaf(float(replica_z(off)), fperiod, s.z);
   };
 
-  int k = grab();
+  /* the bucket pipeline (gravity_kernels.cuh, grab_bucket_raw): k in work, k1 held, k2's atomic in flight */
+  const bool deep = nBuckets >= kDeepPipeBuckets * (int)(gridDim.x * kListWarps);
+  int k = __shfl_sync(kFull, grab_bucket_raw(nextBucket, nBuckets, lane), 0);
+  int k1 = k;
+  if (k < nBuckets) k1 = __shfl_sync(kFull, grab_bucket_raw(nextBucket, nBuckets, lane), 0);
   BucketMeta m = {0, 0, 0, 0};
   if (k < nBuckets) {
-    m = load_bucket_meta(markers, starts, sizes, k);
-    prefetch_bucket(m);
+    const RawMeta r = load_bucket_meta_raw(markers, starts, sizes, k);
+    prefetch_bucket(r);
+    m = bucket_meta_uniform(r);
   }
   cp_async_commit();
 
   while (k < nBuckets) {
-    const int kn = grab();
-    BucketMeta mn = {0, 0, 0, 0};
-    if (kn < nBuckets) mn = load_bucket_meta(markers, starts, sizes, kn);
+    unsigned k2raw = (unsigned)k1;
+    if (deep && k1 < nBuckets) k2raw = grab_bucket_raw(nextBucket, nBuckets, lane);
+    RawMeta mn = {0, 0, 0, 0};
+    if (k1 < nBuckets) mn = load_bucket_meta_raw(markers, starts, sizes, k1);
     bool prefetched = false;
 
     const ILCell *__restrict__ mylist = list + m.begin;
@@ -309,78 +318,40 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
         }
         if (__any_sync(kFull, (slowA | slowB) != 0)) { /* rare: a pair inside the softening length */
           if (!dirty) {
-            for (int r = 0; r < 10 * npairs; ++r)
-              asm volatile("st.shared.f32 [%0], %1;" ::"r"(redCol + r * kRedPitch), "f"(0.0f) : "memory");
+            for (int r = 0; r < 4 * npairs; ++r) sts64(redCol + r * kRed2Pitch, 0ull);
+            for (int r = 0; r < npairs; ++r) sts64(redCol + (4 * NP + r) * kRed2Pitch, 0ull);
             dirty = true;
           }
-          if (slowA) pp_near_lane(sa.x, sa.y, sa.z, sa.m, sa.soft, npairs, tgtAddr, redCol);
-          if (slowB) pp_near_lane(sb.x, sb.y, sb.z, sb.m, sb.soft, npairs, tgtAddr, redCol);
+          if (slowA) pp_near_lane(sa.x, sa.y, sa.z, sa.m, sa.soft, npairs, tgtAddr, redCol, 4 * NP);
+          if (slowB) pp_near_lane(sb.x, sb.y, sb.z, sb.m, sb.soft, npairs, tgtAddr, redCol, 4 * NP);
         }
         curA = nxtA; curB = nxtB;
         nxtA = nnA; nxtB = nnB;
       }
 
-      /* park partial sums: row (particle*5 + component), column lane.  When the spline fix-up wrote into
-       * the scratch (rare, warp-uniform) the sums are combined with what it left there. */
-      auto lds = [](unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
-      auto sts = [](unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
-      if (!dirty) {
+      if (dirty) { /* rare, warp-uniform: fold what the spline fix-up left in my column into my sums */
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
           if (j < npairs) {
-            float a0, a1, b0, b1, c0, c1, e0, e1;
-            unpk2(ax[j], a0, a1); unpk2(ay[j], b0, b1); unpk2(az[j], c0, c1); unpk2(pot[j], e0, e1);
-            const unsigned r0 = redCol + (2 * j) * 5 * kRedPitch;
-            sts(r0, a0); sts(r0 + kRedPitch, b0); sts(r0 + 2 * kRedPitch, c0); sts(r0 + 3 * kRedPitch, e0);
-            sts(r0 + 4 * kRedPitch, idt[2 * j]);
-            sts(r0 + 5 * kRedPitch, a1); sts(r0 + 6 * kRedPitch, b1); sts(r0 + 7 * kRedPitch, c1); sts(r0 + 8 * kRedPitch, e1);
-            sts(r0 + 9 * kRedPitch, idt[2 * j + 1]);
+            const unsigned r0 = redCol + (4 * j) * kRed2Pitch;
+            ax[j] = add2(ax[j], lds64(r0)); ay[j] = add2(ay[j], lds64(r0 + kRed2Pitch));
+            az[j] = add2(az[j], lds64(r0 + 2 * kRed2Pitch)); pot[j] = add2(pot[j], lds64(r0 + 3 * kRed2Pitch));
+            float m0, m1;
+            unpk2(lds64(redCol + (4 * NP + j) * kRed2Pitch), m0, m1);
+            idt[2 * j] = fmaxf(idt[2 * j], m0); idt[2 * j + 1] = fmaxf(idt[2 * j + 1], m1);
           }
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          if (j < npairs) {
-            float v[10];
-            unpk2(ax[j], v[0], v[5]); unpk2(ay[j], v[1], v[6]); unpk2(az[j], v[2], v[7]); unpk2(pot[j], v[3], v[8]);
-            v[4] = idt[2 * j]; v[9] = idt[2 * j + 1];
-            const unsigned r0 = redCol + (2 * j) * 5 * kRedPitch;
-#pragma unroll
-            for (int q = 0; q < 10; ++q) {
-              const float prev = lds(r0 + q * kRedPitch);
-              sts(r0 + q * kRedPitch, (q % 5) == 4 ? fmaxf(prev, v[q]) : prev + v[q]);
-            }
-          }
-        }
+        __syncwarp();
       }
-      float *out = reinterpret_cast<float *>(vars + m.first + p0);
-      float old[2]; /* the accumulators' current values: loaded under the shared-memory reduction */
-#pragma unroll
-      for (int h = 0; h < 2; ++h) old[h] = (lane + 32 * h < 5 * np) ? out[lane + 32 * h] : 0.0f;
-      __syncwarp();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int v = lane + 32 * h;
-        if (v < 5 * np) {
-          const unsigned row = redRow + h * 32 * kRedPitch; /* row v: bank (v + i) % 32 for element i */
-          const bool isMax = (v % 5) == 4;
-          float acc = 0.0f;
-          if (isMax) { /* dtGrav rows */
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc = fmaxf(acc, lds(row + i * 4));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc += lds(row + i * 4);
-          }
-          /* accumulate, never overwrite (HostCUDA.cu:1749-1751); dtGrav is a running max */
-          out[v] = isMax ? fmaxf(old[h], acc) : old[h] + acc;
-        }
-      }
-      __syncwarp();
+      bucket_reduce_store<NP>(ax, ay, az, pot, idt, np, npairs, redBase, lane,
+                              reinterpret_cast<float *>(vars + m.first + p0));
     }
     if (!prefetched) prefetch_bucket(mn); /* empty list: nothing rode under a chunk */
     cp_async_commit();
-    k = kn; m = mn;
+    if (!deep && k1 < nBuckets) k2raw = grab_bucket_raw(nextBucket, nBuckets, lane);
+    k = k1;
+    k1 = (int)__shfl_sync(kFull, k2raw, 0);
+    m = bucket_meta_uniform(mn);
   }
   cp_async_wait<0>();
 }

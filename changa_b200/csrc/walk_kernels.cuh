@@ -445,6 +445,25 @@ __device__ __forceinline__ int walk_path(const WalkTree &t, const NodeLists *lis
   return len;
 }
 
+/* path[b * stride + l] = the ancestor-or-self of bucket b's node at tree level l (-1 below the bucket).
+ * One THREAD per bucket descends from the root by bucket ranges; neighbouring threads read the same
+ * nodes, so the descent runs out of L1.  emit_fill then has every node of a bucket's path at once
+ * (lane = level) instead of climbing parent links one dependent load at a time: the climb was what
+ * bounded it (22 levels x one L2 round trip per bucket-warp, 7.2 ms at 256^3). */
+__global__ void walk_paths_kernel(WalkTree t, int bucketLo, int bucketHi, int stride, int *__restrict__ path) {
+  const int b = bucketLo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bucketHi) return;
+  int *row = path + (size_t)(b - bucketLo) * stride;
+  int v = 0, l = 0;
+  while (v >= 0 && l < stride) {
+    row[l++] = v;
+    const int c0 = t.child0[v], c1 = t.child1[v];
+    if (c0 < 0 && c1 < 0) break;
+    v = (c1 >= 0 && (c0 < 0 || b >= t.bucketFirst[c1])) ? c1 : c0;
+  }
+  for (; l < stride; ++l) row[l] = -1;
+}
+
 /* counts[b] = {cells, softened cells, expanded particle entries} of bucket b (0 outside the range) */
 __global__ void __launch_bounds__(kWalkWarps * 32)
 emit_count_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, WalkPools pools,
@@ -538,13 +557,87 @@ __device__ __forceinline__ void emit_expand(ILCell *__restrict__ dst, ILCell *st
 __global__ void __launch_bounds__(kWalkWarps * 32)
 emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, WalkPools pools,
                  const int *__restrict__ cellMark, const int *__restrict__ softMark, const int *__restrict__ partMark,
-                 ILCell *__restrict__ cellOut, ILCell *__restrict__ softOut, ILCell *__restrict__ partOut) {
+                 ILCell *__restrict__ cellOut, ILCell *__restrict__ softOut, ILCell *__restrict__ partOut,
+                 const int *__restrict__ pathTable, int pathStride) {
   const int lane = threadIdx.x & 31;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int b = p.bucketLo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   __shared__ __align__(16) ILCell stageAll[kWalkWarps * kEmitStage];
+  __shared__ long long pentAll[kWalkWarps * 64];
   ILCell *stage = stageAll + (threadIdx.x >> 5) * kEmitStage;
-  if (b >= t.numBuckets || !walk_bucket_active(p, b)) return;
+  long long *pent = pentAll + (threadIdx.x >> 5) * 64;
+  if (b >= p.bucketHi || !walk_bucket_active(p, b)) return;
   const int bn = t.bucketNode[b];
+  if (pathTable && lists[bn].pathFlagged == 0) {
+    /* The whole path at once: lane l holds the list record of the bucket's ancestor at level l (two
+     * dependent loads for the bucket instead of one per level).  Cells: every level's slice goes to the
+     * place its path total names.  Particle buckets: the levels' entries are first concatenated in a
+     * small staging array, so that the expansion per particle (Compute.cpp:1174-1187) runs on full
+     * batches of 32 source buckets instead of one ragged batch per level. */
+    const long long *__restrict__ clist64 = reinterpret_cast<const long long *>(pools.clist);
+    const long long *__restrict__ lplist64 = reinterpret_cast<const long long *>(pools.lplist);
+    long long *__restrict__ cellOut64 = reinterpret_cast<long long *>(cellOut + cellMark[b]);
+    int wp = partMark[b], held = 0;
+    auto expand_batch = [&](int n) { /* the first n (<= 32) staged source buckets -> their particles */
+      int f = 0, cnt = 0, code = 0;
+      if (lane < n) {
+        const long long e64 = pent[lane];
+        const int2 fl = __ldg(reinterpret_cast<const int2 *>(&t.rec[(int)e64].first));
+        f = fl.x;
+        cnt = fl.y - f + 1;
+        code = (int)(e64 >> 32) & kWalkOffsetMask; /* encodeOffset(0, x, y, z) */
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      emit_expand(partOut + wp, stage, f, cnt, code, incl, lane);
+      wp += __shfl_sync(0xffffffffu, incl, 31);
+    };
+    const int *row = pathTable + (size_t)(b - p.bucketLo) * pathStride;
+    for (int l0 = 0; l0 < pathStride; l0 += 32) {
+      const int v = l0 + lane < pathStride ? __ldg(row + l0 + lane) : -1;
+      int nC = 0, srcC = 0, dstC = 0, nL = 0, srcL = 0;
+      if (v >= 0) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(lists + v);
+        const uint4 a = __ldg(q), c = __ldg(q + 1), d = __ldg(q + 2);
+        /* NodeLists: {cOff, cLen, lOff, lLen | uOff, uLen, visited, pathCells | pathParts, pathFlagged, ownParts, parent} */
+        if (c.z) { nC = (int)a.y; srcC = (int)a.x; dstC = (int)c.w - nC; nL = (int)a.w; srcL = (int)a.z; }
+        (void)d;
+      }
+      unsigned mc = __ballot_sync(0xffffffffu, nC > 0);
+      while (mc) {
+        const int sl = __ffs(mc) - 1;
+        mc &= mc - 1;
+        const int n = __shfl_sync(0xffffffffu, nC, sl), src = __shfl_sync(0xffffffffu, srcC, sl),
+                  dst = __shfl_sync(0xffffffffu, dstC, sl);
+        for (int i = lane; i < n; i += 32) cellOut64[dst + i] = __ldg(clist64 + src + i); /* {node, offsetID} = {index, offsetID} */
+      }
+      unsigned ml = __ballot_sync(0xffffffffu, nL > 0);
+      while (ml) {
+        const int sl = __ffs(ml) - 1;
+        ml &= ml - 1;
+        const int n = __shfl_sync(0xffffffffu, nL, sl), src = __shfl_sync(0xffffffffu, srcL, sl);
+        for (int i0 = 0; i0 < n; i0 += 32) {
+          const int take = min(32, n - i0);
+          if (lane < take) pent[held + lane] = __ldg(lplist64 + src + i0 + lane);
+          held += take;
+          __syncwarp();
+          if (held >= 32) {
+            expand_batch(32);
+            const long long rest = lane < held - 32 ? pent[32 + lane] : 0;
+            __syncwarp();
+            if (lane < held - 32) pent[lane] = rest;
+            held -= 32;
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (held > 0) expand_batch(held);
+    return;
+  }
   if (lists[bn].pathFlagged == 0) {
     /* no cell on the path can be softened for any bucket: every level's entries go to a place the
      * path totals name, so one climb bucket -> root (a single chain of parent links) does it all,

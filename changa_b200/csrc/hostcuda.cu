@@ -1239,6 +1239,7 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   cudaChk(cudaMemsetAsync(ctl, 0, 256, s));
   pools.used = (unsigned long long *)ctl;
   pools.error = (int *)(ctl + 64);
+  pools.stats = (int *)(ctl + 192);
   NodeLists *lists = (NodeLists *)pool_alloc((size_t)numNodes * sizeof(NodeLists), s);
   WalkNodeRec *rec = (WalkNodeRec *)pool_alloc((size_t)numNodes * sizeof(WalkNodeRec), s);
   t.softMaxBits = (const unsigned long long *)(ctl + 128); /* ctl is zeroed above */
@@ -1260,12 +1261,14 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
       attrSet.n[dev].store(1, std::memory_order_release);
     }
   }
+  static const int generalOnly = getenv("CB200_WALK_GENERAL") != nullptr; /* A/B switch: every node through walk_node_general */
   WalkEntry *scratch = (WalkEntry *)pool_alloc((size_t)walkCtas * kWalkWarps * 4 * kWalkCap * sizeof(WalkEntry), s);
   for (int lvl = 0; lvl < numLevels; ++lvl) {
     const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
     if (n <= 0) continue;
     const int need = (n + kWalkWarps - 1) / kWalkWarps;
-    walk_level_kernel<<<need < walkCtas ? need : walkCtas, kWalkWarps * 32, kWalkSmemBytes, s>>>(t, p, lo, n, lists, pools, scratch);
+    walk_level_kernel<<<need < walkCtas ? need : walkCtas, kWalkWarps * 32, kWalkSmemBytes, s>>>(t, p, lo, n, lists, pools, scratch,
+                                                                                                generalOnly);
     cudaChk(cudaPeekAtLastError());
     g_launches.fetch_add(1);
   }
@@ -1299,6 +1302,10 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   unsigned long long wide[3] = {0, 0, 0};
   cudaChk(cudaMemcpyAsync(wide, ctl + 160, sizeof wide, cudaMemcpyDeviceToHost, s));
   cudaChk(cudaStreamSynchronize(s)); /* the list sizes decide the allocations below */
+#ifdef CB200_WALK_STATS
+  { int st[4]; cudaChk(cudaMemcpy(st, ctl + 192, sizeof st, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "walk stats: fast routine gave up on clist %d, buckets %d, undecided %d, ring %d of %d nodes\n", st[0], st[1], st[2], st[3], numNodes); }
+#endif
   out->nCell = (long long)wide[0]; out->nSoft = (long long)wide[1]; out->nPart = (long long)wide[2];
   out->error = totals[3];
   for (int k = 0; k < 3; ++k)

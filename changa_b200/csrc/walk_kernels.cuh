@@ -40,7 +40,7 @@ constexpr int kWalkWarps = 4;           /* warps per CTA */
  * accepted cells, ~45 undecided, ~12 buckets, ~300 appended checklist entries at the leaves). */
 constexpr int kWalkRingS = 512, kWalkClS = 256, kWalkUnS = 128, kWalkLpS = 64;
 constexpr int kWalkRowBytes = 2 * 32 * 5 * 16;                                   /* two buffers of 32 records, 80-byte pitch */
-constexpr int kWalkWarpSmem = kWalkRowBytes + 8 * (kWalkRingS + kWalkClS + kWalkUnS + kWalkLpS);
+constexpr int kWalkWarpSmem = kWalkRowBytes + 8 * (kWalkRingS + kWalkClS + kWalkUnS + 128 /* kWalkLpFast */);
 constexpr int kWalkSmemBytes = kWalkWarps * kWalkWarpSmem;
 constexpr int kWalkOffsetMask = 0x1ff << 22;
 constexpr int kWalkBucketMask = (1 << 22) - 1;
@@ -124,6 +124,7 @@ struct WalkPools {
   unsigned long long capC, capL, capU;  /* entries per pool */
   unsigned long long *used;             /* [3] bump counters */
   int *error;                           /* != 0: a capacity was exceeded */
+  int *stats;                           /* CB200_WALK_STATS builds: nodes the fast routine gave up on, by list */
 };
 
 /* Space::intersect(box, sphere) as the host walk states it (treewalk.cpp box_sphere; restated
@@ -223,18 +224,377 @@ __device__ __forceinline__ void walk_append(WalkEntry *dst, int &count, bool fla
   count += __popc(ballot);
 }
 
+/* ---- the per-node walk ---------------------------------------------------------------------------
+ * walk_level_kernel hands one local node to one warp.  The node's checklist is drained by one of two
+ * routines that leave the node's three lists in the same place (heads in shared memory, what does not
+ * fit in the warp's slice of the global scratch):
+ *   walk_node_fast<LEAF>   the common case: everything the node touches fits the shared-memory heads
+ *                          (checklist ring 512, clist 256, undecided 128, buckets 128; a head that fills up
+ *                          is moved to the scratch as a whole), so no append has to choose between two
+ *                          homes; specialised for bucket nodes (no undecided list, no contained-in-sphere
+ *                          test).  Returns false when the live checklist would outgrow the ring;
+ *   walk_node_general      the first version of this kernel's loop, kept out of line for those nodes. */
+
+/* squared distance from the point c to the box [lo, hi] -- the value walk_box_dist2 computes, bit for
+ * bit: at most one of lo - c and c - hi is positive, so max(lo - c, c - hi, 0) is the larger of the two
+ * with negative values replaced by +0, which is done on the sign bit instead of a second
+ * double-precision max (DSETP + selects + NaN bookkeeping) */
+__device__ __forceinline__ double walk_pos_part(double d) {
+  const int hi = __double2hiint(d), lo = __double2loint(d);
+  const int keep = ~(hi >> 31);
+  return __hiloint2double(hi & keep, lo & keep);
+}
+__device__ __forceinline__ double walk_box_dist2_lean(const double (&lo)[3], const double (&hi)[3], double cx, double cy, double cz) {
+  const double c[3] = {cx, cy, cz};
+  double dsq = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double a = __dsub_rn(lo[d], c[d]), b = __dsub_rn(c[d], hi[d]);
+    const double delta = walk_pos_part(a > b ? a : b);
+    dsq = __dadd_rn(dsq, __dmul_rn(delta, delta));
+  }
+  return dsq;
+}
+
+constexpr int kWalkLpFast = 128; /* bucket-list head of the fast routine (the general one uses kWalkLpS of it) */
+static_assert(kWalkLpFast >= kWalkLpS, "one shared-memory area serves both routines");
+
+template <bool LEAF>
+__device__ __forceinline__ bool walk_node_fast(const WalkTree &t, const WalkParams &p, const WalkPools &pools,
+                                               const WalkNodeRec &mine, const double (&mylo)[3], const double (&myhi)[3],
+                                               int target, int par, const NodeLists *__restrict__ lists, double rmMax,
+                                               const double *shiftTab, uint4 *rows, WalkEntry *sring, WalkEntry *scl,
+                                               WalkEntry *sund, WalkEntry *slp, WalkEntry *cl, WalkEntry *lp, WalkEntry *und,
+                                               int lane, int &nc, int &nl, int &nu, int &flC, int &flL, int &flU,
+                                               int &myParts, int &myFlagged) {
+  constexpr int kMask = kWalkRingS - 1;
+  static_assert((kWalkRingS & kMask) == 0, "ring size is a power of two");
+  int head = 0, tail = 0;
+  nc = nl = nu = 0; myParts = 0; myFlagged = 0;
+  flC = flL = flU = 0; /* entries already moved from a full head to the warp's global scratch */
+  /* initial checklist into the ring: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757) */
+  if (par < 0) {
+    const int side = 2 * p.nReplicas + 1, total = side * side * side;
+    if (total > kWalkRingS) return false;
+    for (int i = lane; i < total; i += 32) {
+      const int x = i / (side * side) - p.nReplicas, y = (i / side) % side - p.nReplicas, z = i % side - p.nReplicas;
+      sring[i] = {0, (((x + 3) | ((y + 3) << 3) | ((z + 3) << 6)) << 22)};
+    }
+    tail = total;
+  } else {
+    const NodeLists pl = lists[par];
+    if (pl.uLen > kWalkRingS) return false;
+    const long long *src = reinterpret_cast<const long long *>(pools.undlist + pl.uOff);
+    long long *dst = reinterpret_cast<long long *>(sring);
+    for (int i = lane; i < pl.uLen; i += 32) dst[i] = __ldg(src + i);
+    tail = pl.uLen;
+  }
+  __syncwarp();
+  const double rm2 = 2.0 * mine.soft;
+  const unsigned below = (1u << lane) - 1;
+  /* records of a batch: four lanes fetch the four 16-byte pieces of one 64-byte record (see walk_node_general) */
+  auto stage = [&](uint4 *dstRows, int node) {
+    const int sub = lane >> 2, piece = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int src = __shfl_sync(0xffffffffu, node, 8 * j + sub);
+      if (src >= 0) cp_async16_ca(&dstRows[(8 * j + sub) * 5 + piece], reinterpret_cast<const uint4 *>(t.rec + src) + piece);
+    }
+    cp_async_commit();
+  };
+  int buf = 0;
+  WalkEntry eN = {-1, 0};
+  if (lane < tail) eN = sring[lane];
+  stage(rows, eN.node);
+  while (head < tail) {
+    const int batch = min(32, tail - head);
+    const bool have = lane < batch;
+    WalkEntry e = eN;
+    cp_async_wait<0>();
+    __syncwarp();
+    WalkNodeRec src;
+    {
+      uint4 *d = reinterpret_cast<uint4 *>(&src);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k] = rows[buf * (32 * 5) + lane * 5 + k];
+    }
+    /* the part of the next batch that is queued already: its records are requested before this batch is tested */
+    const int nextHead = head + batch;
+    const int avail = min(32, tail - nextHead);
+    eN.node = -1;
+    if (avail > 0) { /* warp-uniform */
+      if (lane < avail) eN = sring[(nextHead + lane) & kMask];
+      stage(rows + (buf ^ 1) * (32 * 5), eN.node);
+    }
+    int open = 0;
+    bool srcBucket = false, flagged = false;
+    const int c0 = src.child0, c1 = src.child1;
+    const int npart = src.last - src.first + 1;
+    if (have) {
+      e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
+      const double cx = __dadd_rn(src.cx, shiftTab[(e.offsetID >> 22) & 7]);
+      const double cy = __dadd_rn(src.cy, shiftTab[(e.offsetID >> 25) & 7]);
+      const double cz = __dadd_rn(src.cz, shiftTab[(e.offsetID >> 28) & 7]);
+      const double dsq = walk_box_dist2_lean(mylo, myhi, cx, cy, cz);
+      srcBucket = c0 < 0 && c1 < 0;
+      /* openCriterionNode, gravity.h:652-723 */
+      if (npart <= 6) {
+        open = 1;
+      } else if (dsq <= __dmul_rn(src.ropen, src.ropen)) {
+        if (LEAF) open = 1;
+        else {
+          const double c[3] = {cx, cy, cz};
+          open = walk_box_inside_sphere(mylo, myhi, c, src.ropen) ? 1 : -1;
+        }
+      } else {
+        /* Accepted unless softening interferes (openSoftening, gravity.h:251-260, and the maybe-softened flag
+         * of the emit step).  Every sphere involved is centred on c, none is larger than 2 soft + rmMax, and the
+         * local centre of mass lies in the local box, so its distance to c is not below the box distance:
+         * when dsq clears (2 soft + rmMax)^2 by a margin far above rounding, every one of those tests fails
+         * and none is evaluated.  (Cosmological softenings are a small fraction of a bucket: the exact tests
+         * below run for a handful of entries per node.) */
+        const double rs = 2.0 * src.soft;
+        const double rflag = __dadd_rn(rs, rmMax);
+        const double rflag2 = __dmul_rn(rflag, rflag);
+        if (dsq <= rflag2 * 1.0001) {
+          const double dx = __dsub_rn(mine.cx, cx), dy = __dsub_rn(mine.cy, cy), dz = __dsub_rn(mine.cz, cz);
+          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          const double rr = __dadd_rn(rs, rm2);
+          if ((d2 <= __dmul_rn(rr, rr)) || (dsq <= __dmul_rn(rs, rs)))
+            open = dsq <= __dmul_rn(src.ropenMono, src.ropenMono) ? 1 : 0;
+          flagged = open == 0 && dsq <= rflag2;
+        }
+      }
+    }
+    /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */
+    const bool toC = have && open == 0;
+    const bool toL = have && open != 0 && srcBucket;
+    const bool expand = have && open != 0 && !srcBucket && (LEAF || open == 1);
+    const bool toU = !LEAF && have && open == -1 && !srcBucket;
+    if (toC && flagged) { e.offsetID |= kWalkMaybeSoft; ++myFlagged; }
+    if (toL) myParts += npart;
+    const unsigned bC = __ballot_sync(0xffffffffu, toC), bL = __ballot_sync(0xffffffffu, toL);
+    const unsigned bU = LEAF ? 0u : __ballot_sync(0xffffffffu, toU);
+    const unsigned k0 = __ballot_sync(0xffffffffu, expand && c0 >= 0), k1 = __ballot_sync(0xffffffffu, expand && c1 >= 0);
+    const int totalKids = __popc(k0) + __popc(k1);
+    /* the checklist has no second home here: a node whose live entries outgrow the ring goes to walk_node_general
+     * (warp-uniform; nothing has been written yet) */
+    if (tail + totalKids - nextHead > kWalkRingS) {
+#ifdef CB200_WALK_STATS
+      if (lane == 0) atomicAdd(pools.stats + 3, 1);
+#endif
+      cp_async_wait<0>();
+      __syncwarp();
+      return false;
+    }
+    /* a full head is moved to the warp's scratch as a whole (rare: 2 % of the nodes of a uniform box, a quarter
+     * of a clustered one), so an append never has to choose between two homes */
+    auto flush = [&](WalkEntry *head_, WalkEntry *home, int count, int &flushed) {
+      for (int i = lane; i < count - flushed; i += 32) home[flushed + i] = head_[i];
+      __syncwarp();
+      flushed = count;
+    };
+    if (nc + __popc(bC) > flC + kWalkClS) flush(scl, cl, nc, flC);
+    if (nl + __popc(bL) > flL + kWalkLpFast) flush(slp, lp, nl, flL);
+    if (!LEAF && nu + __popc(bU) > flU + kWalkUnS) flush(sund, und, nu, flU);
+    /* ordered appends (lane order = checklist order): one ballot per list, one store per lane */
+    if (toC) scl[nc - flC + __popc(bC & below)] = e;
+    if (toL) slp[nl - flL + __popc(bL & below)] = e;
+    if (!LEAF && toU) sund[nu - flU + __popc(bU & below)] = e;
+    nc += __popc(bC); nl += __popc(bL); nu += __popc(bU);
+    /* children in order 0, 1 behind everything already queued */
+    if (expand) {
+      int pos = tail + __popc(k0 & below) + __popc(k1 & below);
+      if (c0 >= 0) sring[pos++ & kMask] = {c0, e.offsetID};
+      if (c1 >= 0) sring[pos & kMask] = {c1, e.offsetID};
+    }
+    const int oldTail = tail;
+    tail += totalKids;
+    head = nextHead;
+    __syncwarp();
+    if (avail < 32 && tail > oldTail) { /* warp-uniform: this batch appended entries of the next one */
+      int late = -1;
+      const int i = head + lane;
+      if (lane >= max(avail, 0) && i < tail) { eN = sring[i & kMask]; late = eN.node; }
+      stage(rows + (buf ^ 1) * (32 * 5), late);
+    }
+    buf ^= 1;
+  }
+  return true;
+}
+
+/* the general routine: any list may spill from its shared-memory head into the warp's global scratch
+ * (chk, cl, lp, und: kWalkCap entries each); the checklist starts in the parent's slice of the pool */
+struct WalkNodeCounts { int nc, nl, nu, parts, flagged; };
+__device__ __noinline__ WalkNodeCounts walk_node_general(const WalkTree &t, const WalkParams &p, const WalkPools &pools,
+                                                        const WalkNodeRec mine, double lo0, double lo1, double lo2, double hi0,
+                                                        double hi1, double hi2, int target, int par,
+                                                        const NodeLists *__restrict__ lists, double rmMax, uint4 *rows,
+                                                        WalkEntry *sring, WalkEntry *scl, WalkEntry *sund, WalkEntry *slp,
+                                                        WalkEntry *chk, int lane) {
+  /* by value: a reference would pin the caller's copies (which the fast routine uses) in local memory */
+  const double mylo[3] = {lo0, lo1, lo2}, myhi[3] = {hi0, hi1, hi2};
+  WalkEntry *cl = chk + kWalkCap, *lp = cl + kWalkCap, *und = lp + kWalkCap;
+  const bool myIsBucket = mine.child0 < 0 && mine.child1 < 0;
+  int head = 0, tail = 0, nc = 0, nl = 0, nu = 0;
+  int myParts = 0, myFlagged = 0; /* per lane; summed over the warp at the end */
+  /* initial checklist: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757).
+   * The parent's list is read where it lies (its slice of the undecided pool): FIFO entries
+   * [0, nInit) come from there, everything this node appends lives in the warp's ring `chk` --
+   * copying the slice into the ring first cost a global read-write pass per node (12% of the
+   * level kernel's stall samples sat on those stores, profiles/r02c_ncu_walk_level.json) */
+  const WalkEntry *init = chk;
+  int nInit = 0;
+  if (par < 0) {
+    const int side = 2 * p.nReplicas + 1, total = side * side * side;
+    for (int i = lane; i < total; i += 32) {
+      const int x = i / (side * side) - p.nReplicas, y = (i / side) % side - p.nReplicas, z = i % side - p.nReplicas;
+      const WalkEntry r0 = {0, (((x + 3) | ((y + 3) << 3) | ((z + 3) << 6)) << 22)};
+      if (i < kWalkRingS) sring[i] = r0;
+      else if (i < kWalkCap) chk[i] = r0;
+    }
+    tail = total;
+  } else {
+    const NodeLists pl = lists[par];
+    init = pools.undlist + pl.uOff;
+    nInit = pl.uLen;
+    tail = pl.uLen;
+  }
+  if (tail > kWalkCap) { if (lane == 0) *pools.error = 1; tail = kWalkCap; }
+  __syncwarp();
+  /* FIFO entry i: the parent's slice, then what this node appended (shared ring, global beyond it) */
+  auto fifo = [&](int i) -> WalkEntry {
+    if (i < nInit) return init[i];
+    const int r = i - nInit;
+    return r < kWalkRingS ? sring[r] : chk[r & (kWalkCap - 1)];
+  };
+  auto fifo_put = [&](int i, WalkEntry v) {
+    const int r = i - nInit;
+    if (r < kWalkRingS) sring[r] = v;
+    else chk[r & (kWalkCap - 1)] = v;
+  };
+
+  /* Source records are gathered cooperatively: four lanes fetch the four 16-byte pieces of one
+   * 64-byte record with ONE cp.async instruction per 8 records, into an 80-byte-pitch row of
+   * shared memory (conflict-free 128-bit reads), and every lane then reads its own row.  A
+   * per-lane gather costs one L1 tag lookup per lane and load instruction (five instructions x 32
+   * lines per batch: the L1 was the busiest unit, 74%); this way it is 32 lookups per batch. */
+  auto stage = [&](uint4 *dstRows, int node) {
+    const int sub = lane >> 2, piece = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int src = __shfl_sync(0xffffffffu, node, 8 * j + sub);
+      if (src >= 0) cp_async16_ca(&dstRows[(8 * j + sub) * 5 + piece], reinterpret_cast<const uint4 *>(t.rec + src) + piece);
+    }
+    cp_async_commit();
+  };
+  /* two row buffers: the records of the next batch are requested before the current batch is
+   * tested (entries already in the checklist), the ones this batch appends right after it */
+  int buf = 0;
+  WalkEntry eN = {-1, 0};
+  if (lane < tail) eN = fifo(lane);
+  stage(rows, eN.node);
+  while (head < tail) {
+    const int i = head + lane;
+    const bool have = i < tail;
+    WalkEntry e = eN;
+    const int batch = min(32, tail - head);
+    cp_async_wait<0>();
+    __syncwarp();
+    WalkNodeRec src;
+    {
+      uint4 *d = reinterpret_cast<uint4 *>(&src);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k] = rows[buf * (32 * 5) + lane * 5 + k];
+    }
+    const int iN = i + batch, oldTail = tail;
+    const bool early = iN < oldTail;
+    eN.node = -1;
+    if (head + batch < oldTail) { /* warp-uniform */
+      if (early) eN = fifo(iN);
+      stage(rows + (buf ^ 1) * (32 * 5), eN.node);
+    }
+    int open = 0;
+    bool srcBucket = false;
+    int c0 = -1, c1 = -1;
+    if (have) {
+      e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
+      double c[3];
+      walk_shifted_cm(src, e.offsetID, p.period, c);
+      const double dsq = walk_box_dist2(mylo, myhi, c);
+      open = walk_open_criterion(src, c, dsq, mine, mylo, myhi, myIsBucket);
+      c0 = src.child0; c1 = src.child1;
+      srcBucket = c0 < 0 && c1 < 0;
+      if (open == 0) {
+        /* openSoftening (gravity.h:251-260) is decided per BUCKET at emit time.  Every bucket
+         * below this node has its box and centre of mass inside this node's box, so when the
+         * cell's softening sphere, grown by the largest bucket softening, misses the box no
+         * bucket can see the cell softened: emit then skips the test and the 64-byte gather */
+        const double rflag = __dadd_rn(2.0 * src.soft, rmMax);
+        if (dsq <= __dmul_rn(rflag, rflag)) {
+          e.offsetID |= kWalkMaybeSoft;
+          ++myFlagged;
+        }
+      } else if (srcBucket) {
+        myParts += src.last - src.first + 1;
+      }
+    }
+    /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */
+    const bool toC = have && open == 0;
+    const bool toL = have && open != 0 && srcBucket;
+    const bool expand = have && open != 0 && !srcBucket && (open == 1 || myIsBucket);
+    const bool toU = have && open != 0 && !srcBucket && !expand;
+    /* ordered appends (lane order = checklist order): one ballot per list, one store per lane --
+     * the three lists are consecutive kWalkCap-slices of the warp's scratch */
+    const unsigned below = (1u << lane) - 1;
+    const unsigned bC = __ballot_sync(0xffffffffu, toC), bL = __ballot_sync(0xffffffffu, toL),
+                   bU = __ballot_sync(0xffffffffu, toU);
+    if (toC | toL | toU) {
+      const int pos = toC ? nc + __popc(bC & below) : (toL ? nl + __popc(bL & below) : nu + __popc(bU & below));
+      const int capS = toC ? kWalkClS : (toL ? kWalkLpS : kWalkUnS);
+      WalkEntry *dst = pos < capS ? (toC ? scl : (toL ? slp : sund)) : (toC ? cl : (toL ? lp : und));
+      if (pos < kWalkCap) dst[pos] = e;
+      else *pools.error = 1;
+    }
+    nc += __popc(bC); nl += __popc(bL); nu += __popc(bU);
+    /* children in order 0, 1 behind everything already queued */
+    const unsigned k0 = __ballot_sync(0xffffffffu, expand && c0 >= 0), k1 = __ballot_sync(0xffffffffu, expand && c1 >= 0);
+    const int totalKids = __popc(k0) + __popc(k1);
+    if (tail - head - batch + totalKids > kWalkCap) { if (lane == 0) *pools.error = 1; break; }
+    int pos = tail + __popc(k0 & below) + __popc(k1 & below);
+    if (expand) {
+      if (c0 >= 0) fifo_put(pos++, {c0, e.offsetID});
+      if (c1 >= 0) fifo_put(pos, {c1, e.offsetID});
+    }
+    head += batch;
+    tail += totalKids;
+    __syncwarp();
+    if (tail > oldTail && oldTail < head + 32) { /* warp-uniform: this batch appended entries of the next one */
+      int late = -1;
+      if (!early && iN < tail) { eN = fifo(iN); late = eN.node; }
+      stage(rows + (buf ^ 1) * (32 * 5), late);
+    }
+    buf ^= 1;
+  }
+
+  return {nc, nl, nu, myParts, myFlagged};
+}
+
 /* One level of the local tree: nodes [lo, lo+n).  scratch: per warp 4 x kWalkCap entries
- * (checklist, clist, lplist, undlist). */
+ * (checklist, clist, lplist, undlist) for walk_node_general. */
 #ifndef CB200_WALK_MINB
-#define CB200_WALK_MINB 1
+#define CB200_WALK_MINB 4
 #endif
 __global__ void __launch_bounds__(kWalkWarps * 32, CB200_WALK_MINB)
 walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict__ lists, WalkPools pools,
-                  WalkEntry *__restrict__ scratch) {
+                  WalkEntry *__restrict__ scratch, int generalOnly) {
   const int lane = threadIdx.x & 31;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int totalWarps = (gridDim.x * blockDim.x) >> 5;
   extern __shared__ __align__(16) unsigned char walkSmem[];
+  __shared__ double shiftTab[8];
+  if (threadIdx.x < 8) shiftTab[threadIdx.x] = __dmul_rn((double)((int)threadIdx.x - 3), p.period); /* walk_shifted_cm */
+  __syncthreads();
   unsigned char *wsm = walkSmem + (size_t)(threadIdx.x >> 5) * kWalkWarpSmem;
   uint4 *rows = reinterpret_cast<uint4 *>(wsm);
   WalkEntry *sring = reinterpret_cast<WalkEntry *>(wsm + kWalkRowBytes);
@@ -265,145 +625,21 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
 #pragma unroll
     for (int d = 0; d < 3; ++d) { mylo[d] = t.boxlo[3 * (size_t)my + d]; myhi[d] = t.boxhi[3 * (size_t)my + d]; }
     const double rmMax = 2.0 * __longlong_as_double((long long)*t.softMaxBits);
-    int head = 0, tail = 0, nc = 0, nl = 0, nu = 0;
-    int myParts = 0, myFlagged = 0; /* per lane; summed over the warp at the end */
-    /* initial checklist: the parent's undecided nodes, or the root replicas (TreePiece.cpp:3748-3757).
-     * The parent's list is read where it lies (its slice of the undecided pool): FIFO entries
-     * [0, nInit) come from there, everything this node appends lives in the warp's ring `chk` --
-     * copying the slice into the ring first cost a global read-write pass per node (12% of the
-     * level kernel's stall samples sat on those stores, profiles/r02c_ncu_walk_level.json) */
-    const WalkEntry *init = chk;
-    int nInit = 0;
-    if (par < 0) {
-      const int side = 2 * p.nReplicas + 1, total = side * side * side;
-      for (int i = lane; i < total; i += 32) {
-        const int x = i / (side * side) - p.nReplicas, y = (i / side) % side - p.nReplicas, z = i % side - p.nReplicas;
-        const WalkEntry r0 = {0, (((x + 3) | ((y + 3) << 3) | ((z + 3) << 6)) << 22)};
-        if (i < kWalkRingS) sring[i] = r0;
-        else if (i < kWalkCap) chk[i] = r0;
-      }
-      tail = total;
-    } else {
-      const NodeLists pl = lists[par];
-      init = pools.undlist + pl.uOff;
-      nInit = pl.uLen;
-      tail = pl.uLen;
+    int nc = 0, nl = 0, nu = 0, myParts = 0, myFlagged = 0;
+    int flC = 0, flL = 0, flU = 0;
+    bool done = false;
+    if (!generalOnly) {
+      if (myIsBucket)
+        done = walk_node_fast<true>(t, p, pools, mine, mylo, myhi, target, par, lists, rmMax, shiftTab, rows, sring, scl, sund,
+                                    slp, cl, lp, und, lane, nc, nl, nu, flC, flL, flU, myParts, myFlagged);
+      else
+        done = walk_node_fast<false>(t, p, pools, mine, mylo, myhi, target, par, lists, rmMax, shiftTab, rows, sring, scl, sund,
+                                     slp, cl, lp, und, lane, nc, nl, nu, flC, flL, flU, myParts, myFlagged);
     }
-    if (tail > kWalkCap) { if (lane == 0) *pools.error = 1; tail = kWalkCap; }
-    __syncwarp();
-    /* FIFO entry i: the parent's slice, then what this node appended (shared ring, global beyond it) */
-    auto fifo = [&](int i) -> WalkEntry {
-      if (i < nInit) return init[i];
-      const int r = i - nInit;
-      return r < kWalkRingS ? sring[r] : chk[r & (kWalkCap - 1)];
-    };
-    auto fifo_put = [&](int i, WalkEntry v) {
-      const int r = i - nInit;
-      if (r < kWalkRingS) sring[r] = v;
-      else chk[r & (kWalkCap - 1)] = v;
-    };
-
-    /* Source records are gathered cooperatively: four lanes fetch the four 16-byte pieces of one
-     * 64-byte record with ONE cp.async instruction per 8 records, into an 80-byte-pitch row of
-     * shared memory (conflict-free 128-bit reads), and every lane then reads its own row.  A
-     * per-lane gather costs one L1 tag lookup per lane and load instruction (five instructions x 32
-     * lines per batch: the L1 was the busiest unit, 74%); this way it is 32 lookups per batch. */
-    auto stage = [&](uint4 *dstRows, int node) {
-      const int sub = lane >> 2, piece = lane & 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int src = __shfl_sync(0xffffffffu, node, 8 * j + sub);
-        if (src >= 0) cp_async16_ca(&dstRows[(8 * j + sub) * 5 + piece], reinterpret_cast<const uint4 *>(t.rec + src) + piece);
-      }
-      cp_async_commit();
-    };
-    /* two row buffers: the records of the next batch are requested before the current batch is
-     * tested (entries already in the checklist), the ones this batch appends right after it */
-    int buf = 0;
-    WalkEntry eN = {-1, 0};
-    if (lane < tail) eN = fifo(lane);
-    stage(rows, eN.node);
-    while (head < tail) {
-      const int i = head + lane;
-      const bool have = i < tail;
-      WalkEntry e = eN;
-      const int batch = min(32, tail - head);
-      cp_async_wait<0>();
-      __syncwarp();
-      WalkNodeRec src;
-      {
-        uint4 *d = reinterpret_cast<uint4 *>(&src);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) d[k] = rows[buf * (32 * 5) + lane * 5 + k];
-      }
-      const int iN = i + batch, oldTail = tail;
-      const bool early = iN < oldTail;
-      eN.node = -1;
-      if (head + batch < oldTail) { /* warp-uniform */
-        if (early) eN = fifo(iN);
-        stage(rows + (buf ^ 1) * (32 * 5), eN.node);
-      }
-      int open = 0;
-      bool srcBucket = false;
-      int c0 = -1, c1 = -1;
-      if (have) {
-        e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
-        double c[3];
-        walk_shifted_cm(src, e.offsetID, p.period, c);
-        const double dsq = walk_box_dist2(mylo, myhi, c);
-        open = walk_open_criterion(src, c, dsq, mine, mylo, myhi, myIsBucket);
-        c0 = src.child0; c1 = src.child1;
-        srcBucket = c0 < 0 && c1 < 0;
-        if (open == 0) {
-          /* openSoftening (gravity.h:251-260) is decided per BUCKET at emit time.  Every bucket
-           * below this node has its box and centre of mass inside this node's box, so when the
-           * cell's softening sphere, grown by the largest bucket softening, misses the box no
-           * bucket can see the cell softened: emit then skips the test and the 64-byte gather */
-          const double rflag = __dadd_rn(2.0 * src.soft, rmMax);
-          if (dsq <= __dmul_rn(rflag, rflag)) {
-            e.offsetID |= kWalkMaybeSoft;
-            ++myFlagged;
-          }
-        } else if (srcBucket) {
-          myParts += src.last - src.first + 1;
-        }
-      }
-      /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */
-      const bool toC = have && open == 0;
-      const bool toL = have && open != 0 && srcBucket;
-      const bool expand = have && open != 0 && !srcBucket && (open == 1 || myIsBucket);
-      const bool toU = have && open != 0 && !srcBucket && !expand;
-      /* ordered appends (lane order = checklist order): one ballot per list, one store per lane --
-       * the three lists are consecutive kWalkCap-slices of the warp's scratch */
-      const unsigned below = (1u << lane) - 1;
-      const unsigned bC = __ballot_sync(0xffffffffu, toC), bL = __ballot_sync(0xffffffffu, toL),
-                     bU = __ballot_sync(0xffffffffu, toU);
-      if (toC | toL | toU) {
-        const int pos = toC ? nc + __popc(bC & below) : (toL ? nl + __popc(bL & below) : nu + __popc(bU & below));
-        const int capS = toC ? kWalkClS : (toL ? kWalkLpS : kWalkUnS);
-        WalkEntry *dst = pos < capS ? (toC ? scl : (toL ? slp : sund)) : (toC ? cl : (toL ? lp : und));
-        if (pos < kWalkCap) dst[pos] = e;
-        else *pools.error = 1;
-      }
-      nc += __popc(bC); nl += __popc(bL); nu += __popc(bU);
-      /* children in order 0, 1 behind everything already queued */
-      const unsigned k0 = __ballot_sync(0xffffffffu, expand && c0 >= 0), k1 = __ballot_sync(0xffffffffu, expand && c1 >= 0);
-      const int totalKids = __popc(k0) + __popc(k1);
-      if (tail - head - batch + totalKids > kWalkCap) { if (lane == 0) *pools.error = 1; break; }
-      int pos = tail + __popc(k0 & below) + __popc(k1 & below);
-      if (expand) {
-        if (c0 >= 0) fifo_put(pos++, {c0, e.offsetID});
-        if (c1 >= 0) fifo_put(pos, {c1, e.offsetID});
-      }
-      head += batch;
-      tail += totalKids;
-      __syncwarp();
-      if (tail > oldTail && oldTail < head + 32) { /* warp-uniform: this batch appended entries of the next one */
-        int late = -1;
-        if (!early && iN < tail) { eN = fifo(iN); late = eN.node; }
-        stage(rows + (buf ^ 1) * (32 * 5), late);
-      }
-      buf ^= 1;
+    if (!done) {
+      const WalkNodeCounts r = walk_node_general(t, p, pools, mine, mylo[0], mylo[1], mylo[2], myhi[0], myhi[1], myhi[2], target,
+                                                 par, lists, rmMax, rows, sring, scl, sund, slp, chk, lane);
+      nc = r.nc; nl = r.nl; nu = r.nu; myParts = r.parts; myFlagged = r.flagged;
     }
 
     /* exact-size slices of the pools */
@@ -416,9 +652,15 @@ walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict
     }
     oc = __shfl_sync(0xffffffffu, oc, 0); ol = __shfl_sync(0xffffffffu, ol, 0); ou = __shfl_sync(0xffffffffu, ou, 0);
     nc = __shfl_sync(0xffffffffu, nc, 0); nl = __shfl_sync(0xffffffffu, nl, 0); nu = __shfl_sync(0xffffffffu, nu, 0);
-    for (int i = lane; i < nc; i += 32) pools.clist[oc + i] = i < kWalkClS ? scl[i] : cl[i];
-    for (int i = lane; i < nl; i += 32) pools.lplist[ol + i] = i < kWalkLpS ? slp[i] : lp[i];
-    for (int i = lane; i < nu; i += 32) pools.undlist[ou + i] = i < kWalkUnS ? sund[i] : und[i];
+    if (done) { /* fast routine: the first fl* entries were moved to the scratch, the rest is the head */
+      for (int i = lane; i < nc; i += 32) pools.clist[oc + i] = i < flC ? cl[i] : scl[i - flC];
+      for (int i = lane; i < nl; i += 32) pools.lplist[ol + i] = i < flL ? lp[i] : slp[i - flL];
+      for (int i = lane; i < nu; i += 32) pools.undlist[ou + i] = i < flU ? und[i] : sund[i - flU];
+    } else { /* general routine: the head is the first part, the scratch holds what did not fit */
+      for (int i = lane; i < nc; i += 32) pools.clist[oc + i] = i < kWalkClS ? scl[i] : cl[i];
+      for (int i = lane; i < nl; i += 32) pools.lplist[ol + i] = i < kWalkLpS ? slp[i] : lp[i];
+      for (int i = lane; i < nu; i += 32) pools.undlist[ou + i] = i < kWalkUnS ? sund[i] : und[i];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       myParts += __shfl_xor_sync(0xffffffffu, myParts, o);

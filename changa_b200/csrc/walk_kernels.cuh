@@ -770,6 +770,7 @@ __global__ void walk_totals_kernel(const int *__restrict__ counts, int nb1, unsi
  * strided stores per instruction (a quarter of every 32-byte sector), and the particle lists are 40%
  * of all list bytes. */
 constexpr int kEmitStage = 512;
+constexpr int kEmitPieces = 64; /* <= 32-entry pieces of the cell slices of one bucket's path (emit_fill) */
 __device__ __forceinline__ void emit_expand(ILCell *__restrict__ dst, ILCell *stage, int f, int cnt, int code, int incl,
                                             int lane) {
   const int total = __shfl_sync(0xffffffffu, incl, 31);
@@ -805,8 +806,10 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
   const int b = p.bucketLo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   __shared__ __align__(16) ILCell stageAll[kWalkWarps * kEmitStage];
   __shared__ long long pentAll[kWalkWarps * 64];
+  __shared__ int4 pieceAll[kWalkWarps * kEmitPieces];
   ILCell *stage = stageAll + (threadIdx.x >> 5) * kEmitStage;
   long long *pent = pentAll + (threadIdx.x >> 5) * 64;
+  int4 *piece = pieceAll + (threadIdx.x >> 5) * kEmitPieces;
   if (b >= p.bucketHi || !walk_bucket_active(p, b)) return;
   const int bn = t.bucketNode[b];
   if (pathTable && lists[bn].pathFlagged == 0) {
@@ -848,13 +851,44 @@ emit_fill_kernel(WalkTree t, WalkParams p, const NodeLists *__restrict__ lists, 
         if (c.z) { nC = (int)a.y; srcC = (int)a.x; dstC = (int)c.w - nC; nL = (int)a.w; srcL = (int)a.z; }
         (void)d;
       }
-      unsigned mc = __ballot_sync(0xffffffffu, nC > 0);
-      while (mc) {
-        const int sl = __ffs(mc) - 1;
-        mc &= mc - 1;
-        const int n = __shfl_sync(0xffffffffu, nC, sl), src = __shfl_sync(0xffffffffu, srcC, sl),
-                  dst = __shfl_sync(0xffffffffu, dstC, sl);
-        for (int i = lane; i < n; i += 32) cellOut64[dst + i] = __ldg(clist64 + src + i); /* {node, offsetID} = {index, offsetID} */
+      /* Cells: the levels' slices are cut into pieces of <= 32 entries, described in a small table, and copied
+       * four pieces at a time -- four independent loads in flight per lane.  One slice after the other (a load,
+       * then the store that waits for it, 17 times per bucket) left the kernel waiting on its own loads:
+       * long-scoreboard 61 % of the stall samples, 1050 of 1580 instructions per bucket in that loop
+       * (profiles/r02l_ncu_emit_fill_4M.json). */
+      const int myPieces = (nC + 31) >> 5;
+      int inclP = myPieces;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inclP, o);
+        if (lane >= o) inclP += u;
+      }
+      const int nPieces = __shfl_sync(0xffffffffu, inclP, 31);
+      if (nPieces <= kEmitPieces) {
+        for (int k = 0; k < myPieces; ++k)
+          piece[inclP - myPieces + k] = make_int4(srcC + 32 * k, dstC + 32 * k, min(32, nC - 32 * k), 0);
+        __syncwarp();
+        for (int j0 = 0; j0 < nPieces; j0 += 4) {
+          int4 d[4];
+          long long v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = j0 + q < nPieces ? piece[j0 + q] : make_int4(0, 0, 0, 0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = lane < d[q].z ? __ldg(clist64 + d[q].x + lane) : 0ll;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (lane < d[q].z) cellOut64[d[q].y + lane] = v[q]; /* {node, offsetID} = {index, offsetID} */
+        }
+        __syncwarp();
+      } else { /* a path with more pieces than the table holds: slice by slice */
+        unsigned mc = __ballot_sync(0xffffffffu, nC > 0);
+        while (mc) {
+          const int sl = __ffs(mc) - 1;
+          mc &= mc - 1;
+          const int n = __shfl_sync(0xffffffffu, nC, sl), src = __shfl_sync(0xffffffffu, srcC, sl),
+                    dst = __shfl_sync(0xffffffffu, dstC, sl);
+          for (int i = lane; i < n; i += 32) cellOut64[dst + i] = __ldg(clist64 + src + i);
+        }
       }
       unsigned ml = __ballot_sync(0xffffffffu, nL > 0);
       while (ml) {

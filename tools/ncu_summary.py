@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Condense one `ncu --set full` report into the numbers DESIGN.md / bench.py quote.
-  python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/rXX_ncu_<kernel>.json
+  python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/rXX_ncu_<kernel>.json [launch index in the report]
 (runs `ncu -i ... --page raw --csv` and `--page source --csv --print-source sass`)"""
 import csv, io, json, subprocess, sys
 
@@ -36,9 +36,10 @@ def to_bytes(v, unit):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(raw)))
-    h, u, v = r[0], r[1], r[2]
+    h, u, v = r[0], r[1], r[2 + which]
     res = {"report": rep, "kernel": v[h.index("Kernel Name")] if "Kernel Name" in h else None, "stalls_per_issue": {}}
     for n, un, val in zip(h, u, v):
         if n in KEYS:
@@ -55,6 +56,13 @@ def main():
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                          capture_output=True, text=True).stdout
     s = list(csv.reader(io.StringIO(src)))
+    # one section per launch (a report with several launches repeats "Kernel Name" / header rows; ncu prints each twice)
+    heads = [i for i, x in enumerate(s) if x and x[0] == "Kernel Name"]
+    if len(heads) > 1:
+        per = 2 if len(heads) >= 2 * (len(r) - 2) else 1
+        a = heads[min(per * which, len(heads) - 1)]
+        nxt = [i for i in heads if i > a]
+        s = s[a:(nxt[0] if nxt else len(s))]
     if len(s) > 2:
         hh = s[1]
         c, ie = hh.index("Warp Stall Sampling (All Samples)"), hh.index("Instructions Executed")

@@ -1282,10 +1282,14 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   out->d_partMarkers = (int *)pool_alloc(nb1 * sizeof(int), s);
   out->d_starts = (int *)pool_alloc(nb1 * sizeof(int), s);
   out->d_sizes = (int *)pool_alloc(nb1 * sizeof(int), s);
-  const int emitGrid = (numBuckets + kWalkWarps - 1) / kWalkWarps;
-  emit_count_kernel<<<emitGrid, kWalkWarps * 32, 0, s>>>(t, p, lists, pools, counts, counts + nb1, counts + 2 * nb1,
-                                                       out->d_starts, out->d_sizes);
+  int *flaggedBuckets = (int *)pool_alloc(nb1 * sizeof(int), s);
+  emit_count_kernel<<<(numBuckets + 255) / 256, 256, 0, s>>>(t, p, lists, counts, counts + nb1, counts + 2 * nb1, out->d_starts,
+                                                            out->d_sizes, flaggedBuckets, (int *)(ctl + 208));
   cudaChk(cudaPeekAtLastError());
+  emit_count_flagged_kernel<<<sms * 8, kWalkWarps * 32, 0, s>>>(t, p, lists, pools, counts, counts + nb1, flaggedBuckets,
+                                                               (const int *)(ctl + 208));
+  cudaChk(cudaPeekAtLastError());
+  g_launches.fetch_add(1);
   walk_totals_kernel<<<((int)nb1 + 255) / 256, 256, 0, s>>>(counts, (int)nb1, (unsigned long long *)(ctl + 160));
   size_t tmpBytes = 0;
   cudaChk(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts, out->d_cellMarkers, (int)nb1, s));
@@ -1337,6 +1341,7 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
     cudaChk(cudaPeekAtLastError());
     g_launches.fetch_add(3);
   }
+  pool_free(flaggedBuckets, s);
   pool_free(tmp, s); pool_free(counts, s); pool_free(scratch, s); pool_free(lists, s); pool_free(ctl, s);
   pool_free(rec, s); pool_free(scanTmp, s); pool_free(activeIdx, s); pool_free(nextActive, s);
   pool_free(pools.clist, s); pool_free(pools.lplist, s); pool_free(pools.undlist, s);

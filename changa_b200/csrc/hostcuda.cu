@@ -1263,12 +1263,24 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   }
   static const int generalOnly = getenv("CB200_WALK_GENERAL") != nullptr; /* A/B switch: every node through walk_node_general */
   WalkEntry *scratch = (WalkEntry *)pool_alloc((size_t)walkCtas * kWalkWarps * 4 * kWalkCap * sizeof(WalkEntry), s);
+  /* per level, the nodes above the range's buckets (all of them on one GPU) */
+  int2 *levelRange = (int2 *)pool_alloc(66 * sizeof(int2), s);
+  {
+    WalkLevels lv;
+    lv.n = numLevels < 65 ? numLevels : 65;
+    for (int l = 0; l <= lv.n; ++l) lv.start[l] = h_levelStart[l];
+    walk_level_ranges_kernel<<<1, 96, 0, s>>>(t, lv, p.bucketLo, p.bucketHi, levelRange);
+    cudaChk(cudaPeekAtLastError());
+    g_launches.fetch_add(1);
+  }
+  const double rangeFrac = frac * 1.25 + 1e-3 < 1.0 ? frac * 1.25 + 1e-3 : 1.0; /* grid bound only: the kernel loops */
   for (int lvl = 0; lvl < numLevels; ++lvl) {
-    const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
-    if (n <= 0) continue;
+    const int nAll = h_levelStart[lvl + 1] - h_levelStart[lvl];
+    if (nAll <= 0) continue;
+    const int n = (int)((double)nAll * rangeFrac) + 64 < nAll ? (int)((double)nAll * rangeFrac) + 64 : nAll;
     const int need = (n + kWalkWarps - 1) / kWalkWarps;
-    walk_level_kernel<<<need < walkCtas ? need : walkCtas, kWalkWarps * 32, kWalkSmemBytes, s>>>(t, p, lo, n, lists, pools, scratch,
-                                                                                                generalOnly);
+    walk_level_kernel<<<need < walkCtas ? need : walkCtas, kWalkWarps * 32, kWalkSmemBytes, s>>>(t, p, levelRange + lvl, lists, pools,
+                                                                                                scratch, generalOnly);
     cudaChk(cudaPeekAtLastError());
     g_launches.fetch_add(1);
   }
@@ -1335,13 +1347,16 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
       cudaChk(cudaPeekAtLastError());
     }
     pool_free(path, s);
-    out->d_nodeParticles = pool_alloc((size_t)numNodes * sizeof(PackedPart), s);
-    nodes_as_particles_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(d_moments_f64, (PackedPart *)out->d_nodeParticles,
-                                                                    numNodes);
-    cudaChk(cudaPeekAtLastError());
-    g_launches.fetch_add(3);
+    if (out->nSoft > 0) { /* the sources of the softened-cell list: made only when some cell is softened */
+      out->d_nodeParticles = pool_alloc((size_t)numNodes * sizeof(PackedPart), s);
+      nodes_as_particles_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(d_moments_f64, (PackedPart *)out->d_nodeParticles,
+                                                                      numNodes);
+      cudaChk(cudaPeekAtLastError());
+      g_launches.fetch_add(1);
+    }
+    g_launches.fetch_add(2);
   }
-  pool_free(flaggedBuckets, s);
+  pool_free(flaggedBuckets, s); pool_free(levelRange, s);
   pool_free(tmp, s); pool_free(counts, s); pool_free(scratch, s); pool_free(lists, s); pool_free(ctl, s);
   pool_free(rec, s); pool_free(scanTmp, s); pool_free(activeIdx, s); pool_free(nextActive, s);
   pool_free(pools.clist, s); pool_free(pools.lplist, s); pool_free(pools.undlist, s);

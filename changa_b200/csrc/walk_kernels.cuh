@@ -580,14 +580,38 @@ __device__ __noinline__ WalkNodeCounts walk_node_general(const WalkTree &t, cons
   return {nc, nl, nu, myParts, myFlagged};
 }
 
-/* One level of the local tree: nodes [lo, lo+n).  scratch: per warp 4 x kWalkCap entries
- * (checklist, clist, lplist, undlist) for walk_node_general. */
+/* The nodes of a level that have a bucket in [bucketLo, bucketHi): nodes of a level are in SFC order and their
+ * bucket ranges ascend, so it is one index range per level (two binary searches).  A rank that owns 1/8 of the
+ * buckets visits 1/8 of every deep level; walking the whole level to find them (and writing a "not visited"
+ * record for the other 7/8) was 40 % of a rank's level kernels at eight ranks (profiles/r02s). */
+struct WalkLevels { int start[66]; int n; };
+__global__ void walk_level_ranges_kernel(WalkTree t, WalkLevels lv, int bucketLo, int bucketHi, int2 *__restrict__ range) {
+  const int l = threadIdx.x;
+  if (l >= lv.n) return;
+  const int a0 = lv.start[l], b0 = lv.start[l + 1];
+  int a = a0, b = b0;
+  while (a < b) { /* first node whose buckets end behind bucketLo */
+    const int mid = a + ((b - a) >> 1);
+    if (t.bucketFirst[mid] + t.bucketCount[mid] <= bucketLo) a = mid + 1; else b = mid;
+  }
+  const int lo = a;
+  b = b0;
+  while (a < b) { /* first node whose buckets start at or behind bucketHi */
+    const int mid = a + ((b - a) >> 1);
+    if (t.bucketFirst[mid] < bucketHi) a = mid + 1; else b = mid;
+  }
+  range[l] = make_int2(lo, a - lo);
+}
+
+/* One level of the local tree: nodes [range->x, range->x + range->y) (walk_level_ranges_kernel).  scratch: per
+ * warp 4 x kWalkCap entries (checklist, clist, lplist, undlist) for walk_node_general. */
 #ifndef CB200_WALK_MINB
 #define CB200_WALK_MINB 4
 #endif
 __global__ void __launch_bounds__(kWalkWarps * 32, CB200_WALK_MINB)
-walk_level_kernel(WalkTree t, WalkParams p, int lo, int n, NodeLists *__restrict__ lists, WalkPools pools,
+walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, NodeLists *__restrict__ lists, WalkPools pools,
                   WalkEntry *__restrict__ scratch, int generalOnly) {
+  const int lo = range->x, n = range->y;
   const int lane = threadIdx.x & 31;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int totalWarps = (gridDim.x * blockDim.x) >> 5;

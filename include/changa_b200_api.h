@@ -239,7 +239,7 @@ typedef struct cb200_lists {
   ILCell *d_cell, *d_soft, *d_part; /* cells | softened cells (index = node) | particles, expanded */
   int *d_cellMarkers, *d_softMarkers, *d_partMarkers; /* numBuckets+1 each; empty lists outside the range */
   int *d_starts, *d_sizes;          /* first target particle / particle count of every bucket */
-  void *d_nodeParticles;            /* every node as a packed source particle {cm, M | soft}: sources of d_soft */
+  void *d_nodeParticles;            /* every node as a packed source particle {cm, M | soft}: sources of d_soft (NULL when nSoft == 0) */
   long long nCell, nSoft, nPart;
   int numBuckets;
   int error;

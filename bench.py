@@ -383,6 +383,7 @@ def bench_box(hc, comm, kind, n, steps, warmup, local, want_parity=True, want_cp
            "pc_pairs": float(tot[0]), "pp_pairs": float(tot[1]), "rows": float(tot[2]), "h2d": float(tot[3]), "d2h": float(tot[4]),
            "list_entries": float(tot[5] + tot[6]),
            "nodes": res.numNodes, "buckets": res.numBuckets, "levels": res.numLevels,
+           "let_block_level": int(res.letBlockLevel), "let_fallback": int(res.letFallback),
            "e2e_s_per_step": e2e_wall / steps, "e2e_event_ms_per_step": e2e_ev / steps,
            "resident_ms_per_step": res_ev / steps, "resident_wall_ms_per_step": res_wall / steps * 1e3,
            "launches_per_step": launches_per_step, "clocks": clocks,
@@ -549,7 +550,8 @@ def main():
                       "e2e_ms": t["e2e_s_per_step"] * 1e3, "e2e_interactions_per_s": pairs / t["e2e_s_per_step"],
                       "pc_pairs": t["pc_pairs"], "pp_pairs": t["pp_pairs"], "rank0_phases_ms": t["rank0_phases_ms"],
                       "rank0": t["rank0"], "max_rank": t["max_rank"], "parity": t.get("parity"),
-                      "rank0_hbm_in_use_gb": t.get("rank0_hbm_in_use_gb"), "nodes": t["nodes"], "buckets": t["buckets"]}
+                      "rank0_hbm_in_use_gb": t.get("rank0_hbm_in_use_gb"), "nodes": t["nodes"], "buckets": t["buckets"],
+                      "let_block_level": t.get("let_block_level"), "let_fallback": t.get("let_fallback")}
         except Exception as e:
             target = {"error": repr(e)}
 
@@ -568,11 +570,14 @@ def main():
             "config": {"workload": workload_name(kind, n), "particles_total": n, "theta": THETA, "expansion": "hexadecapole",
                        "bucket_size": BUCKET, "pc_pairs": box["pc_pairs"], "pp_pairs": box["pp_pairs"],
                        "nodes": box["nodes"], "buckets": box["buckets"], "tree_levels": box["levels"],
+                       "moment_build": (f"locally essential below tree level {box['let_block_level']}: a rank builds the subtrees near its "
+                                        f"own buckets, block records exchanged by one integer all-reduce (fallbacks: {box['let_fallback']})")
+                       if box.get("let_block_level", -1) >= 0 else "every rank builds every node",
                        "l2": "inputs larger than L2: 40 B x N particle records, > 10 GB of lists per step; nothing is reused between steps",
                        "launch": "cb200_step_run: eager launches on the step's stream, 3 host synchronisations per step",
                        "cpu_affinity": f"{numa} GPU-local cores per rank (NVML)" if numa else None,
                        "parallelism": (f"one process per GPU x{world}: buckets sharded by SFC range (cost-balanced), one NCCL "
-                                       f"all-gather of the 40-byte particle records per step, tree and moments replicated")
+                                       f"all-gather of the 40-byte particle records per step, tree topology replicated")
                        if world > 1 else "single GPU"},
             "force_step_ms": ms_step,
             "timing": {"value": "sum of the steps' CUDA-event times (first enqueue to last kernel) on the step's stream, max over ranks; "

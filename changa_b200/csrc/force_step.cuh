@@ -192,6 +192,12 @@ struct cb200_step {
   cb200_tree tree;
   cb200_lists lists;
   bool haveTree = false, haveLists = false;
+  /* locally essential moment build (let_kernels.cuh) */
+  bool letOff = false;
+  unsigned char *d_letFlag = nullptr;
+  LetBox *d_letCover = nullptr;
+  double *d_letScalars = nullptr; /* [0] largest particle softening, [1] (int) cover count */
+  int letLevel = -1;
   /* cost feedback: last step's particle cuts and the cost every rank measured between them */
   std::vector<double> prevCost;
   std::vector<long long> prevCut;
@@ -351,7 +357,8 @@ void cb200_step_destroy(cb200_step *st) {
   cudaChk(cudaStreamSynchronize(st->stream));
   for (void *p : {(void *)st->d_rec, (void *)st->d_all, (void *)st->d_vars, (void *)st->d_out, (void *)st->d_counts,
                   (void *)st->d_rung, (void *)st->d_rungAll, (void *)st->d_markers, (void *)st->d_hxyz, (void *)st->d_ewald,
-                  (void *)st->d_mom64, (void *)st->d_pkMom, (void *)st->d_mom32, (void *)st->d_bucketActive})
+                  (void *)st->d_mom64, (void *)st->d_pkMom, (void *)st->d_mom32, (void *)st->d_bucketActive, (void *)st->d_letFlag,
+                  (void *)st->d_letCover, (void *)st->d_letScalars})
     if (p) cudaChk(cudaFree(p));
   for (cudaEvent_t &e : st->ev) cudaEventDestroy(e);
   cudaEventDestroy(st->evFork); cudaEventDestroy(st->evJoin);
@@ -391,6 +398,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   const int n = (int)st->n, world = st->world, rank = st->rank, chunk = st->chunk;
   const bool multistep = cfg.activeRung > 0;
   memset(res, 0, sizeof *res);
+  res->letBlockLevel = -1;
   step_release_products(st);
   nvtx_push("cb200_step_run");
 
@@ -447,26 +455,94 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   if (tr.error) { res->error = 10 + tr.error; nvtx_pop(); return; }
   const int nn = tr.numNodes, nb = tr.numBuckets;
 
-  /* moments */
-  nvtx_push("CUDA_SER_TREE moments");
-  if (nn > st->nodeCap) {
-    for (void *p : {(void *)st->d_mom64, (void *)st->d_pkMom}) if (p) cudaChk(cudaFree(p));
-    st->nodeCap = nn + nn / 16 + 1024;
-    cudaChk(cudaMalloc((void **)&st->d_mom64, (size_t)st->nodeCap * 27 * sizeof(double)));
-    cudaChk(cudaMalloc((void **)&st->d_pkMom, (size_t)st->nodeCap * sizeof(PackedCell)));
-  }
-  /* the double records (walk, Ewald set-up) and the packed rows of the force kernels straight from the
-   * build: no float AoS copy, no repack pass */
-  build_moments_impl(tr.d_pos, tr.d_mass, tr.d_soft, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last, tr.d_geolo,
-                     tr.d_geohi, tr.d_boxlo, tr.d_boxhi, tr.levelStart, tr.numLevels, nn, nullptr, st->d_mom64, st->d_pkMom, s);
-  cudaChk(cudaMemsetAsync(st->d_vars, 0, (size_t)n * sizeof(VariablePartData), s));
-  nvtx_pop();
-  cudaChk(cudaEventRecord(st->ev[PH_MOMENTS + 1], s));
-
   /* my share: buckets [b0, b1) = particles [p0, p1) */
   int b0 = cuts[2 * cutRank], p0 = cuts[2 * cutRank + 1], b1 = cuts[2 * cutRank + 2], p1 = cuts[2 * cutRank + 3];
   if (cutRank == 0) { b0 = 0; p0 = 0; }
   if (cutRank == cutWorld - 1) { b1 = nb; p1 = n; }
+
+  /* moments */
+  nvtx_push("CUDA_SER_TREE moments");
+  if (nn > st->nodeCap) {
+    for (void *p : {(void *)st->d_mom64, (void *)st->d_pkMom, (void *)st->d_letFlag}) if (p) cudaChk(cudaFree(p));
+    st->nodeCap = nn + nn / 16 + 1024;
+    cudaChk(cudaMalloc((void **)&st->d_mom64, (size_t)st->nodeCap * 27 * sizeof(double)));
+    cudaChk(cudaMalloc((void **)&st->d_pkMom, (size_t)st->nodeCap * sizeof(PackedCell)));
+    st->d_letFlag = nullptr;
+  }
+  /* Locally essential build (let_kernels.cuh): below a block level only the subtrees near my buckets.  The block
+   * level is the first with blocksPerRank x world nodes (blocks much smaller than a rank's domain keep the halo
+   * thin) that still has three levels below it; the cover level the first with 64 x world nodes. */
+  static const int letEnv = getenv("CB200_LET") ? atoi(getenv("CB200_LET")) : 1;
+  static const int letBlocksPerRank = getenv("CB200_LET_BLOCKS_PER_RANK") ? atoi(getenv("CB200_LET_BLOCKS_PER_RANK")) : 32768;
+  st->letLevel = -1;
+  if (world > 1 && !multistep && letEnv && !st->letOff) {
+    int Lb = -1, Ld = -1;
+    for (int l = 0; l < tr.numLevels; ++l) {
+      const long long cnt = tr.levelStart[l + 1] - tr.levelStart[l];
+      if (Ld < 0 && cnt >= 64LL * world) Ld = l;
+      if (Lb < 0 && cnt >= (long long)letBlocksPerRank * world) Lb = l;
+    }
+    if (Lb >= 0 && Lb + 3 < tr.numLevels) {
+      if (Ld < 0 || Ld > Lb) Ld = Lb;
+      st->letLevel = Lb;
+      if (!st->d_letFlag) cudaChk(cudaMalloc((void **)&st->d_letFlag, (size_t)st->nodeCap));
+      if (!st->d_letCover) cudaChk(cudaMalloc((void **)&st->d_letCover, kLetCoverCap * sizeof(LetBox)));
+      if (!st->d_letScalars) cudaChk(cudaMalloc((void **)&st->d_letScalars, 2 * sizeof(double)));
+      cudaChk(cudaMemsetAsync(st->d_letScalars, 0, 2 * sizeof(double), s));
+      int *nCover = reinterpret_cast<int *>(st->d_letScalars + 1);
+      { /* largest particle softening */
+        size_t bytes = 0;
+        cudaChk(cub::DeviceReduce::Max(nullptr, bytes, tr.d_soft, st->d_letScalars, n, s));
+        void *tmp = pool_alloc(bytes, s);
+        cudaChk(cub::DeviceReduce::Max(tmp, bytes, tr.d_soft, st->d_letScalars, n, s));
+        pool_free(tmp, s);
+      }
+      const int coverEnd = tr.levelStart[Ld + 1];
+      let_cover_kernel<<<(coverEnd + 255) / 256, 256, 0, s>>>(tr.d_child0, tr.d_child1, tr.d_bucketFirst, tr.d_bucketCount,
+                                                             tr.d_boxlo, tr.d_boxhi, tr.levelStart[Ld], coverEnd, b0, b1,
+                                                             st->d_letCover, nCover);
+      cudaChk(cudaPeekAtLastError());
+      const int lo = tr.levelStart[Lb], cnt = tr.levelStart[Lb + 1] - lo;
+      const double geom = 2.0 / sqrt(3.0) / cfg.theta;
+      const int images = (cfg.nReplicas || cfg.ewald) ? (cfg.nReplicas > 0 ? cfg.nReplicas : 1) : 0;
+      let_block_flags_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(tr.d_bucketFirst, tr.d_bucketCount, tr.d_boxlo, tr.d_boxhi, lo, cnt, b0,
+                                                              b1, st->d_letCover, nCover, geom > 1.0 ? geom : 1.0,
+                                                              st->d_letScalars, cfg.period, images, st->d_letFlag);
+      cudaChk(cudaPeekAtLastError());
+      for (int l = Lb; l + 1 < tr.numLevels; ++l) {
+        const int llo = tr.levelStart[l], ln = tr.levelStart[l + 1] - llo;
+        if (ln <= 0) continue;
+        let_propagate_kernel<<<(ln + 255) / 256, 256, 0, s>>>(tr.d_child0, tr.d_child1, llo, ln, st->d_letFlag);
+      }
+      cudaChk(cudaPeekAtLastError());
+      g_launches.fetch_add(3 + tr.numLevels - Lb);
+    }
+  }
+  MomentLet let;
+  if (st->letLevel >= 0) {
+    let.blockLevel = st->letLevel;
+    let.flag = st->d_letFlag;
+    let.exchange = [&](double *work, size_t numNodes, int words, int lo, int cnt) {
+      const size_t total = (size_t)words * cnt;
+      unsigned long long *buf = (unsigned long long *)pool_alloc(total * sizeof(unsigned long long), s);
+      let_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(work, numNodes, words, lo, cnt, tr.d_first, p0, p1, buf);
+      cudaChk(cudaPeekAtLastError());
+      ncclChk(nccl_api()->AllReduce(buf, buf, total, ncclUint64, ncclSum, st->comm->comm, s));
+      let_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(work, numNodes, words, lo, cnt, buf);
+      cudaChk(cudaPeekAtLastError());
+      pool_free(buf, s);
+      g_launches.fetch_add(2);
+    };
+  }
+  /* the double records (walk, Ewald set-up) and the packed rows of the force kernels straight from the
+   * build: no float AoS copy, no repack pass */
+  build_moments_impl(tr.d_pos, tr.d_mass, tr.d_soft, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last, tr.d_geolo,
+                     tr.d_geohi, tr.d_boxlo, tr.d_boxhi, tr.levelStart, tr.numLevels, nn, nullptr, st->d_mom64, st->d_pkMom, s,
+                     st->letLevel >= 0 ? &let : nullptr);
+  cudaChk(cudaMemsetAsync(st->d_vars, 0, (size_t)n * sizeof(VariablePartData), s));
+  nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_MOMENTS + 1], s));
+
   const unsigned char *bucketActive = nullptr;
   int nAct = n;
   if (multistep) {
@@ -540,11 +616,45 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
 
   /* interaction lists of my buckets */
   nvtx_push("CUDA_SER_LIST");
+  WalkExtras extras;
+  if (st->letLevel >= 0) {
+    extras.built = st->d_letFlag;
+    extras.builtAlways = tr.levelStart[st->letLevel + 1]; /* every node down to the block level has a record */
+    extras.reduceSoftMax = [&](unsigned long long *d_bits, cudaStream_t ws) {
+      /* the largest node softening over the whole tree (a non-negative double orders like its bit pattern): every
+       * node is built by the rank that owns it, so the maximum over the ranks is the single-GPU value */
+      ncclChk(nccl_api()->AllReduce(d_bits, d_bits, 1, ncclUint64, ncclMax, st->comm->comm, ws));
+    };
+    tl_walkExtras = &extras;
+  }
   cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
                            tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
                            cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
+  tl_walkExtras = nullptr;
+  /* a walk that met a node outside the part this rank built (let_kernels.cuh: not expected) is repeated on the
+   * full build, and the locally essential build stays off for this step object -- on every rank, or the next
+   * step's exchange would wait for a rank that no longer takes part */
+  if (st->letLevel >= 0) {
+    double bad = st->lists.error == kWalkNotBuilt ? 1.0 : 0.0;
+    cb200_comm_allreduce_f64(st->comm, &bad, 1, 1, s);
+    if (bad > 0.0) {
+      fprintf(stderr, "changa_b200: rank %d: the walk left the locally essential tree (block level %d); full moment build from here on\n",
+              rank, st->letLevel);
+      st->letOff = true;
+      st->letLevel = -1;
+      res->letFallback = 1;
+      cb200_lists_free(&st->lists, s);
+      build_moments_impl(tr.d_pos, tr.d_mass, tr.d_soft, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last, tr.d_geolo,
+                         tr.d_geohi, tr.d_boxlo, tr.d_boxhi, tr.levelStart, tr.numLevels, nn, nullptr, st->d_mom64, st->d_pkMom, s);
+      cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
+                               tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
+                               cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
+    }
+  }
+  res->letBlockLevel = st->letLevel;
   st->haveLists = true;
   cb200_lists &li = st->lists;
+
   nvtx_pop();
   if (cfg.overlapEwald && cfg.ewald && p1 > p0) cudaChk(cudaStreamWaitEvent(s, st->evJoin, 0));
   cudaChk(cudaEventRecord(st->ev[PH_WALK + 1], s));

@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -34,10 +35,12 @@
 #include "pp_stream_kernel.cuh"
 #include "moments_build.cuh"
 #include "walk_kernels.cuh"
+#include "let_kernels.cuh"
 #include "tree_kernels.cuh"
 #include "ewald_setup.cuh"
 #include <nvtx3/nvToolsExt.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -962,24 +965,30 @@ void cb200_timing_read(double out[6]) {
 long long cb200_kernel_launches(void) { return g_launches.load(); }
 
 /* ---- device moment build ---- */
+/* the locally essential build of a multi-GPU step (let_kernels.cuh); exchange() is called once, between the
+ * build and the export of the block level, with the component-major work records */
+struct MomentLet {
+  int blockLevel;
+  const unsigned char *flag; /* per node: 1 = built by this rank (meaningful at and below the block level) */
+  std::function<void(double *work, size_t numNodes, int words, int lo, int n)> exchange;
+};
 static void build_moments_impl(const double *d_pos_xyz, const double *d_mass, const double *d_soft, const int *d_child0,
                                const int *d_child1, const int *d_firstPart, const int *d_lastPart,
                                const double *d_geolo_xyz, const double *d_geohi_xyz, const double *d_boxlo_xyz,
                                const double *d_boxhi_xyz, const int *h_levelStart, int numLevels, int numNodes,
-                               real *d_moments_out, double *d_moments_f64_out, PackedCell *d_packed_out, cudaStream_t s) {
+                               real *d_moments_out, double *d_moments_f64_out, PackedCell *d_packed_out, cudaStream_t s,
+                               const MomentLet *let = nullptr) {
   if (numNodes <= 0) return;
   MomentNode *work = (MomentNode *)pool_alloc((size_t)numNodes * sizeof(MomentNode), s);
   /* CB200_MOM_VARIANT: resident CTAs (of 64 threads) per SM the kernel is compiled for -- default 8
    * (128 registers, some spills: 0.886 ms at 4 M particles), 4: no bound (192 registers, no spills:
    * 1.043 ms), 3: 5 (168: 0.915), 2: 10 (96: 1.039) -- the FP64 chains want warps more than registers */
   static const int variant = getenv("CB200_MOM_VARIANT") ? atoi(getenv("CB200_MOM_VARIANT")) : 0;
-  for (int lvl = numLevels - 1; lvl >= 0; --lvl) { /* bottom-up: children are on deeper levels */
-    const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
-    if (n <= 0) continue;
+  auto launch = [&](int lo, int n, const unsigned char *flag, int mode) {
 #define CB200_MOM_LAUNCH(MINB)                                                                                     \
   build_moments_level_kernel<MINB><<<(n + kMomThreads - 1) / kMomThreads, kMomThreads, 0, s>>>(                     \
       d_pos_xyz, d_mass, d_soft, d_child0, d_child1, d_firstPart, d_lastPart, d_geolo_xyz, d_geohi_xyz, d_boxlo_xyz, \
-      d_boxhi_xyz, lo, n, numNodes, work, d_moments_out, d_moments_f64_out, d_packed_out)
+      d_boxhi_xyz, lo, n, numNodes, work, d_moments_out, d_moments_f64_out, d_packed_out, flag, mode)
     if (variant == 4) CB200_MOM_LAUNCH(1);
     else if (variant == 2) CB200_MOM_LAUNCH(10);
     else if (variant == 3) CB200_MOM_LAUNCH(5);
@@ -987,6 +996,19 @@ static void build_moments_impl(const double *d_pos_xyz, const double *d_mass, co
 #undef CB200_MOM_LAUNCH
     cudaChk(cudaPeekAtLastError());
     g_launches.fetch_add(1);
+  };
+  for (int lvl = numLevels - 1; lvl >= 0; --lvl) { /* bottom-up: children are on deeper levels */
+    const int lo = h_levelStart[lvl], n = h_levelStart[lvl + 1] - lo;
+    if (n <= 0) continue;
+    if (let && lvl > let->blockLevel) {
+      launch(lo, n, let->flag, 0);
+    } else if (let && lvl == let->blockLevel) {
+      launch(lo, n, let->flag, 1); /* my blocks (own and halo) */
+      let->exchange(reinterpret_cast<double *>(work), (size_t)numNodes, (int)(sizeof(MomentNode) / sizeof(double)), lo, n);
+      launch(lo, n, nullptr, 2);   /* every block of the level, from the exchanged records */
+    } else {
+      launch(lo, n, nullptr, 0);
+    }
   }
   pool_free(work, s);
 }
@@ -1179,6 +1201,14 @@ struct MinOp {
   __host__ __device__ int operator()(int a, int b) const { return a < b ? a : b; }
 };
 
+/* what a multi-GPU force step adds to the walk (force_step.cuh sets it around its call, on its own thread): the
+ * part of the tree it built and the reduction of the largest node softening over the ranks */
+struct WalkExtras {
+  const unsigned char *built = nullptr;
+  int builtAlways = 0;
+  std::function<void(unsigned long long *d_softMaxBits, cudaStream_t)> reduceSoftMax;
+};
+static thread_local const WalkExtras *tl_walkExtras = nullptr;
 void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const int *h_levelStart,
                               const int *d_child0, const int *d_child1, const int *d_parent,
                               const int *d_firstPart, const int *d_lastPart, const int *d_bucketFirst,
@@ -1243,9 +1273,13 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   NodeLists *lists = (NodeLists *)pool_alloc((size_t)numNodes * sizeof(NodeLists), s);
   WalkNodeRec *rec = (WalkNodeRec *)pool_alloc((size_t)numNodes * sizeof(WalkNodeRec), s);
   t.softMaxBits = (const unsigned long long *)(ctl + 128); /* ctl is zeroed above */
+  const WalkExtras *extras = tl_walkExtras;
   walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, p.theta, p.thetaMono, rec,
-                                                                (unsigned long long *)(ctl + 128));
+                                                                (unsigned long long *)(ctl + 128),
+                                                                extras ? extras->built : nullptr,
+                                                                extras ? extras->builtAlways : 0);
   cudaChk(cudaPeekAtLastError());
+  if (extras && extras->reduceSoftMax) extras->reduceSoftMax((unsigned long long *)(ctl + 128), s);
   g_launches.fetch_add(1);
   t.rec = rec;
   /* 4 CTAs of 4 warps per SM: what the kernel's registers (113) and its 50 KB of shared memory

@@ -290,18 +290,29 @@ build_moments_level_kernel(const double *__restrict__ pos, const double *__restr
                            const double *__restrict__ geohi, const double *__restrict__ boxlo,
                            const double *__restrict__ boxhi, int lo, int n, int numNodes,
                            MomentNode *__restrict__ work, real *__restrict__ out,
-                           double *__restrict__ out64, PackedCell *__restrict__ packed) {
+                           double *__restrict__ out64, PackedCell *__restrict__ packed,
+                           const unsigned char *__restrict__ flag, int mode) {
+  /* flag (or NULL = every node): the nodes of this level that belong to the rank's locally essential tree
+   * (force_step.cuh); the others are left alone.  mode 0: build and export; 1: build only (the level whose
+   * records are exchanged between the ranks before they are exported); 2: export the records already in `work` */
   __shared__ __align__(16) double stage[kMomThreads * 32]; /* 27 doubles per record; 32 reals per packed row */
   const int base = blockIdx.x * kMomThreads;
   const int t = base + threadIdx.x;
   const int valid = min(kMomThreads, n - base);
+  const bool mine = t < n && (!flag || flag[lo + t]);
+  if (!__syncthreads_or(mine)) return;
   /* the per-node work records are kept component-major (work[k * numNodes + node]): neighbouring
    * threads own neighbouring nodes and their children are neighbours one level down, so every
    * load and store of a component is a run of consecutive doubles instead of a 224-byte stride */
   double *w = reinterpret_cast<double *>(work);
   constexpr int kWords = (int)(sizeof(MomentNode) / sizeof(double));
   MomentNode m;
-  if (t < n) {
+  if (mine && mode == 2) {
+    double *pm = reinterpret_cast<double *>(&m);
+#pragma unroll
+    for (int k = 0; k < kWords; ++k) pm[k] = w[(size_t)k * numNodes + lo + t];
+    node_export(m, stage + threadIdx.x * 27);
+  } else if (mine) {
     const int i = lo + t;
     const int c0 = child0[i], c1 = child1[i];
     if (c0 < 0 && c1 < 0) {
@@ -327,8 +338,9 @@ build_moments_level_kernel(const double *__restrict__ pos, const double *__restr
 #pragma unroll
       for (int k = 0; k < kWords; ++k) w[(size_t)k * numNodes + i] = pm[k];
     }
-    node_export(m, stage + threadIdx.x * 27);
+    if (mode != 1) node_export(m, stage + threadIdx.x * 27);
   }
+  if (mode == 1) return;
   __syncthreads();
   const size_t first = (size_t)(lo + base);
   if (out64)

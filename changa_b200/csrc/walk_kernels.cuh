@@ -70,11 +70,17 @@ struct WalkTree {
 
 constexpr int kWalkMaybeSoft = 1 << 31; /* clist entries only: some bucket below the owner MAY see this cell softened */
 
+/* built (or NULL = every node): nodes from index builtAlways on carry a record only where built[] is set (the
+ * locally essential build of a multi-GPU step, let_kernels.cuh); the others get a harmless record with the mark
+ * first = -1, which the walk reports if it ever meets one */
+constexpr int kWalkNotBuilt = 4; /* cb200_lists.error: the walk touched a node outside the built part of the tree */
 __global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMono, WalkNodeRec *__restrict__ out,
-                                       unsigned long long *softMaxBits) {
+                                       unsigned long long *softMaxBits, const unsigned char *__restrict__ built,
+                                       int builtAlways) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool have = i < t.numNodes && (!built || i < builtAlways || built[i]);
   double soft = 0.0;
-  if (i < t.numNodes) soft = fmax(t.mom[(size_t)i * 27 + 1], 0.0);
+  if (have) soft = fmax(t.mom[(size_t)i * 27 + 1], 0.0);
   /* non-negative doubles order like their bit patterns */
   unsigned long long b = (unsigned long long)__double_as_longlong(soft);
 #pragma unroll
@@ -84,6 +90,13 @@ __global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMon
   }
   if ((threadIdx.x & 31) == 0) atomicMax(softMaxBits, b);
   if (i >= t.numNodes) return;
+  if (!have) {
+    WalkNodeRec r;
+    r.cx = r.cy = r.cz = r.ropen = r.soft = r.ropenMono = 0.0;
+    r.child0 = r.child1 = -1; r.first = -1; r.last = -2;
+    out[i] = r;
+    return;
+  }
   const double *m = t.mom + (size_t)i * 27;
   WalkNodeRec r;
   /* the two radii of openCriterionNode depend on the source node only: computed once here with the
@@ -331,6 +344,7 @@ __device__ __forceinline__ bool walk_node_fast(const WalkTree &t, const WalkPara
     const int c0 = src.child0, c1 = src.child1;
     const int npart = src.last - src.first + 1;
     if (have) {
+      if (src.first < 0) *pools.error = kWalkNotBuilt;
       e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
       const double cx = __dadd_rn(src.cx, shiftTab[(e.offsetID >> 22) & 7]);
       const double cy = __dadd_rn(src.cy, shiftTab[(e.offsetID >> 25) & 7]);
@@ -518,6 +532,7 @@ __device__ __noinline__ WalkNodeCounts walk_node_general(const WalkTree &t, cons
     bool srcBucket = false;
     int c0 = -1, c1 = -1;
     if (have) {
+      if (src.first < 0) *pools.error = kWalkNotBuilt;
       e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
       double c[3];
       walk_shifted_cm(src, e.offsetID, p.period, c);

@@ -334,6 +334,9 @@ typedef struct cb200_step_result {
   double cost;                            /* 198 pcPairs + 30 ppPairs */
   float ms[CB200_PH_COUNT];               /* CUDA events on the step's stream; with overlapEwald the Ewald
                                              kernel's time lies inside the walk phase */
+  int letBlockLevel;                      /* multi-GPU: tree level below which this rank built only the subtrees near its
+                                             own buckets (locally essential moment build); -1: everything built */
+  int letFallback;                        /* 1: this step's walk left that part and was repeated on the full build */
 } cb200_step_result;
 
 /* the costCuts rule on the host: last step's boundaries prevCut[0..world] (particle indices) and the cost

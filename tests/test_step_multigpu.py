@@ -64,7 +64,7 @@ for cost in (0, 1):
         res = st.run()
     np.savez(os.path.join(outdir, f"rank{{rank}}_cost{{cost}}.npz"), idx=st.idx.array[:res.rows].copy(),
              rows=st.out.array[:res.rows].copy(), range=np.array([res.bucketLo, res.bucketHi, res.partLo, res.partHi]),
-             cost=res.cost, pairs=np.array([res.pcPairs, res.ppPairs]))
+             cost=res.cost, pairs=np.array([res.pcPairs, res.ppPairs]), let=np.array([res.letBlockLevel, res.letFallback]))
     st.free()
 tot = comm.allreduce([1.0, rank], "sum")
 assert tot[0] == world and tot[1] == world * (world - 1) / 2
@@ -75,10 +75,19 @@ print("rank", rank, "ok")
 
 
 @pytest.mark.gpu
-def test_two_ranks_over_nccl_equal_the_single_gpu_step(tmp_path):
+@pytest.mark.parametrize("let_blocks", [0, 64])
+def test_two_ranks_over_nccl_equal_the_single_gpu_step(tmp_path, let_blocks, monkeypatch):
+    """let_blocks = 64: the locally essential moment build (csrc/let_kernels.cuh) is switched on for this small box
+    (block level = first level with 64 x world nodes; by default a box needs 32768 x world): every rank builds only
+    the subtrees near its own buckets below that level, exchanges the block records, and must still reproduce the
+    single-GPU rows bit for bit without falling back to the full build"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    if let_blocks:
+        monkeypatch.setenv("CB200_LET_BLOCKS_PER_RANK", str(let_blocks))
+    else:
+        monkeypatch.setenv("CB200_LET", "0")
     from changa_b200.hostcuda import HostCUDA
     from changa_b200.step import NativeStep
     from changa_b200.workloads import clustered_box
@@ -105,6 +114,10 @@ def test_two_ranks_over_nccl_equal_the_single_gpu_step(tmp_path):
         for k in range(2):
             got[r[k]["idx"]] = r[k]["rows"]
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))       # bit for bit, every particle once
+        for k in range(2):
+            level, fallback = (int(x) for x in r[k]["let"])
+            assert fallback == 0
+            assert (level >= 0) == bool(let_blocks), (level, let_blocks)
         assert tuple(r[0]["pairs"] + r[1]["pairs"]) == pairs1                    # same work, split not duplicated
         if cost:  # the measured costs of the two ranks are closer than with equal particle counts
             c = np.array([float(r[0]["cost"]), float(r[1]["cost"])])

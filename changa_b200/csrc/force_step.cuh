@@ -419,6 +419,33 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   nvtx_push("all-gather");
   const double *box = st->d_rec;
   const unsigned char *rungs = st->d_rung;
+  /* Distributed sort: every rank keys and sorts its OWN slice on the second stream while the records travel,
+   * the sorted runs (key + caller index, 12 bytes per particle) are all-gathered and merged pairwise
+   * (cub::DeviceMerge, stable: runs are in rank = caller order) -- log2(N) passes over the box instead of the
+   * eight passes of a radix sort of all of it on every rank. */
+  static const int dsortEnv = getenv("CB200_DSORT") ? atoi(getenv("CB200_DSORT")) : 1;
+  const bool dsort = world > 1 && dsortEnv != 0;
+  unsigned long long *runKeys[2] = {nullptr, nullptr};
+  int *runIdx[2] = {nullptr, nullptr};
+  unsigned long long *myKeys = nullptr;
+  int *myIdx = nullptr;
+  if (dsort) {
+    const size_t all = (size_t)chunk * world;
+    for (int k = 0; k < 2; ++k) {
+      runKeys[k] = (unsigned long long *)pool_alloc(all * 8, s);
+      runIdx[k] = (int *)pool_alloc(all * 4, s);
+    }
+    myKeys = (unsigned long long *)pool_alloc((size_t)chunk * 8, s);
+    myIdx = (int *)pool_alloc((size_t)chunk * 4, s);
+    cudaChk(cudaEventRecord(st->evFork, s));
+    cudaChk(cudaStreamWaitEvent(st->aux, st->evFork, 0));
+    const long long base = (long long)rank * chunk;
+    const int myRows = (int)(base >= n ? 0 : (n - base < chunk ? n - base : chunk));
+    TreeInput mine;
+    mine.pos = st->d_rec; mine.mass = st->d_rec + 3; mine.soft = st->d_rec + 4; mine.posStride = 5; mine.attrStride = 5;
+    tree_sorted_keys(mine, myRows, cfg.rootlo, cfg.roothi, (int)base, myKeys, myIdx, st->aux);
+    cudaChk(cudaEventRecord(st->evJoin, st->aux));
+  }
   if (world > 1) {
     ncclChk(nccl_api()->AllGather(st->d_rec, st->d_all, (size_t)chunk * 5, ncclDouble, st->comm->comm, s));
     box = st->d_all;
@@ -426,6 +453,11 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
       ncclChk(nccl_api()->AllGather(st->d_rung, st->d_rungAll, (size_t)chunk, ncclChar, st->comm->comm, s));
       rungs = st->d_rungAll;
     }
+  }
+  if (dsort) {
+    cudaChk(cudaStreamWaitEvent(s, st->evJoin, 0));
+    ncclChk(nccl_api()->AllGather(myKeys, runKeys[0], (size_t)chunk, ncclUint64, st->comm->comm, s));
+    ncclChk(nccl_api()->AllGather(myIdx, runIdx[0], (size_t)chunk, ncclInt32, st->comm->comm, s));
   }
   nvtx_pop();
   cudaChk(cudaEventRecord(st->ev[PH_GATHER + 1], s));
@@ -446,7 +478,22 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   else for (int r = 0; r <= cutWorld; ++r) targets[r] = (int)((long long)r * n / cutWorld);
   TreeInput in;
   in.pos = box; in.mass = box + 3; in.soft = box + 4; in.posStride = 5; in.attrStride = 5;
-  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, targets, cutWorld + 1, cuts, s);
+  unsigned long long *preKeys = nullptr;
+  int *preOrder = nullptr;
+  if (dsort) {
+    std::vector<long long> off;
+    std::vector<int> len;
+    for (int r = 0; r < world; ++r) {
+      const long long base = (long long)r * chunk;
+      off.push_back(base);
+      len.push_back((int)(base >= n ? 0 : (n - base < chunk ? n - base : chunk)));
+    }
+    const int at = merge_sorted_runs(runKeys, runIdx, off, len, s);
+    preKeys = runKeys[at]; preOrder = runIdx[at]; /* owned by the tree from here */
+    pool_free(runKeys[at ^ 1], s); pool_free(runIdx[at ^ 1], s);
+    pool_free(myKeys, s); pool_free(myIdx, s);
+  }
+  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, targets, cutWorld + 1, cuts, s, preKeys, preOrder);
   st->haveTree = true;
   cb200_tree &tr = st->tree;
   nvtx_pop();

@@ -41,6 +41,7 @@
 #include <nvtx3/nvToolsExt.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_reduce.cuh>
+#include <cub/device/device_merge.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -1058,8 +1059,73 @@ __global__ void tree_set_buckets_kernel(const int *__restrict__ rank, int n, Tre
 /* the build; input as three arrays or one record array (TreeInput).  h_targets (optional, nCuts <= 17 particle
  * indices, host): rank boundaries looked up on the device and returned in cuts[2r] (bucket) / cuts[2r+1]
  * (particle).  ONE stream synchronisation (the node / bucket / level counts size everything downstream). */
+/* keys of rows [0, n) of `in` and their stable sort (ties keep the row order, as the host comparator): keysOut /
+ * orderOut get the sorted keys and the rows' indices idxBase + row */
+static void tree_sorted_keys(const TreeInput &in, int n, const double *rootlo, const double *roothi, int idxBase,
+                             unsigned long long *keysOut, int *orderOut, cudaStream_t s) {
+  if (n <= 0) return;
+  TreeBox box;
+  for (int d = 0; d < 3; ++d) { box.lo[d] = rootlo[d]; box.inv[d] = 1.0 / (roothi[d] - rootlo[d]); }
+  unsigned long long *keysIn = (unsigned long long *)pool_alloc((size_t)n * 8, s);
+  int *idxIn = (int *)pool_alloc((size_t)n * 4, s);
+  tree_keys_kernel<<<(n + 255) / 256, 256, 0, s>>>(in, n, box, keysIn, idxIn, idxBase);
+  cudaChk(cudaPeekAtLastError());
+  size_t tmpBytes = 0;
+  cudaChk(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keysIn, keysOut, idxIn, orderOut, n, 0, kTreeKeyBits, s));
+  void *tmp = pool_alloc(tmpBytes, s);
+  cudaChk(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keysOut, idxIn, orderOut, n, 0, kTreeKeyBits, s));
+  pool_free(tmp, s); pool_free(keysIn, s); pool_free(idxIn, s);
+  g_launches.fetch_add(3);
+}
+
+/* Stable merge of sorted runs into one: run r = (keys + off[r], idx + off[r], len[r]), runs in rank order, so equal
+ * keys end up in the caller's order exactly as one stable sort of the whole box leaves them.  Pairwise rounds of
+ * cub::DeviceMerge between two buffer pairs; returns 0 / 1: the pair that holds the n merged entries from offset 0. */
+static int merge_sorted_runs(unsigned long long *keys[2], int *idx[2], std::vector<long long> off, std::vector<int> len,
+                             cudaStream_t s) {
+  int cur = 0;
+  size_t maxTmp = 0;
+  void *tmp = nullptr;
+  bool compact = false; /* the first round also closes the gaps between the padded slices */
+  while (len.size() > 1 || !compact) {
+    std::vector<long long> noff;
+    std::vector<int> nlen;
+    long long at = 0;
+    for (size_t r = 0; r < len.size(); r += 2) {
+      if (r + 1 < len.size()) {
+        size_t bytes = 0;
+        cudaChk(cub::DeviceMerge::MergePairs(nullptr, bytes, keys[cur] + off[r], idx[cur] + off[r], len[r], keys[cur] + off[r + 1],
+                                             idx[cur] + off[r + 1], len[r + 1], keys[cur ^ 1] + at, idx[cur ^ 1] + at,
+                                             ::cuda::std::less<>{}, s));
+        if (bytes > maxTmp) { pool_free(tmp, s); tmp = pool_alloc(bytes, s); maxTmp = bytes; }
+        cudaChk(cub::DeviceMerge::MergePairs(tmp, bytes, keys[cur] + off[r], idx[cur] + off[r], len[r], keys[cur] + off[r + 1],
+                                             idx[cur] + off[r + 1], len[r + 1], keys[cur ^ 1] + at, idx[cur ^ 1] + at,
+                                             ::cuda::std::less<>{}, s));
+        noff.push_back(at); nlen.push_back(len[r] + len[r + 1]);
+        at += len[r] + len[r + 1];
+      } else {
+        if (len[r] > 0) {
+          cudaChk(cudaMemcpyAsync(keys[cur ^ 1] + at, keys[cur] + off[r], (size_t)len[r] * 8, cudaMemcpyDeviceToDevice, s));
+          cudaChk(cudaMemcpyAsync(idx[cur ^ 1] + at, idx[cur] + off[r], (size_t)len[r] * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        noff.push_back(at); nlen.push_back(len[r]);
+        at += len[r];
+      }
+      g_launches.fetch_add(1);
+    }
+    off.swap(noff); len.swap(nlen);
+    cur ^= 1;
+    compact = true;
+  }
+  pool_free(tmp, s);
+  return cur;
+}
+
+/* preKeys / preOrder (or NULL): the sorted keys and the sorted rows' caller indices, made elsewhere (the multi-GPU
+ * step sorts every rank's slice on its own GPU and merges the runs); both pool blocks of stream s, owned from here */
 static void build_tree_impl(const TreeInput &in, int n, int maxBucket, const double *rootlo, const double *roothi,
-                            cb200_tree *out, const int *h_targets, int nCuts, int *h_cuts, cudaStream_t s) {
+                            cb200_tree *out, const int *h_targets, int nCuts, int *h_cuts, cudaStream_t s,
+                            unsigned long long *preKeys = nullptr, int *preOrder = nullptr) {
   memset(out, 0, sizeof *out);
   out->numParticles = n;
   if (n <= 0) return;
@@ -1067,17 +1133,13 @@ static void build_tree_impl(const TreeInput &in, int n, int maxBucket, const dou
   for (int d = 0; d < 3; ++d) { box.lo[d] = rootlo[d]; box.inv[d] = 1.0 / (roothi[d] - rootlo[d]); }
   const int tb = 256;
   /* keys, stable sort by key (ties keep the caller's order), sorted particle arrays */
-  unsigned long long *keysIn = (unsigned long long *)pool_alloc((size_t)n * 8, s);
-  unsigned long long *keys = (unsigned long long *)pool_alloc((size_t)n * 8, s);
-  int *idxIn = (int *)pool_alloc((size_t)n * 4, s);
-  out->d_order = (int *)pool_alloc((size_t)n * 4, s);
-  tree_keys_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(in, n, box, keysIn, idxIn);
-  cudaChk(cudaPeekAtLastError());
-  size_t tmpBytes = 0;
-  cudaChk(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keysIn, keys, idxIn, out->d_order, n, 0, kTreeKeyBits, s));
-  void *tmp = pool_alloc(tmpBytes, s);
-  cudaChk(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keys, idxIn, out->d_order, n, 0, kTreeKeyBits, s));
-  pool_free(tmp, s); pool_free(keysIn, s); pool_free(idxIn, s);
+  unsigned long long *keys = preKeys;
+  out->d_order = preOrder;
+  if (!keys) {
+    keys = (unsigned long long *)pool_alloc((size_t)n * 8, s);
+    out->d_order = (int *)pool_alloc((size_t)n * 4, s);
+    tree_sorted_keys(in, n, rootlo, roothi, 0, keys, out->d_order, s);
+  }
   out->d_pos = (double *)pool_alloc((size_t)n * 24, s);
   out->d_mass = (double *)pool_alloc((size_t)n * 8, s);
   out->d_soft = (double *)pool_alloc((size_t)n * 8, s);
@@ -1085,7 +1147,7 @@ static void build_tree_impl(const TreeInput &in, int n, int maxBucket, const dou
   tree_gather_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(in, out->d_order, n, out->d_pos, out->d_mass, out->d_soft,
                                                       (PackedPart *)out->d_packedParts);
   cudaChk(cudaPeekAtLastError());
-  g_launches.fetch_add(5);
+  g_launches.fetch_add(2);
 
   /* nodes, level by level inside one cooperative kernel; capacity: a node holds at least one
    * particle, chains of single children are the only way past ~n/3 nodes */

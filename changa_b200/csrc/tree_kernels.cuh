@@ -45,8 +45,9 @@ struct TreeInput {
   int posStride, attrStride;
 };
 
+/* idxBase: index of row 0 in the caller's order (a rank keys its own slice of the box, force_step.cuh) */
 __global__ void tree_keys_kernel(TreeInput in, int n, TreeBox box,
-                                 unsigned long long *__restrict__ keys, int *__restrict__ idx) {
+                                 unsigned long long *__restrict__ keys, int *__restrict__ idx, int idxBase = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned q[3];
@@ -62,7 +63,7 @@ __global__ void tree_keys_kernel(TreeInput in, int n, TreeBox box,
   for (int b = kTreeKeyBitsPerDim - 1; b >= 0; --b)
     k = (k << 3) | (unsigned long long)((((q[0] >> b) & 1) << 2) | (((q[1] >> b) & 1) << 1) | ((q[2] >> b) & 1));
   keys[i] = k;
-  idx[i] = i;
+  idx[i] = idxBase + i;
 }
 
 __global__ void tree_gather_kernel(TreeInput in, const int *__restrict__ order, int n,

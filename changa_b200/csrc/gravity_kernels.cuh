@@ -678,11 +678,22 @@ __device__ __forceinline__ BucketMeta load_bucket_meta(const int *__restrict__ m
  * on the first use of the bucket's markers -- both at the top of a bucket, with nothing to overlap. */
 __device__ __forceinline__ unsigned grab_bucket_raw(unsigned int *nextBucket, int nBuckets, int lane) {
   unsigned int k = 0;
-  if (lane == 0) {
-    k = atomicAdd(nextBucket, 1u);
-    if (k == (unsigned int)nBuckets + gridDim.x * kListWarps - 1u) *nextBucket = 0u;
-  }
+  /* inline PTX, and nothing looks at k here: nvcc turns a plain atomicAdd under `lane == 0` into its
+   * warp-aggregated form, which broadcasts the result with a SHFL right behind the atomic -- the round trip this
+   * pipeline exists to hide (6.2 % of the p-p kernel's stall samples, profiles/r02aa_ncu_pp_256.json).  The counter
+   * is put back to zero by the launch's last warp to leave (list_kernel_exit) instead of by whoever draws the last
+   * value (grab_bucket): that test needs the value at once. */
+  if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(k) : "l"(nextBucket) : "memory");
+  (void)nBuckets;
   return k;
+}
+/* every warp of a launch calls this once, behind its last draw: nextBucket[1] counts the warps that are done, the
+ * last one zeroes both words for the next launch on the stream */
+__device__ __forceinline__ void list_kernel_exit(unsigned int *nextBucket, int lane) {
+  if (lane == 0) {
+    const unsigned int d = atomicAdd(nextBucket + 1, 1u);
+    if (d == gridDim.x * kListWarps - 1u) { nextBucket[0] = 0u; nextBucket[1] = 0u; }
+  }
 }
 /* markers / start / size of a bucket, loaded through asm so that ptxas does not treat the values as
  * warp-uniform: a uniform value is moved to the uniform register file at once (R2UR right behind the
@@ -949,6 +960,7 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
     m = bucket_meta_uniform(mn);
   }
   cp_async_wait<0>();
+  list_kernel_exit(nextBucket, lane);
 }
 #endif /* !CUDA_USE_DOUBLE */
 

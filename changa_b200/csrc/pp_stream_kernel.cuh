@@ -360,6 +360,7 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
     m = bucket_meta_uniform(mn);
   }
   cp_async_wait<0>();
+  list_kernel_exit(nextBucket, lane);
 }
 
 }  // namespace cb200

@@ -334,7 +334,7 @@ def time_steps(st, comm, steps, resident):
     ev = 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = st.run(resident=resident)
+        res = st.run(resident=resident, sfc_order=True)  # rows in SFC order + caller indices at every N
         ev += float(res.ms[len(res.ms) - 1])
     hc.L.cb200_device_synchronize()
     wall = time.perf_counter() - t0
@@ -601,7 +601,8 @@ def main():
             "e2e": {"value": pairs / box["e2e_s_per_step"], "unit": "interactions/s", "ms_per_step": box["e2e_s_per_step"] * 1e3,
                     "steps": args.steps, "h2d_bytes_per_step": box["h2d"], "d2h_bytes_per_step": box["d2h"],
                     "timing": "wall clock around cb200_step_run from pinned host records to accelerations in pinned host memory "
-                              "(caller order), max over ranks"},
+                              "(each rank's rows in SFC order with their caller indices, copied back slab by slab under the list "
+                              "kernels), max over ranks"},
             "gpu_launches": int(round(box["launches_per_step"] * args.steps * 2)),
             "clocks": box["clocks"],
             "hbm_in_use_gb_rank0": box.get("rank0_hbm_in_use_gb"),

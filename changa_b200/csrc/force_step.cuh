@@ -162,6 +162,7 @@ __global__ void step_marker_range_kernel(const int *__restrict__ markers, int nA
 }
 
 /* ------------------------------------------------------------------- step */
+constexpr int kOutSlabsMax = 8;
 enum { PH_H2D = 0, PH_GATHER, PH_TREE, PH_MOMENTS, PH_EWALD, PH_WALK, PH_PC, PH_PP, PH_FINISH, PH_TOTAL, PH_N };
 
 struct cb200_step {
@@ -170,8 +171,9 @@ struct cb200_step {
   int rank = 0, world = 1, device = 0;
   long long n = 0;
   int chunk = 0;
-  cudaStream_t stream = nullptr, aux = nullptr;
-  cudaEvent_t ev[PH_N + 2], evFork = nullptr, evJoin = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr, outStream = nullptr;
+  cudaEvent_t ev[PH_N + 2], evFork = nullptr, evJoin = nullptr, evTree = nullptr, evOut = nullptr;
+  cudaEvent_t evSlab[kOutSlabsMax][3]; /* start / after p-c / after p-p of every output slab */
   int ewaldSlot = 0;
   int nEwh = 0;
   int *d_hxyz = nullptr;
@@ -317,6 +319,10 @@ cb200_step *cb200_step_create(cb200_comm *comm, const cb200_step_config *cfg) {
   st->chunk = (int)((st->n + st->world - 1) / st->world);
   cudaChk(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
   cudaChk(cudaStreamCreateWithFlags(&st->aux, cudaStreamNonBlocking));
+  cudaChk(cudaStreamCreateWithFlags(&st->outStream, cudaStreamNonBlocking));
+  cudaChk(cudaEventCreateWithFlags(&st->evTree, cudaEventDisableTiming));
+  cudaChk(cudaEventCreateWithFlags(&st->evOut, cudaEventDisableTiming));
+  for (auto &e3 : st->evSlab) for (cudaEvent_t &e : e3) cudaChk(cudaEventCreate(&e));
   for (cudaEvent_t &e : st->ev) cudaChk(cudaEventCreate(&e));
   cudaChk(cudaEventCreateWithFlags(&st->evFork, cudaEventDisableTiming));
   cudaChk(cudaEventCreateWithFlags(&st->evJoin, cudaEventDisableTiming));
@@ -361,7 +367,9 @@ void cb200_step_destroy(cb200_step *st) {
                   (void *)st->d_letCover, (void *)st->d_letScalars})
     if (p) cudaChk(cudaFree(p));
   for (cudaEvent_t &e : st->ev) cudaEventDestroy(e);
-  cudaEventDestroy(st->evFork); cudaEventDestroy(st->evJoin);
+  cudaEventDestroy(st->evFork); cudaEventDestroy(st->evJoin); cudaEventDestroy(st->evTree); cudaEventDestroy(st->evOut);
+  for (auto &e3 : st->evSlab) for (cudaEvent_t &e : e3) cudaEventDestroy(e);
+  cudaStreamDestroy(st->outStream);
   pool_forget_stream(st->stream); pool_forget_stream(st->aux);
   drop_companion(st->stream); drop_stream_counter(st->stream);
   drop_companion(st->aux); drop_stream_counter(st->aux);
@@ -464,7 +472,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
 
   /* tree; the rank boundaries ride back with its one synchronisation */
   nvtx_push("CUDA_SER_TREE");
-  int targets[18], cuts[36];
+  int targets[18], cuts[2 * kTreeMaxCuts], fine[kTreeMaxCuts];
   const bool byCost = cfg.costCuts && !multistep && (int)st->prevCost.size() == world && world > 1;
   /* profiling aid: CB200_EMULATE_RANK="r/N" makes a single-GPU step do the work of rank r of N (its bucket
    * range only; tree and moments whole, as on every rank), so that ncu can look at one rank's share */
@@ -493,7 +501,21 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
     pool_free(runKeys[at ^ 1], s); pool_free(runIdx[at ^ 1], s);
     pool_free(myKeys, s); pool_free(myIdx, s);
   }
-  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, targets, cutWorld + 1, cuts, s, preKeys, preOrder);
+  /* Output slabs: rows that come back in SFC order (several ranks, or one GPU with an index array) are copied
+   * out slab by slab while the next slab's list kernels run, so the slab boundaries are looked up with the rank
+   * boundaries: fine[r * S + j] = target r plus j/S of the way to target r + 1 */
+  static const int slabsEnv = getenv("CB200_OUT_SLABS") ? atoi(getenv("CB200_OUT_SLABS")) : 0;
+  const bool sfcOut = h_out && (world > 1 || h_index);
+  /* about a million rows per slab, at most eight: the last slab's copy is the only one nothing hides, and a list
+   * launch over fewer buckets loses to its own tail (a multistep step re-cuts by active particles: one slab) */
+  int S = sfcOut && !multistep ? (slabsEnv > 0 ? slabsEnv : n / cutWorld / (1 << 20)) : 1;
+  if (S < 1) S = 1;
+  if (S > kOutSlabsMax) S = kOutSlabsMax;
+  for (int r = 0; r < cutWorld; ++r)
+    for (int j = 0; j < S; ++j)
+      fine[r * S + j] = targets[r] + (int)(((long long)(targets[r + 1] - targets[r]) * j) / S);
+  fine[cutWorld * S] = targets[cutWorld];
+  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, fine, cutWorld * S + 1, cuts, s, preKeys, preOrder);
   st->haveTree = true;
   cb200_tree &tr = st->tree;
   nvtx_pop();
@@ -502,10 +524,13 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   if (tr.error) { res->error = 10 + tr.error; nvtx_pop(); return; }
   const int nn = tr.numNodes, nb = tr.numBuckets;
 
-  /* my share: buckets [b0, b1) = particles [p0, p1) */
-  int b0 = cuts[2 * cutRank], p0 = cuts[2 * cutRank + 1], b1 = cuts[2 * cutRank + 2], p1 = cuts[2 * cutRank + 3];
-  if (cutRank == 0) { b0 = 0; p0 = 0; }
-  if (cutRank == cutWorld - 1) { b1 = nb; p1 = n; }
+  /* my share: buckets [b0, b1) = particles [p0, p1), in S slabs */
+  int slabB[kOutSlabsMax + 1], slabP[kOutSlabsMax + 1];
+  for (int j = 0; j <= S; ++j) { slabB[j] = cuts[2 * (cutRank * S + j)]; slabP[j] = cuts[2 * (cutRank * S + j) + 1]; }
+  if (cutRank == 0) { slabB[0] = 0; slabP[0] = 0; }
+  if (cutRank == cutWorld - 1) { slabB[S] = nb; slabP[S] = n; }
+  for (int j = 1; j <= S; ++j) { if (slabB[j] < slabB[j - 1]) slabB[j] = slabB[j - 1]; if (slabP[j] < slabP[j - 1]) slabP[j] = slabP[j - 1]; }
+  int b0 = slabB[0], p0 = slabP[0], b1 = slabB[S], p1 = slabP[S];
 
   /* moments */
   nvtx_push("CUDA_SER_TREE moments");
@@ -618,6 +643,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
       pool_free(d_at, s); pool_free(d_cut, s);
       b0 = rank == 0 ? 0 : cuts[2 * rank]; p0 = rank == 0 ? 0 : cuts[2 * rank + 1];
       b1 = rank == world - 1 ? nb : cuts[2 * rank + 2]; p1 = rank == world - 1 ? n : cuts[2 * rank + 3];
+      slabB[0] = b0; slabB[1] = b1; slabP[0] = p0; slabP[1] = p1; /* S == 1 here */
     }
   }
   res->bucketLo = b0; res->bucketHi = b1; res->partLo = p0; res->partHi = p1;
@@ -714,22 +740,38 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   /* the list kernels see only this rank's buckets [b0, b1): markers, starts and sizes are offset, the
    * marker VALUES still index the whole lists (a launch over all buckets made every warp draw and skip
    * the other ranks' empty buckets: 0.5 ms of a 3.7 ms p-p launch at two ranks) */
-  const int nMine = b1 - b0;
-  nvtx_push("CUDA_GRAV_LOCAL");
-  if (nMine > 0)
-    dispatch_cell_list(cfg.maxBucket, P, st->d_vars, st->d_pkMom, li.d_cell, li.d_cellMarkers + b0, li.d_starts + b0,
-                       li.d_sizes + b0, nMine, fper, counter, s);
-  nvtx_pop();
-  cudaChk(cudaEventRecord(st->ev[PH_PC + 1], s));
-  nvtx_push("CUDA_PART_GRAV_LOCAL");
-  if (nMine > 0) {
-    dispatch_part_list(cfg.maxBucket, P, st->d_vars, P, li.d_part, li.d_partMarkers + b0, li.d_starts + b0, li.d_sizes + b0,
-                       nMine, fper, counter, s);
-    if (li.nSoft)
-      dispatch_part_list(cfg.maxBucket, P, st->d_vars, (const PackedPart *)li.d_nodeParticles, li.d_soft, li.d_softMarkers + b0,
-                         li.d_starts + b0, li.d_sizes + b0, nMine, fper, counter, s);
+  const bool streamOut = sfcOut && p1 - p0 <= outCapacityRows;
+  if (streamOut && p1 > p0) { /* the caller indices of my rows travel under the first slab's kernels */
+    cudaChk(cudaEventRecord(st->evTree, s));
+    cudaChk(cudaStreamWaitEvent(st->outStream, st->evTree, 0));
+    cudaChk(cudaMemcpyAsync(h_index, tr.d_order + p0, (size_t)(p1 - p0) * sizeof(int), cudaMemcpyDeviceToHost, st->outStream));
+    res->d2hBytes += (long long)(p1 - p0) * (long long)sizeof(int);
+  }
+  nvtx_push("CUDA_GRAV_LOCAL / CUDA_PART_GRAV_LOCAL");
+  for (int j = 0; j < S; ++j) {
+    const int bs = slabB[j], nS = slabB[j + 1] - slabB[j];
+    cudaChk(cudaEventRecord(st->evSlab[j][0], s));
+    if (nS > 0)
+      dispatch_cell_list(cfg.maxBucket, P, st->d_vars, st->d_pkMom, li.d_cell, li.d_cellMarkers + bs, li.d_starts + bs,
+                         li.d_sizes + bs, nS, fper, counter, s);
+    cudaChk(cudaEventRecord(st->evSlab[j][1], s));
+    if (nS > 0) {
+      dispatch_part_list(cfg.maxBucket, P, st->d_vars, P, li.d_part, li.d_partMarkers + bs, li.d_starts + bs, li.d_sizes + bs,
+                         nS, fper, counter, s);
+      if (li.nSoft)
+        dispatch_part_list(cfg.maxBucket, P, st->d_vars, (const PackedPart *)li.d_nodeParticles, li.d_soft, li.d_softMarkers + bs,
+                           li.d_starts + bs, li.d_sizes + bs, nS, fper, counter, s);
+    }
+    cudaChk(cudaEventRecord(st->evSlab[j][2], s));
+    if (streamOut && slabP[j + 1] > slabP[j]) { /* this slab's rows are final: out they go, under the next slab's kernels */
+      cudaChk(cudaStreamWaitEvent(st->outStream, st->evSlab[j][2], 0));
+      cudaChk(cudaMemcpyAsync((VariablePartData *)h_out + (slabP[j] - p0), st->d_vars + slabP[j],
+                              (size_t)(slabP[j + 1] - slabP[j]) * sizeof(VariablePartData), cudaMemcpyDeviceToHost, st->outStream));
+      res->d2hBytes += (long long)(slabP[j + 1] - slabP[j]) * (long long)sizeof(VariablePartData);
+    }
   }
   nvtx_pop();
+  cudaChk(cudaEventRecord(st->ev[PH_PC + 1], s));
   cudaChk(cudaEventRecord(st->ev[PH_PP + 1], s));
 
   /* pair counts (the metric) and results */
@@ -742,11 +784,16 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   }
   unsigned long long pairs[2] = {0, 0};
   cudaChk(cudaMemcpyAsync(pairs, st->d_counts, sizeof pairs, cudaMemcpyDeviceToHost, s));
-  if (world == 1) {
+  if (sfcOut) {
+    res->rows = p1 - p0;
+    if (!streamOut) res->error = 30; /* the rank's share outgrew the caller's result buffer */
+    cudaChk(cudaEventRecord(st->evOut, st->outStream));
+    cudaChk(cudaStreamWaitEvent(s, st->evOut, 0));
+  } else if (world == 1) {
     res->rows = n;
     if (h_out && n > outCapacityRows) {
       res->error = 30;
-    } else if (h_out) {
+    } else if (h_out) { /* caller's order: one scatter on the device, one copy */
       step_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(st->d_vars, tr.d_order, n, st->d_out);
       cudaChk(cudaPeekAtLastError());
       cudaChk(cudaMemcpyAsync(h_out, st->d_out, (size_t)n * sizeof(VariablePartData), cudaMemcpyDeviceToHost, s));
@@ -754,13 +801,6 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
     }
   } else {
     res->rows = p1 - p0;
-    if (h_out && p1 - p0 > outCapacityRows) {
-      res->error = 30; /* the rank's share outgrew the caller's result buffer */
-    } else if (h_out && p1 > p0) {
-      cudaChk(cudaMemcpyAsync(h_out, st->d_vars + p0, (size_t)(p1 - p0) * sizeof(VariablePartData), cudaMemcpyDeviceToHost, s));
-      cudaChk(cudaMemcpyAsync(h_index, tr.d_order + p0, (size_t)(p1 - p0) * sizeof(int), cudaMemcpyDeviceToHost, s));
-      res->d2hBytes += (long long)(p1 - p0) * (long long)(sizeof(VariablePartData) + sizeof(int));
-    }
   }
   g_launches.fetch_add(3);
   nvtx_pop();
@@ -770,6 +810,13 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   res->pcPairs = (long long)pairs[0]; res->ppPairs = (long long)pairs[1];
   res->cost = 198.0 * (double)pairs[0] + 30.0 * (double)pairs[1];
   for (int k = 0; k < PH_FINISH + 1; ++k) cudaChk(cudaEventElapsedTime(&res->ms[k], st->ev[k], st->ev[k + 1]));
+  res->ms[PH_PC] = res->ms[PH_PP] = 0.0f;
+  for (int j = 0; j < S; ++j) { /* the slabs' list kernels alternate: their times are summed per kind */
+    float a = 0.0f, b = 0.0f;
+    cudaChk(cudaEventElapsedTime(&a, st->evSlab[j][0], st->evSlab[j][1]));
+    cudaChk(cudaEventElapsedTime(&b, st->evSlab[j][1], st->evSlab[j][2]));
+    res->ms[PH_PC] += a; res->ms[PH_PP] += b;
+  }
   cudaChk(cudaEventElapsedTime(&res->ms[PH_TOTAL], st->ev[0], st->ev[PH_FINISH + 1]));
 
   /* cost feedback for the next step's cuts: every rank learns every rank's cost and range */

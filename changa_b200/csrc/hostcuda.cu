@@ -1188,7 +1188,7 @@ static void build_tree_impl(const TreeInput &in, int n, int maxBucket, const dou
   if (nCuts > 0) {
     d_targets = (int *)pool_alloc((size_t)nCuts * 4, s);
     cudaChk(cudaMemcpyAsync(d_targets, h_targets, (size_t)nCuts * 4, cudaMemcpyHostToDevice, s));
-    tree_cuts_kernel<<<1, 32, 0, s>>>(flag, rank, n, d_targets, nCuts, meta);
+    tree_cuts_kernel<<<1, 160, 0, s>>>(flag, rank, n, d_targets, nCuts, meta); /* nCuts <= kTreeMaxCuts */
   }
   g_launches.fetch_add(6);
   TreeMeta hm;

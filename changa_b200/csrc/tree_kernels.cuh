@@ -145,10 +145,11 @@ __device__ __forceinline__ void tree_emit_children(TreeArrays t, int i, int s, i
 }
 
 /* what the host needs to know about the finished tree: one 4-byte-aligned record, copied back once */
+constexpr int kTreeMaxCuts = 144; /* 17 ranks x 8 output slabs + 1, rounded up */
 struct TreeMeta {
   int numLevels, numNodes, numBuckets, error;
   int levelStart[kTreeMaxLevels + 2];
-  int cuts[2 * 18]; /* bucket and particle index of up to 17 rank boundaries (tree_cuts_kernel) */
+  int cuts[2 * kTreeMaxCuts]; /* bucket and particle index of the rank (and output-slab) boundaries (tree_cuts_kernel) */
 };
 
 /* The whole level loop in ONE cooperative launch (round 1 launched split / scan / emit per level and

@@ -178,7 +178,7 @@ class NativeStep:
             self.rung = hc.allocatePinnedHostMemory((self.chunk,), np.uint8)
             self.rung.array[:] = 0
         self.out = hc.allocatePinnedHostMemory((self.capacity, 5), np.float32)
-        self.idx = hc.allocatePinnedHostMemory((self.capacity,), np.int32) if self.world > 1 else None
+        self.idx = hc.allocatePinnedHostMemory((self.capacity,), np.int32)
         self.result = StepResult()
 
     def my_rows(self):
@@ -218,14 +218,16 @@ class NativeStep:
                                      self.rung.array.nbytes, self.stream)
         self.hc.stream_synchronize(self.stream)
 
-    def run(self, resident=False, keep_lists=False):
+    def run(self, resident=False, keep_lists=False, sfc_order=False):
         """one step.  resident: records already on the device (upload()), results stay there.  Returns the
-        StepResult; rows are in self.out.array[:rows] (and self.idx.array[:rows] when world > 1)."""
+        StepResult.  world > 1, or sfc_order on one GPU: self.out.array[:rows] holds this rank's rows in SFC (tree)
+        order and self.idx.array[:rows] their caller indices -- the form that is copied back slab by slab under the
+        list kernels; one GPU without sfc_order: all rows in the caller's order (one scatter + one copy at the end)."""
         res = self.result
         rec = None if resident else self.rec.array.ctypes.data
         rung = None if (resident or self.rung is None) else self.rung.array.ctypes.data
         out = None if resident else self.out.array.ctypes.data
-        idx = None if (resident or self.idx is None) else self.idx.array.ctypes.data
+        idx = None if (resident or not (self.world > 1 or sfc_order)) else self.idx.array.ctypes.data
         self.L.cb200_step_run(self.handle, rec, rung, out, idx, self.capacity, 1 if keep_lists else 0, C.byref(res))
         if res.error:
             raise RuntimeError(f"cb200_step_run: error {res.error} (11 node capacity, 2x walk capacity, 30 result buffer)")

@@ -353,8 +353,11 @@ void *cb200_step_stream(const cb200_step *step);
 double *cb200_step_device_records(const cb200_step *step);
 unsigned char *cb200_step_device_rungs(const cb200_step *step);
 /* h_records NULL: the records are already in cb200_step_device_records().  h_out NULL: results stay on the
- * device.  world == 1: h_out gets numParticles VariablePartData rows in the caller's order (h_index unused);
- * world > 1: result->rows rows of this rank's SFC range, caller indices in h_index.  Blocking. */
+ * device.  world > 1, or world == 1 with h_index != NULL: h_out gets result->rows VariablePartData rows of this rank's
+ * SFC range (tree order, as TransferParticleVarsBack returns a TreePiece's rows) and h_index their caller indices;
+ * the rows are copied back in up to eight slabs (about a million rows each), each as soon as its list kernels are done, under the next slab's
+ * kernels.  world == 1 with h_index == NULL: numParticles rows in the caller's order (one scatter on the device and
+ * one copy at the end).  Blocking. */
 void cb200_step_run(cb200_step *step, const double *h_records, const unsigned char *h_rungs, void *h_out, int *h_index,
                     int outCapacityRows, int keepLists, cb200_step_result *result);
 /* products of the last run, valid until the next run / destroy (tests, parity sampling) */

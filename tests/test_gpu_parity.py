@@ -607,6 +607,34 @@ def test_raw_particle_step_matches_oracle(hc):
     compare(got[wl["order"]], want, median_tol=5e-6, max_tol=3e-4, pot_tol=2e-5, floor_frac=0.1)
 
 
+def test_native_step_sfc_order_output_in_slabs(hc):
+    """cb200_step_run on one GPU: rows in the caller's order (scatter + one copy) and rows in SFC order with their
+    caller indices (copied back in three slabs under the list kernels: about a million rows per slab) are
+    the same accelerations bit for bit; the resident step leaves the same values on the device"""
+    from changa_b200.step import NativeStep
+    from changa_b200.workloads import uniform_box
+    n = 3 * (1 << 20) + 4321
+    pos, mass, soft = uniform_box(n, seed=3)
+    st = NativeStep(hc, n, theta=0.7, n_replicas=1, period=1.0, ewald={"dEwCut": 2.6, "dEwhCut": 2.8})
+    try:
+        st.set_particles(pos, float(mass[0]), float(soft[0]))
+        res = st.run()
+        assert res.rows == n
+        caller = st.out.array[:n].copy()
+        res = st.run(sfc_order=True)
+        assert res.rows == n
+        idx, rows = st.idx.array[:n].copy(), st.out.array[:n].copy()
+        assert np.array_equal(np.sort(idx), np.arange(n))
+        st.upload()
+        st.run(resident=True)
+        dev = st.vars()
+    finally:
+        st.free()
+    assert np.isfinite(caller).all() and np.abs(caller[:, :3]).max() > 0
+    assert np.array_equal(caller[idx].view(np.uint32), rows.view(np.uint32))
+    assert np.array_equal(dev.view(np.uint32), rows.view(np.uint32))
+
+
 def test_clustered_box_device_path(hc):
     """SURVEY config C4's recipe at a testable size (Plummer halos on a uniform background: 40-level
     tree, softened cells, long lists): device tree == host tree, device lists == host lists, forces

@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1 << 22)
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=1 << 22)
     ap.add_argument("--kind", default="uniform", choices=["uniform", "clustered"])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--no-overlap", action="store_true")

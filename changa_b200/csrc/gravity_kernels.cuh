@@ -952,7 +952,10 @@ cell_list_x2_kernel(const PackedPart *__restrict__ parts, VariablePartData *__re
       bucket_reduce_store<NP>(ax, ay, az, pot, idt, np, npairs, tbase, lane,
                               reinterpret_cast<float *>(vars + m.first + p0));
     }
-    if (!prefetched) prefetch_bucket(mn); /* empty list: nothing rode under a tile */
+    if (!prefetched) { /* empty list: nothing rode under a tile, and nothing waited for this bucket's own prefetch */
+      cp_async_wait<0>(); /* two copies in flight to the same staging bytes may land in either order (racecheck, r02ag) */
+      prefetch_bucket(mn);
+    }
     cp_async_commit();
     if (!deep && k1 < nBuckets) k2raw = grab_bucket_raw(nextBucket, nBuckets, lane);
     k = k1;

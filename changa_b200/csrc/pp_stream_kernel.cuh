@@ -352,7 +352,10 @@ part_list_stream_kernel(const PackedPart *__restrict__ parts, VariablePartData *
       bucket_reduce_store<NP>(ax, ay, az, pot, idt, np, npairs, redBase, lane,
                               reinterpret_cast<float *>(vars + m.first + p0));
     }
-    if (!prefetched) prefetch_bucket(mn); /* empty list: nothing rode under a chunk */
+    if (!prefetched) { /* empty list: nothing rode under a chunk, and nothing waited for this bucket's own prefetch */
+      cp_async_wait<0>(); /* two copies in flight to the same staging bytes may land in either order (racecheck, r02ag) */
+      prefetch_bucket(mn);
+    }
     cp_async_commit();
     if (!deep && k1 < nBuckets) k2raw = grab_bucket_raw(nextBucket, nBuckets, lane);
     k = k1;

@@ -1336,12 +1336,18 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   WalkNodeRec *rec = (WalkNodeRec *)pool_alloc((size_t)numNodes * sizeof(WalkNodeRec), s);
   t.softMaxBits = (const unsigned long long *)(ctl + 128); /* ctl is zeroed above */
   const WalkExtras *extras = tl_walkExtras;
-  walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, p.theta, p.thetaMono, rec,
+  WalkNodeRecF *recf = (WalkNodeRecF *)pool_alloc((size_t)numNodes * sizeof(WalkNodeRecF), s);
+  walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, p.theta, p.thetaMono, p.period, rec, recf,
                                                                 (unsigned long long *)(ctl + 128),
                                                                 extras ? extras->built : nullptr,
                                                                 extras ? extras->builtAlways : 0);
   cudaChk(cudaPeekAtLastError());
   if (extras && extras->reduceSoftMax) extras->reduceSoftMax((unsigned long long *)(ctl + 128), s);
+  t.recf = recf;
+  t.ftol = (const WalkFloatTol *)(ctl + 224);
+  walk_float_tol_kernel<<<1, 1, 0, s>>>(t, p.period, (WalkFloatTol *)(ctl + 224));
+  cudaChk(cudaPeekAtLastError());
+  g_launches.fetch_add(1);
   g_launches.fetch_add(1);
   t.rec = rec;
   /* 4 CTAs of 4 warps per SM: what the kernel's registers (113) and its 50 KB of shared memory
@@ -1454,7 +1460,7 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   }
   pool_free(flaggedBuckets, s); pool_free(levelRange, s);
   pool_free(tmp, s); pool_free(counts, s); pool_free(scratch, s); pool_free(lists, s); pool_free(ctl, s);
-  pool_free(rec, s); pool_free(scanTmp, s); pool_free(activeIdx, s); pool_free(nextActive, s);
+  pool_free(rec, s); pool_free(recf, s); pool_free(scanTmp, s); pool_free(activeIdx, s); pool_free(nextActive, s);
   pool_free(pools.clist, s); pool_free(pools.lplist, s); pool_free(pools.undlist, s);
 }
 

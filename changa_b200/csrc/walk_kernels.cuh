@@ -58,6 +58,30 @@ struct __align__(16) WalkNodeRec {
 };
 static_assert(sizeof(WalkNodeRec) == 64, "WalkNodeRec");
 
+/* The same node for the FLOAT FILTER of walk_node_fast: an opening test is first evaluated in single precision with
+ * a rigorous error band; only a test that lands inside the band (or near the softening reach) is repeated in double
+ * from the 64-byte record, so every decision is the double one.  With u = 2^-24 and Mc = (largest coordinate of the
+ * root's tight box) + 3 * period:
+ *   - the shifted centre c, the box edges and their differences carry at most E2 = 6.2 u Mc each (conversion of cm,
+ *     shift, edge; two rounded float operations), so |delta_f - delta| <= E2 per axis;
+ *   - q_f = fl(sum delta_f^2) differs from the double dsq by at most 3.5 E2 sqrt(dsq) + 3 E2^2 + 3.2 u dsq, and
+ *     sqrt(dsq) <= (dsq / R + R) / 2 for the node's opening radius R, so
+ *       |q_f - R2_f| > tau (q_f + R2_f) + absTol,   tau = 1.8 E2 / R + 3.3 u (+ the cast of R^2),  absTol = 3 E2^2
+ *     decides dsq <= R^2 either way (tau and absTol below carry a further factor 4 on E2).
+ * tau travels with the node (it depends on R), absTol and the softening gate with the walk. */
+struct __align__(16) WalkNodeRecF {
+  float cx, cy, cz, ropen2;
+  float tau;
+  int child0, child1;
+  int npart; /* last - first + 1; -1: not built by this rank (let_kernels.cuh) */
+};
+static_assert(sizeof(WalkNodeRecF) == 32, "WalkNodeRecF");
+struct WalkFloatTol {
+  float absTol;   /* 3 E2^2, rounded up */
+  float softGate; /* q_f above it: the box is out of reach of every softening test and of the maybe-softened flag */
+  float e2;       /* E2 (with the safety factor), for the gate */
+};
+
 /* moments arrive as 27 doubles per node in CudaMultipoleMoments order */
 struct WalkTree {
   int numNodes, numBuckets;
@@ -65,6 +89,8 @@ struct WalkTree {
   const double *boxlo, *boxhi, *mom;
   const int *bucketNode;
   const WalkNodeRec *rec;
+  const WalkNodeRecF *recf;
+  const WalkFloatTol *ftol; /* filled by walk_float_tol_kernel once the largest softening is known */
   const unsigned long long *softMaxBits; /* max over nodes of `soft`, as the bits of a non-negative double */
 };
 
@@ -74,9 +100,26 @@ constexpr int kWalkMaybeSoft = 1 << 31; /* clist entries only: some bucket below
  * locally essential build of a multi-GPU step, let_kernels.cuh); the others get a harmless record with the mark
  * first = -1, which the walk reports if it ever meets one */
 constexpr int kWalkNotBuilt = 4; /* cb200_lists.error: the walk touched a node outside the built part of the tree */
-__global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMono, WalkNodeRec *__restrict__ out,
-                                       unsigned long long *softMaxBits, const unsigned char *__restrict__ built,
-                                       int builtAlways) {
+/* scale of the float filter's error band: (largest |coordinate| of the root's tight box) + 3 |period| */
+__device__ __forceinline__ double walk_coord_scale(const WalkTree &t, double period) {
+  double m = 0.0;
+  for (int d = 0; d < 3; ++d) { m = fmax(m, fabs(t.boxlo[d])); m = fmax(m, fabs(t.boxhi[d])); }
+  return m + 3.0 * fabs(period);
+}
+constexpr double kWalkU = 5.9604644775390625e-08;           /* 2^-24 */
+constexpr double kWalkE2Factor = 4.0 * 6.2 * kWalkU;         /* E2 = this x Mc (safety factor 4) */
+__global__ void walk_float_tol_kernel(WalkTree t, double period, WalkFloatTol *__restrict__ out) {
+  const double e2 = kWalkE2Factor * walk_coord_scale(t, period);
+  const double B = 2.0 * (2.0 * __longlong_as_double((long long)*t.softMaxBits)) * 1.0001; /* (2 soft + rmMax) <= 2 rmMax */
+  WalkFloatTol w;
+  w.absTol = (float)(3.0 * e2 * e2 * 1.001) + 1e-37f;
+  w.softGate = (float)((B * B * (1.0 + 4.0 * kWalkU) + 3.5 * e2 * B + 3.0 * e2 * e2) * 1.001) + 1e-37f;
+  w.e2 = (float)(e2 * 1.001);
+  *out = w;
+}
+__global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMono, double period, WalkNodeRec *__restrict__ out,
+                                       WalkNodeRecF *__restrict__ outf, unsigned long long *softMaxBits,
+                                       const unsigned char *__restrict__ built, int builtAlways) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool have = i < t.numNodes && (!built || i < builtAlways || built[i]);
   double soft = 0.0;
@@ -95,6 +138,10 @@ __global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMon
     r.cx = r.cy = r.cz = r.ropen = r.soft = r.ropenMono = 0.0;
     r.child0 = r.child1 = -1; r.first = -1; r.last = -2;
     out[i] = r;
+    WalkNodeRecF f;
+    f.cx = f.cy = f.cz = f.ropen2 = f.tau = 0.0f;
+    f.child0 = f.child1 = -1; f.npart = -1;
+    outf[i] = f;
     return;
   }
   const double *m = t.mom + (size_t)i * 27;
@@ -109,6 +156,15 @@ __global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMon
   r.soft = m[1]; r.cx = m[3]; r.cy = m[4]; r.cz = m[5];
   r.child0 = t.child0[i]; r.child1 = t.child1[i]; r.first = t.first[i]; r.last = t.last[i];
   out[i] = r;
+  WalkNodeRecF f;
+  f.cx = (float)r.cx; f.cy = (float)r.cy; f.cz = (float)r.cz;
+  f.ropen2 = (float)__dmul_rn(ropen, ropen);
+  const double e2 = kWalkE2Factor * walk_coord_scale(t, period);
+  /* R == 0 (a point): the band is everything, the test goes to double */
+  const double tau = ropen > 0.0 ? (1.8 * e2 / ropen + 4.5 * kWalkU) * 1.001 : 3.0e38;
+  f.tau = tau < 3.0e38 ? (float)tau : 3.0e38f;
+  f.child0 = r.child0; f.child1 = r.child1; f.npart = r.last - r.first + 1;
+  outf[i] = f;
 }
 
 struct WalkParams {
@@ -271,15 +327,50 @@ __device__ __forceinline__ double walk_box_dist2_lean(const double (&lo)[3], con
 
 constexpr int kWalkLpFast = 128; /* bucket-list head of the fast routine (the general one uses kWalkLpS of it) */
 static_assert(kWalkLpFast >= kWalkLpS, "one shared-memory area serves both routines");
+constexpr int kWalkRowF = 3; /* uint4 per staged float record: 32 bytes + 16 of padding (48-byte pitch: LDS.128 conflict-free) */
+
+/* the local node of a warp, in double, for the (rare) tests that are repeated in double: kept in shared memory so
+ * that the hot loop holds only the float copies.  wd[0..2] box lo, [3..5] box hi, [6..8] centre of mass, [9] soft */
+constexpr int kWalkMineDoubles = 10;
+
+/* one opening test in double, exactly as walk_node_general evaluates it (openCriterionNode, gravity.h:652-723;
+ * openSoftening :251-260; the maybe-softened flag of the emit step): 1 open, -1 undecided, 0 accept */
+template <bool LEAF>
+__device__ __noinline__ int walk_test_double(const WalkNodeRec *__restrict__ rec, int node, int offsetID, const double *wd,
+                                             const double *shiftTab, double rmMax, int *flaggedOut) {
+  const WalkNodeRec src = rec[node];
+  const double lo[3] = {wd[0], wd[1], wd[2]}, hi[3] = {wd[3], wd[4], wd[5]};
+  const double cx = __dadd_rn(src.cx, shiftTab[(offsetID >> 22) & 7]);
+  const double cy = __dadd_rn(src.cy, shiftTab[(offsetID >> 25) & 7]);
+  const double cz = __dadd_rn(src.cz, shiftTab[(offsetID >> 28) & 7]);
+  const double dsq = walk_box_dist2_lean(lo, hi, cx, cy, cz);
+  int open = 0;
+  *flaggedOut = 0;
+  if (src.last - src.first + 1 <= 6) return 1;
+  if (dsq <= __dmul_rn(src.ropen, src.ropen)) {
+    if (LEAF) return 1;
+    const double c[3] = {cx, cy, cz};
+    return walk_box_inside_sphere(lo, hi, c, src.ropen) ? 1 : -1;
+  }
+  const double rs = 2.0 * src.soft, rm2 = 2.0 * wd[9];
+  const double rflag = __dadd_rn(rs, rmMax);
+  const double rflag2 = __dmul_rn(rflag, rflag);
+  const double dx = __dsub_rn(wd[6], cx), dy = __dsub_rn(wd[7], cy), dz = __dsub_rn(wd[8], cz);
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  const double rr = __dadd_rn(rs, rm2);
+  if ((d2 <= __dmul_rn(rr, rr)) || (dsq <= __dmul_rn(rs, rs)))
+    open = dsq <= __dmul_rn(src.ropenMono, src.ropenMono) ? 1 : 0;
+  *flaggedOut = (open == 0 && dsq <= rflag2) ? 1 : 0;
+  return open;
+}
 
 template <bool LEAF>
 __device__ __forceinline__ bool walk_node_fast(const WalkTree &t, const WalkParams &p, const WalkPools &pools,
-                                               const WalkNodeRec &mine, const double (&mylo)[3], const double (&myhi)[3],
-                                               int target, int par, const NodeLists *__restrict__ lists, double rmMax,
-                                               const double *shiftTab, uint4 *rows, WalkEntry *sring, WalkEntry *scl,
-                                               WalkEntry *sund, WalkEntry *slp, WalkEntry *cl, WalkEntry *lp, WalkEntry *und,
-                                               int lane, int &nc, int &nl, int &nu, int &flC, int &flL, int &flU,
-                                               int &myParts, int &myFlagged) {
+                                               const double *wd, int target, int par, const NodeLists *__restrict__ lists,
+                                               double rmMax, const double *shiftTab, const float *shiftTabF, uint4 *rows,
+                                               WalkEntry *sring, WalkEntry *scl, WalkEntry *sund, WalkEntry *slp, WalkEntry *cl,
+                                               WalkEntry *lp, WalkEntry *und, int lane, int &nc, int &nl, int &nu, int &flC,
+                                               int &flL, int &flU, int &myParts, int &myFlagged) {
   constexpr int kMask = kWalkRingS - 1;
   static_assert((kWalkRingS & kMask) == 0, "ring size is a power of two");
   int head = 0, tail = 0;
@@ -303,15 +394,19 @@ __device__ __forceinline__ bool walk_node_fast(const WalkTree &t, const WalkPara
     tail = pl.uLen;
   }
   __syncwarp();
-  const double rm2 = 2.0 * mine.soft;
+  /* the local box in float: its rounding is part of the error band (WalkNodeRecF) */
+  const float lox = (float)wd[0], loy = (float)wd[1], loz = (float)wd[2];
+  const float hix = (float)wd[3], hiy = (float)wd[4], hiz = (float)wd[5];
+  const WalkFloatTol ftol = *t.ftol;
   const unsigned below = (1u << lane) - 1;
-  /* records of a batch: four lanes fetch the four 16-byte pieces of one 64-byte record (see walk_node_general) */
+  /* records of a batch: two lanes fetch the two 16-byte halves of one 32-byte float record, 16 records per
+   * cp.async instruction, into rows of 48-byte pitch (every lane then reads its own row with two LDS.128) */
   auto stage = [&](uint4 *dstRows, int node) {
-    const int sub = lane >> 2, piece = lane & 3;
+    const int sub = lane >> 1, piece = lane & 1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int src = __shfl_sync(0xffffffffu, node, 8 * j + sub);
-      if (src >= 0) cp_async16_ca(&dstRows[(8 * j + sub) * 5 + piece], reinterpret_cast<const uint4 *>(t.rec + src) + piece);
+    for (int j = 0; j < 2; ++j) {
+      const int src = __shfl_sync(0xffffffffu, node, 16 * j + sub);
+      if (src >= 0) cp_async16_ca(&dstRows[(16 * j + sub) * kWalkRowF + piece], reinterpret_cast<const uint4 *>(t.recf + src) + piece);
     }
     cp_async_commit();
   };
@@ -325,59 +420,52 @@ __device__ __forceinline__ bool walk_node_fast(const WalkTree &t, const WalkPara
     WalkEntry e = eN;
     cp_async_wait<0>();
     __syncwarp();
-    WalkNodeRec src;
-    {
-      uint4 *d = reinterpret_cast<uint4 *>(&src);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) d[k] = rows[buf * (32 * 5) + lane * 5 + k];
-    }
+    const uint4 ra = rows[buf * (32 * kWalkRowF) + lane * kWalkRowF], rb = rows[buf * (32 * kWalkRowF) + lane * kWalkRowF + 1];
     /* the part of the next batch that is queued already: its records are requested before this batch is tested */
     const int nextHead = head + batch;
     const int avail = min(32, tail - nextHead);
     eN.node = -1;
     if (avail > 0) { /* warp-uniform */
       if (lane < avail) eN = sring[(nextHead + lane) & kMask];
-      stage(rows + (buf ^ 1) * (32 * 5), eN.node);
+      stage(rows + (buf ^ 1) * (32 * kWalkRowF), eN.node);
     }
     int open = 0;
-    bool srcBucket = false, flagged = false;
-    const int c0 = src.child0, c1 = src.child1;
-    const int npart = src.last - src.first + 1;
+    bool flagged = false;
+    const int c0 = (int)rb.y, c1 = (int)rb.z, npart = (int)rb.w;
+    const bool srcBucket = c0 < 0 && c1 < 0;
     if (have) {
-      if (src.first < 0) *pools.error = kWalkNotBuilt;
+      if (npart < 0) *pools.error = kWalkNotBuilt;
       e.offsetID = target | (kWalkOffsetMask & e.offsetID); /* reEncodeOffset, TreePiece.cpp:3647-3652 */
-      const double cx = __dadd_rn(src.cx, shiftTab[(e.offsetID >> 22) & 7]);
-      const double cy = __dadd_rn(src.cy, shiftTab[(e.offsetID >> 25) & 7]);
-      const double cz = __dadd_rn(src.cz, shiftTab[(e.offsetID >> 28) & 7]);
-      const double dsq = walk_box_dist2_lean(mylo, myhi, cx, cy, cz);
-      srcBucket = c0 < 0 && c1 < 0;
-      /* openCriterionNode, gravity.h:652-723 */
+      bool exact = false;
       if (npart <= 6) {
-        open = 1;
-      } else if (dsq <= __dmul_rn(src.ropen, src.ropen)) {
-        if (LEAF) open = 1;
-        else {
-          const double c[3] = {cx, cy, cz};
-          open = walk_box_inside_sphere(mylo, myhi, c, src.ropen) ? 1 : -1;
-        }
+        open = 1; /* openCriterionNode opens a node of at most six particles whatever the distance */
       } else {
-        /* Accepted unless softening interferes (openSoftening, gravity.h:251-260, and the maybe-softened flag
-         * of the emit step).  Every sphere involved is centred on c, none is larger than 2 soft + rmMax, and the
-         * local centre of mass lies in the local box, so its distance to c is not below the box distance:
-         * when dsq clears (2 soft + rmMax)^2 by a margin far above rounding, every one of those tests fails
-         * and none is evaluated.  (Cosmological softenings are a small fraction of a bucket: the exact tests
-         * below run for a handful of entries per node.) */
-        const double rs = 2.0 * src.soft;
-        const double rflag = __dadd_rn(rs, rmMax);
-        const double rflag2 = __dmul_rn(rflag, rflag);
-        if (dsq <= rflag2 * 1.0001) {
-          const double dx = __dsub_rn(mine.cx, cx), dy = __dsub_rn(mine.cy, cy), dz = __dsub_rn(mine.cz, cz);
-          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-          const double rr = __dadd_rn(rs, rm2);
-          if ((d2 <= __dmul_rn(rr, rr)) || (dsq <= __dmul_rn(rs, rs)))
-            open = dsq <= __dmul_rn(src.ropenMono, src.ropenMono) ? 1 : 0;
-          flagged = open == 0 && dsq <= rflag2;
-        }
+        const float cx = __uint_as_float(ra.x) + shiftTabF[(e.offsetID >> 22) & 7];
+        const float cy = __uint_as_float(ra.y) + shiftTabF[(e.offsetID >> 25) & 7];
+        const float cz = __uint_as_float(ra.z) + shiftTabF[(e.offsetID >> 28) & 7];
+        const float R2 = __uint_as_float(ra.w), tau = __uint_as_float(rb.x);
+        const float ax = lox - cx, bx = cx - hix, ay = loy - cy, by = cy - hiy, az = loz - cz, bz = cz - hiz;
+        const float dx = fmaxf(fmaxf(ax, bx), 0.0f), dy = fmaxf(fmaxf(ay, by), 0.0f), dz = fmaxf(fmaxf(az, bz), 0.0f);
+        const float q = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (fabsf(q - R2) <= fmaf(tau, q + R2, ftol.absTol)) {
+          exact = true; /* inside the error band of dsq <= ropen^2 */
+        } else if (q < R2) {
+          if (LEAF) {
+            open = 1;
+          } else { /* contained in the sphere?  (Space::contained: the farthest corner) */
+            const float wx = fmaxf(fabsf(ax), fabsf(bx)), wy = fmaxf(fabsf(ay), fabsf(by)), wz = fmaxf(fabsf(az), fabsf(bz));
+            const float sq = fmaf(wz, wz, fmaf(wy, wy, wx * wx));
+            if (fabsf(sq - R2) <= fmaf(tau, sq + R2, ftol.absTol)) exact = true;
+            else open = sq < R2 ? 1 : -1;
+          }
+        } else if (!(q > ftol.softGate)) {
+          exact = true; /* within reach of a softening test or of the maybe-softened flag */
+        } /* else: accepted, and no softening test can say otherwise */
+      }
+      if (exact) {
+        int fl = 0;
+        open = walk_test_double<LEAF>(t.rec, e.node, e.offsetID, wd, shiftTab, rmMax, &fl);
+        flagged = fl != 0;
       }
     }
     /* ListCompute::doWork with the LocalOpt table (Opt.h:86-128) */
@@ -430,7 +518,7 @@ __device__ __forceinline__ bool walk_node_fast(const WalkTree &t, const WalkPara
       int late = -1;
       const int i = head + lane;
       if (lane >= max(avail, 0) && i < tail) { eN = sring[i & kMask]; late = eN.node; }
-      stage(rows + (buf ^ 1) * (32 * 5), late);
+      stage(rows + (buf ^ 1) * (32 * kWalkRowF), late);
     }
     buf ^= 1;
   }
@@ -632,8 +720,14 @@ walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, Node
   const int totalWarps = (gridDim.x * blockDim.x) >> 5;
   extern __shared__ __align__(16) unsigned char walkSmem[];
   __shared__ double shiftTab[8];
-  if (threadIdx.x < 8) shiftTab[threadIdx.x] = __dmul_rn((double)((int)threadIdx.x - 3), p.period); /* walk_shifted_cm */
+  __shared__ float shiftTabF[8];
+  __shared__ double mineD[kWalkWarps][kWalkMineDoubles];
+  if (threadIdx.x < 8) {
+    shiftTab[threadIdx.x] = __dmul_rn((double)((int)threadIdx.x - 3), p.period); /* walk_shifted_cm */
+    shiftTabF[threadIdx.x] = (float)shiftTab[threadIdx.x];
+  }
   __syncthreads();
+  double *wd = mineD[threadIdx.x >> 5];
   unsigned char *wsm = walkSmem + (size_t)(threadIdx.x >> 5) * kWalkWarpSmem;
   uint4 *rows = reinterpret_cast<uint4 *>(wsm);
   WalkEntry *sring = reinterpret_cast<WalkEntry *>(wsm + kWalkRowBytes);
@@ -658,25 +752,31 @@ walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, Node
       continue;
     }
     target &= kWalkBucketMask;
-    const WalkNodeRec mine = t.rec[my];
-    const bool myIsBucket = mine.child0 < 0 && mine.child1 < 0;
-    double mylo[3], myhi[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { mylo[d] = t.boxlo[3 * (size_t)my + d]; myhi[d] = t.boxhi[3 * (size_t)my + d]; }
+    /* the local node in double goes to shared memory (walk_test_double, walk_node_general read it from there) */
+    __syncwarp();
+    if (lane < 3) { wd[lane] = t.boxlo[3 * (size_t)my + lane]; wd[3 + lane] = t.boxhi[3 * (size_t)my + lane]; }
+    const WalkNodeRecF mineF = t.recf[my];
+    if (lane == 0) {
+      const WalkNodeRec mine = t.rec[my];
+      wd[6] = mine.cx; wd[7] = mine.cy; wd[8] = mine.cz; wd[9] = mine.soft;
+    }
+    __syncwarp();
+    const bool myIsBucket = mineF.child0 < 0 && mineF.child1 < 0;
     const double rmMax = 2.0 * __longlong_as_double((long long)*t.softMaxBits);
     int nc = 0, nl = 0, nu = 0, myParts = 0, myFlagged = 0;
     int flC = 0, flL = 0, flU = 0;
     bool done = false;
     if (!generalOnly) {
       if (myIsBucket)
-        done = walk_node_fast<true>(t, p, pools, mine, mylo, myhi, target, par, lists, rmMax, shiftTab, rows, sring, scl, sund,
-                                    slp, cl, lp, und, lane, nc, nl, nu, flC, flL, flU, myParts, myFlagged);
+        done = walk_node_fast<true>(t, p, pools, wd, target, par, lists, rmMax, shiftTab, shiftTabF, rows, sring, scl, sund, slp, cl,
+                                    lp, und, lane, nc, nl, nu, flC, flL, flU, myParts, myFlagged);
       else
-        done = walk_node_fast<false>(t, p, pools, mine, mylo, myhi, target, par, lists, rmMax, shiftTab, rows, sring, scl, sund,
-                                     slp, cl, lp, und, lane, nc, nl, nu, flC, flL, flU, myParts, myFlagged);
+        done = walk_node_fast<false>(t, p, pools, wd, target, par, lists, rmMax, shiftTab, shiftTabF, rows, sring, scl, sund, slp, cl,
+                                     lp, und, lane, nc, nl, nu, flC, flL, flU, myParts, myFlagged);
     }
     if (!done) {
-      const WalkNodeCounts r = walk_node_general(t, p, pools, mine, mylo[0], mylo[1], mylo[2], myhi[0], myhi[1], myhi[2], target,
+      const WalkNodeRec mine = t.rec[my];
+      const WalkNodeCounts r = walk_node_general(t, p, pools, mine, wd[0], wd[1], wd[2], wd[3], wd[4], wd[5], target,
                                                  par, lists, rmMax, rows, sring, scl, sund, slp, chk, lane);
       nc = r.nc; nl = r.nl; nu = r.nu; myParts = r.parts; myFlagged = r.flagged;
     }

@@ -1352,7 +1352,7 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   t.rec = rec;
   /* 4 CTAs of 4 warps per SM: what the kernel's registers (113) and its 50 KB of shared memory
    * (the heads of the per-node lists) both allow; the walk is latency-bound */
-  const int walkCtas = sms * 4;
+  const int walkCtas = sms * CB200_WALK_MINB; /* resident CTAs per SM the level kernel is compiled for */
   {
     static CtaCache attrSet;
     int dev = 0;

@@ -39,8 +39,12 @@ constexpr int kWalkWarps = 4;           /* warps per CTA */
  * slice of the global scratch at the same index.  Sizes cover the typical node (host walk: ~110
  * accepted cells, ~45 undecided, ~12 buckets, ~300 appended checklist entries at the leaves). */
 constexpr int kWalkRingS = 512, kWalkClS = 256, kWalkUnS = 128, kWalkLpS = 64;
-constexpr int kWalkRowBytes = 2 * 32 * 5 * 16;                                   /* two buffers of 32 records, 80-byte pitch */
-constexpr int kWalkWarpSmem = kWalkRowBytes + 8 * (kWalkRingS + kWalkClS + kWalkUnS + 128 /* kWalkLpFast */);
+/* staged source records of a batch: the fast routine keeps two buffers of 32 float records at a 48-byte pitch, the
+ * general routine one buffer of 32 double records at an 80-byte pitch */
+constexpr int kWalkRowBytes = 2 * 32 * 48;
+static_assert(kWalkRowBytes >= 32 * 80, "the general routine's single buffer fits");
+constexpr int kWalkLpHead = 96;                                                  /* bucket-list head of the fast routine */
+constexpr int kWalkWarpSmem = kWalkRowBytes + 8 * (kWalkRingS + kWalkClS + kWalkUnS + kWalkLpHead);
 constexpr int kWalkSmemBytes = kWalkWarps * kWalkWarpSmem;
 constexpr int kWalkOffsetMask = 0x1ff << 22;
 constexpr int kWalkBucketMask = (1 << 22) - 1;
@@ -325,7 +329,7 @@ __device__ __forceinline__ double walk_box_dist2_lean(const double (&lo)[3], con
   return dsq;
 }
 
-constexpr int kWalkLpFast = 128; /* bucket-list head of the fast routine (the general one uses kWalkLpS of it) */
+constexpr int kWalkLpFast = kWalkLpHead; /* the general routine uses kWalkLpS of it */
 static_assert(kWalkLpFast >= kWalkLpS, "one shared-memory area serves both routines");
 constexpr int kWalkRowF = 3; /* uint4 per staged float record: 32 bytes + 16 of padding (48-byte pitch: LDS.128 conflict-free) */
 
@@ -607,14 +611,15 @@ __device__ __noinline__ WalkNodeCounts walk_node_general(const WalkTree &t, cons
     {
       uint4 *d = reinterpret_cast<uint4 *>(&src);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) d[k] = rows[buf * (32 * 5) + lane * 5 + k];
+      for (int k = 0; k < 4; ++k) d[k] = rows[lane * 5 + k];
     }
+    __syncwarp(); /* one buffer: every lane holds its record before the next batch's records are requested */
     const int iN = i + batch, oldTail = tail;
     const bool early = iN < oldTail;
     eN.node = -1;
     if (head + batch < oldTail) { /* warp-uniform */
       if (early) eN = fifo(iN);
-      stage(rows + (buf ^ 1) * (32 * 5), eN.node);
+      stage(rows, eN.node);
     }
     int open = 0;
     bool srcBucket = false;
@@ -675,7 +680,7 @@ __device__ __noinline__ WalkNodeCounts walk_node_general(const WalkTree &t, cons
     if (tail > oldTail && oldTail < head + 32) { /* warp-uniform: this batch appended entries of the next one */
       int late = -1;
       if (!early && iN < tail) { eN = fifo(iN); late = eN.node; }
-      stage(rows + (buf ^ 1) * (32 * 5), late);
+      stage(rows, late);
     }
     buf ^= 1;
   }
@@ -709,7 +714,7 @@ __global__ void walk_level_ranges_kernel(WalkTree t, WalkLevels lv, int bucketLo
 /* One level of the local tree: nodes [range->x, range->x + range->y) (walk_level_ranges_kernel).  scratch: per
  * warp 4 x kWalkCap entries (checklist, clist, lplist, undlist) for walk_node_general. */
 #ifndef CB200_WALK_MINB
-#define CB200_WALK_MINB 4
+#define CB200_WALK_MINB 5
 #endif
 __global__ void __launch_bounds__(kWalkWarps * 32, CB200_WALK_MINB)
 walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, NodeLists *__restrict__ lists, WalkPools pools,

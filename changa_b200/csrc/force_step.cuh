@@ -578,10 +578,13 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
                                                              st->d_letCover, nCover);
       cudaChk(cudaPeekAtLastError());
       const int lo = tr.levelStart[Lb], cnt = tr.levelStart[Lb + 1] - lo;
-      const double geom = 2.0 / sqrt(3.0) / cfg.theta;
+      /* CB200_LET_RADIUS_SCALE (tests): shrinks the halo radius below its bound, so that the walk DOES leave the
+       * built part and the fallback is exercised */
+      static const double radiusScale = getenv("CB200_LET_RADIUS_SCALE") ? atof(getenv("CB200_LET_RADIUS_SCALE")) : 1.0;
+      const double geom = radiusScale * 2.0 / sqrt(3.0) / cfg.theta;
       const int images = (cfg.nReplicas || cfg.ewald) ? (cfg.nReplicas > 0 ? cfg.nReplicas : 1) : 0;
       let_block_flags_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(tr.d_bucketFirst, tr.d_bucketCount, tr.d_boxlo, tr.d_boxhi, lo, cnt, b0,
-                                                              b1, st->d_letCover, nCover, geom > 1.0 ? geom : 1.0,
+                                                              b1, st->d_letCover, nCover, radiusScale < 1.0 ? geom : (geom > 1.0 ? geom : 1.0),
                                                               st->d_letScalars, cfg.period, images, st->d_letFlag);
       cudaChk(cudaPeekAtLastError());
       for (int l = Lb; l + 1 < tr.numLevels; ++l) {

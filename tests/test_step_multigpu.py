@@ -62,6 +62,8 @@ for cost in (0, 1):
     st.set_particles(pos, mass, soft)
     for it in range(2 + cost):        # the cost rule needs one step to measure
         res = st.run()
+        if cost == 0 and it == 0:
+            np.savez(os.path.join(outdir, f"rank{{rank}}_first.npz"), let=np.array([res.letBlockLevel, res.letFallback]))
     np.savez(os.path.join(outdir, f"rank{{rank}}_cost{{cost}}.npz"), idx=st.idx.array[:res.rows].copy(),
              rows=st.out.array[:res.rows].copy(), range=np.array([res.bucketLo, res.bucketHi, res.partLo, res.partHi]),
              cost=res.cost, pairs=np.array([res.pcPairs, res.ppPairs]), let=np.array([res.letBlockLevel, res.letFallback]))
@@ -75,7 +77,7 @@ print("rank", rank, "ok")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("let_blocks", [0, 64])
+@pytest.mark.parametrize("let_blocks", [0, 64, -64])
 def test_two_ranks_over_nccl_equal_the_single_gpu_step(tmp_path, let_blocks, monkeypatch):
     """let_blocks = 64: the locally essential moment build (csrc/let_kernels.cuh) is switched on for this small box
     (block level = first level with 64 x world nodes; by default a box needs 32768 x world): every rank builds only
@@ -85,7 +87,9 @@ def test_two_ranks_over_nccl_equal_the_single_gpu_step(tmp_path, let_blocks, mon
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     if let_blocks:
-        monkeypatch.setenv("CB200_LET_BLOCKS_PER_RANK", str(let_blocks))
+        monkeypatch.setenv("CB200_LET_BLOCKS_PER_RANK", str(abs(let_blocks)))
+        if let_blocks < 0:  # a halo far too thin: the walk must notice, fall back to the full build and still be exact
+            monkeypatch.setenv("CB200_LET_RADIUS_SCALE", "0.02")
     else:
         monkeypatch.setenv("CB200_LET", "0")
     from changa_b200.hostcuda import HostCUDA
@@ -116,8 +120,11 @@ def test_two_ranks_over_nccl_equal_the_single_gpu_step(tmp_path, let_blocks, mon
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))       # bit for bit, every particle once
         for k in range(2):
             level, fallback = (int(x) for x in r[k]["let"])
-            assert fallback == 0
-            assert (level >= 0) == bool(let_blocks), (level, let_blocks)
+            if let_blocks >= 0:
+                assert fallback == 0
+                assert (level >= 0) == bool(let_blocks), (level, let_blocks)
+        if let_blocks < 0:  # the first step fell back (both ranks together); later steps build everything
+            assert all(int(np.load(tmp_path / f"rank{k}_first.npz")["let"][1]) == 1 for k in range(2))
         assert tuple(r[0]["pairs"] + r[1]["pairs"]) == pairs1                    # same work, split not duplicated
         if cost:  # the measured costs of the two ranks are closer than with equal particle counts
             c = np.array([float(r[0]["cost"]), float(r[1]["cost"])])

@@ -74,7 +74,10 @@ def measured_peaks():
             pass
     out["pc_traffic"], out["pc_traffic_source"] = None, None
     import glob
-    caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_ncu_cell_list_x2_256.json")))
+    # the latest ncu capture of the p-c kernel in the 256^3 step (session tags sort as r02a < ... < r02z < r02aa < ...)
+    caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_ncu_cell_list_x2_256.json")) +
+                  glob.glob(os.path.join(ROOT, "profiles", "r02*_ncu_pc_256.json")),
+                  key=lambda f: (len(os.path.basename(f).split("_")[0]), os.path.basename(f)))
     if caps:
         try:
             out["pc_traffic"] = float(json.load(open(caps[-1]))["dram_bytes"])

@@ -1350,8 +1350,8 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   g_launches.fetch_add(1);
   g_launches.fetch_add(1);
   t.rec = rec;
-  /* 4 CTAs of 4 warps per SM: what the kernel's registers (113) and its 50 KB of shared memory
-   * (the heads of the per-node lists) both allow; the walk is latency-bound */
+  /* CB200_WALK_MINB (5) CTAs of 4 warps per SM: what the kernel's 96 registers and its 44 KB of shared memory
+   * (the heads of the per-node lists) both allow; the walk is latency-bound and wants the warps */
   const int walkCtas = sms * CB200_WALK_MINB; /* resident CTAs per SM the level kernel is compiled for */
   {
     static CtaCache attrSet;

@@ -23,7 +23,9 @@
  *                       list) and then particle buckets expanded per particle
  *                       (GenericList<ILPart>::serialize, Compute.cpp:1174-1187).
  *
- * All geometry in double, like the host walk (gravity.h:251-260, 652-723).
+ * Every opening decision is the double-precision one of the host walk (gravity.h:251-260,
+ * 652-723): walk_node_fast evaluates a test in single precision first and accepts the result
+ * only outside a rigorous error band (WalkNodeRecF); inside it the test is repeated in double.
  */
 #ifndef CB200_WALK_KERNELS_CUH
 #define CB200_WALK_KERNELS_CUH

@@ -6,7 +6,7 @@ The reference steps particles on individual power-of-two rungs (dDelta 0.1, dEta
 particle takes the same step dDelta / 2^k, which is the same integrator on its finest rung.
 
   python tools/teststep_energy.py --engine oracle --div 16        CPU: host tree + walk, oracle forces
-  python tools/teststep_energy.py --engine gpu --div 16           B200: RawParticleStep (tree, lists, forces on the device)
+  python tools/teststep_energy.py --engine gpu --div 16           B200: cb200_step_run (tree, moments, lists, forces on the device)
 
 Velocities come from the reference's file when it is present, else from tests/golden/king_velocities.npz."""
 import argparse, json, os, struct, sys, time
@@ -59,14 +59,14 @@ class GpuEngine:
         self.st = None
 
     def forces(self, pos, mass, soft):
-        from changa_b200.device_step import RawParticleStep
+        from changa_b200.step import NativeStep
         if self.st is None:  # one step object for the whole run; the root box leaves room for the drift
             ext = float(np.abs(pos).max()) * 1.5
-            self.st = RawParticleStep(self.hc, pos, mass, soft, theta=0.7, n_replicas=0, period=1.0, ewald=None,
-                                      root_lo=(-ext,) * 3, root_hi=(ext,) * 3)
-        else:
-            self.st.update_positions(pos)
-        return np.asarray(self.st.run(), dtype=np.float64).copy()
+            self.st = NativeStep(self.hc, len(pos), theta=0.7, n_replicas=0, period=1.0, ewald=None,
+                                 root_lo=(-ext,) * 3, root_hi=(ext,) * 3)
+        self.st.set_particles(pos, mass, soft)
+        self.st.run()  # cb200_step_run: tree, moments, lists and forces on the device, rows in the caller's order
+        return np.asarray(self.st.out.array[: len(pos)], dtype=np.float64).copy()
 
 
 def energy(mass, vel, f):

@@ -699,6 +699,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   if (st->letLevel >= 0) {
     extras.built = st->d_letFlag;
     extras.builtAlways = tr.levelStart[st->letLevel + 1]; /* every node down to the block level has a record */
+    extras.markEnd = tr.levelStart[st->letLevel + 2 <= tr.numLevels ? st->letLevel + 2 : tr.numLevels];
     extras.reduceSoftMax = [&](unsigned long long *d_bits, cudaStream_t ws) {
       /* the largest node softening over the whole tree (a non-negative double orders like its bit pattern): every
        * node is built by the rank that owns it, so the maximum over the ranks is the single-GPU value */

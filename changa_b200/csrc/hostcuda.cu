@@ -1268,6 +1268,7 @@ struct MinOp {
 struct WalkExtras {
   const unsigned char *built = nullptr;
   int builtAlways = 0;
+  int markEnd = 0; /* end of the level below the block level: unbuilt nodes in [builtAlways, markEnd) carry the mark */
   std::function<void(unsigned long long *d_softMaxBits, cudaStream_t)> reduceSoftMax;
 };
 static thread_local const WalkExtras *tl_walkExtras = nullptr;
@@ -1340,7 +1341,8 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   walk_pack_nodes_kernel<<<(numNodes + 255) / 256, 256, 0, s>>>(t, p.theta, p.thetaMono, p.period, rec, recf,
                                                                 (unsigned long long *)(ctl + 128),
                                                                 extras ? extras->built : nullptr,
-                                                                extras ? extras->builtAlways : 0);
+                                                                extras ? extras->builtAlways : 0,
+                                                                extras ? extras->markEnd : 0);
   cudaChk(cudaPeekAtLastError());
   if (extras && extras->reduceSoftMax) extras->reduceSoftMax((unsigned long long *)(ctl + 128), s);
   t.recf = recf;

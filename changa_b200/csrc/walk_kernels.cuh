@@ -125,7 +125,10 @@ __global__ void walk_float_tol_kernel(WalkTree t, double period, WalkFloatTol *_
 }
 __global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMono, double period, WalkNodeRec *__restrict__ out,
                                        WalkNodeRecF *__restrict__ outf, unsigned long long *softMaxBits,
-                                       const unsigned char *__restrict__ built, int builtAlways) {
+                                       const unsigned char *__restrict__ built, int builtAlways, int markEnd) {
+  /* markEnd: nodes in [builtAlways, markEnd) -- the level right below the block level -- get the "not built"
+   * mark when they are not built; deeper unbuilt nodes get nothing: a walk can only reach them through one of
+   * those marked records, whose child links are empty */
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool have = i < t.numNodes && (!built || i < builtAlways || built[i]);
   double soft = 0.0;
@@ -140,6 +143,7 @@ __global__ void walk_pack_nodes_kernel(WalkTree t, double theta, double thetaMon
   if ((threadIdx.x & 31) == 0) atomicMax(softMaxBits, b);
   if (i >= t.numNodes) return;
   if (!have) {
+    if (i >= markEnd) return;
     WalkNodeRec r;
     r.cx = r.cy = r.cz = r.ropen = r.soft = r.ropenMono = 0.0;
     r.child0 = r.child1 = -1; r.first = -1; r.last = -2;

@@ -1322,9 +1322,12 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
                                65536ull + 4096ull * (unsigned long long)numLevels;
   if (visited > (unsigned long long)numNodes) visited = (unsigned long long)numNodes;
   WalkPools pools;
-  pools.capC = visited * 256 + (1u << 16);
-  pools.capU = visited * 128 + (1u << 16);
-  pools.capL = visited * 64 + (1u << 16);
+  /* + what the warps' last chunks of every level may leave unused (walk_level_kernel reserves in chunks) */
+  const unsigned long long chunkSlack = (unsigned long long)sms * CB200_WALK_MINB * kWalkWarps * 4096ull * 8ull +
+                                        (unsigned long long)numLevels * 4096ull * 64ull;
+  pools.capC = visited * 256 + (1u << 16) + chunkSlack;
+  pools.capU = visited * 128 + (1u << 16) + chunkSlack / 4;
+  pools.capL = visited * 64 + (1u << 16) + chunkSlack / 2;
   pools.clist = (WalkEntry *)pool_alloc(pools.capC * sizeof(WalkEntry), s);
   pools.lplist = (WalkEntry *)pool_alloc(pools.capL * sizeof(WalkEntry), s);
   pools.undlist = (WalkEntry *)pool_alloc(pools.capU * sizeof(WalkEntry), s);
@@ -1383,8 +1386,12 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
     if (nAll <= 0) continue;
     const int n = (int)((double)nAll * rangeFrac) + 64 < nAll ? (int)((double)nAll * rangeFrac) + 64 : nAll;
     const int need = (n + kWalkWarps - 1) / kWalkWarps;
-    walk_level_kernel<<<need < walkCtas ? need : walkCtas, kWalkWarps * 32, kWalkSmemBytes, s>>>(t, p, levelRange + lvl, lists, pools,
-                                                                                                scratch, generalOnly);
+    const int grid = need < walkCtas ? need : walkCtas;
+    /* pool chunk of a warp: ~128 cell entries per node it will see, between 256 and 4096 */
+    const long long perWarp = ((long long)n + (long long)grid * kWalkWarps - 1) / ((long long)grid * kWalkWarps);
+    const int chunk = (int)(perWarp * 128 < 256 ? 256 : (perWarp * 128 > 4096 ? 4096 : perWarp * 128));
+    walk_level_kernel<<<grid, kWalkWarps * 32, kWalkSmemBytes, s>>>(t, p, levelRange + lvl, lists, pools, scratch, generalOnly,
+                                                                  chunk);
     cudaChk(cudaPeekAtLastError());
     g_launches.fetch_add(1);
   }

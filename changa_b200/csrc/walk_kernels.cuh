@@ -724,7 +724,9 @@ __global__ void walk_level_ranges_kernel(WalkTree t, WalkLevels lv, int bucketLo
 #endif
 __global__ void __launch_bounds__(kWalkWarps * 32, CB200_WALK_MINB)
 walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, NodeLists *__restrict__ lists, WalkPools pools,
-                  WalkEntry *__restrict__ scratch, int generalOnly) {
+                  WalkEntry *__restrict__ scratch, int generalOnly, int chunk) {
+  /* chunk: entries a warp reserves from the cell pool at a time (half of it from the bucket pool, a quarter from
+   * the undecided pool): the host scales it with the nodes a warp will see on this level */
   const int lo = range->x, n = range->y;
   const int lane = threadIdx.x & 31;
   const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -733,6 +735,9 @@ walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, Node
   __shared__ double shiftTab[8];
   __shared__ float shiftTabF[8];
   __shared__ double mineD[kWalkWarps][kWalkMineDoubles];
+  __shared__ unsigned long long poolCursor[kWalkWarps][6]; /* {cursor, end} of the warp's chunk of the three pools */
+  if (threadIdx.x < kWalkWarps * 6) poolCursor[threadIdx.x / 6][threadIdx.x % 6] = 0ull;
+  unsigned long long *wpool = poolCursor[threadIdx.x >> 5];
   if (threadIdx.x < 8) {
     shiftTab[threadIdx.x] = __dmul_rn((double)((int)threadIdx.x - 3), p.period); /* walk_shifted_cm */
     shiftTabF[threadIdx.x] = (float)shiftTab[threadIdx.x];
@@ -746,6 +751,7 @@ walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, Node
   WalkEntry *chk = scratch + (size_t)warpGlobal * 4 * kWalkCap;
   WalkEntry *cl = chk + kWalkCap, *lp = cl + kWalkCap, *und = lp + kWalkCap;
 
+  const double rmMax = 2.0 * __longlong_as_double((long long)*t.softMaxBits);
   for (int w = warpGlobal; w < n; w += totalWarps) {
     const int my = lo + w;
     NodeLists out = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -773,7 +779,6 @@ walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, Node
     }
     __syncwarp();
     const bool myIsBucket = mineF.child0 < 0 && mineF.child1 < 0;
-    const double rmMax = 2.0 * __longlong_as_double((long long)*t.softMaxBits);
     int nc = 0, nl = 0, nu = 0, myParts = 0, myFlagged = 0;
     int flC = 0, flL = 0, flU = 0;
     bool done = false;
@@ -792,13 +797,31 @@ walk_level_kernel(WalkTree t, WalkParams p, const int2 *__restrict__ range, Node
       nc = r.nc; nl = r.nl; nu = r.nu; myParts = r.parts; myFlagged = r.flagged;
     }
 
-    /* exact-size slices of the pools */
+    /* Exact-size slices of the pools, cut from CHUNKS the warp reserves: three atomics per node were a full
+     * round trip at the end of every node (5 % of the leaf level's stall samples); a chunk lasts for dozens of nodes
+     * and its cursor lives in shared memory.  What is left of a chunk when the launch ends is lost (the host sizes
+     * the pools for it). */
     unsigned long long oc = 0, ol = 0, ou = 0;
     if (lane == 0) {
-      oc = atomicAdd(pools.used + 0, (unsigned long long)nc);
-      ol = atomicAdd(pools.used + 1, (unsigned long long)nl);
-      ou = atomicAdd(pools.used + 2, (unsigned long long)nu);
-      if (oc + nc > pools.capC || ol + nl > pools.capL || ou + nu > pools.capU) { *pools.error = 2; nc = nl = nu = 0; }
+      const int need[3] = {nc, nl, nu};
+      const unsigned long long cap[3] = {pools.capC, pools.capL, pools.capU};
+      unsigned long long off[3];
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        unsigned long long cur = wpool[2 * k], end = wpool[2 * k + 1];
+        if (cur + (unsigned long long)need[k] > end) {
+          const unsigned long long want = (unsigned long long)(need[k] > (chunk >> k) ? need[k] : (chunk >> k));
+          cur = atomicAdd(pools.used + k, want);
+          end = cur + want;
+          if (end > cap[k]) ok = false;
+        }
+        off[k] = cur;
+        wpool[2 * k] = cur + (unsigned long long)need[k];
+        wpool[2 * k + 1] = end;
+      }
+      oc = off[0]; ol = off[1]; ou = off[2];
+      if (!ok) { *pools.error = 2; nc = nl = nu = 0; }
     }
     oc = __shfl_sync(0xffffffffu, oc, 0); ol = __shfl_sync(0xffffffffu, ol, 0); ou = __shfl_sync(0xffffffffu, ou, 0);
     nc = __shfl_sync(0xffffffffu, nc, 0); nl = __shfl_sync(0xffffffffu, nl, 0); nu = __shfl_sync(0xffffffffu, nu, 0);

@@ -194,6 +194,10 @@ struct cb200_step {
   cb200_tree tree;
   cb200_lists lists;
   bool haveTree = false, haveLists = false;
+  /* sizes learned from the last step: node arrays (tree build) and the walk's pools, instead of their worst cases */
+  double treeCapFactor = 0.0;              /* 0: not known yet */
+  unsigned long long poolHint[3] = {0, 0, 0};
+  long long stepsRun = 0;
   /* locally essential moment build (let_kernels.cuh) */
   bool letOff = false;
   unsigned char *d_letFlag = nullptr;
@@ -515,7 +519,24 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
     for (int j = 0; j < S; ++j)
       fine[r * S + j] = targets[r] + (int)(((long long)(targets[r + 1] - targets[r]) * j) / S);
   fine[cutWorld * S] = targets[cutWorld];
-  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, fine, cutWorld * S + 1, cuts, s, preKeys, preOrder);
+  /* Node arrays: 1.5 n nodes can never be exceeded by a tree of particles at distinct places, but a real tree has
+   * about n / 4; the first step of a step object asks for 0.75 n, later ones for 1.3 x what the last tree had.  The
+   * build reports an overflow; it is then repeated with the full size (rare: every rank sees the same tree, so all
+   * ranks repeat together; the repeat sorts the whole box itself). */
+  static const double capEnv = getenv("CB200_TREE_CAP_FACTOR") ? atof(getenv("CB200_TREE_CAP_FACTOR")) : 0.0;
+  double capFactor = st->treeCapFactor > 0.0 ? st->treeCapFactor : 0.75;
+  if (capEnv > 0.0 && st->stepsRun == 0) capFactor = capEnv; /* tests: force the overflow path on the first step */
+  build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, fine, cutWorld * S + 1, cuts, s, preKeys, preOrder,
+                  capFactor);
+  if (st->tree.error == 1 && capFactor < 1.5) {
+    cb200_tree_free(&st->tree, s);
+    build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, fine, cutWorld * S + 1, cuts, s, nullptr, nullptr, 1.5);
+    res->treeRebuilt = 1;
+  }
+  if (!st->tree.error) {
+    const double f = 1.3 * (double)st->tree.numNodes / (double)n + 0.01;
+    st->treeCapFactor = f < 1.5 ? f : 1.5;
+  }
   st->haveTree = true;
   cb200_tree &tr = st->tree;
   nvtx_pop();
@@ -696,6 +717,9 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   /* interaction lists of my buckets */
   nvtx_push("CUDA_SER_LIST");
   WalkExtras extras;
+  static const double hintScale = getenv("CB200_POOL_HINT_SCALE") ? atof(getenv("CB200_POOL_HINT_SCALE")) : 1.0; /* tests */
+  for (int k = 0; k < 3; ++k) extras.poolHint[k] = (unsigned long long)((double)st->poolHint[k] * hintScale);
+  tl_walkExtras = &extras;
   if (st->letLevel >= 0) {
     extras.built = st->d_letFlag;
     extras.builtAlways = tr.levelStart[st->letLevel + 1]; /* every node down to the block level has a record */
@@ -705,32 +729,52 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
        * node is built by the rank that owns it, so the maximum over the ranks is the single-GPU value */
       ncclChk(nccl_api()->AllReduce(d_bits, d_bits, 1, ncclUint64, ncclMax, st->comm->comm, ws));
     };
-    tl_walkExtras = &extras;
   }
   cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
                            tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
                            cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
-  tl_walkExtras = nullptr;
-  /* a walk that met a node outside the part this rank built (let_kernels.cuh: not expected) is repeated on the
-   * full build, and the locally essential build stays off for this step object -- on every rank, or the next
-   * step's exchange would wait for a rank that no longer takes part */
-  if (st->letLevel >= 0) {
-    double bad = st->lists.error == kWalkNotBuilt ? 1.0 : 0.0;
-    cb200_comm_allreduce_f64(st->comm, &bad, 1, 1, s);
-    if (bad > 0.0) {
-      fprintf(stderr, "changa_b200: rank %d: the walk left the locally essential tree (block level %d); full moment build from here on\n",
-              rank, st->letLevel);
-      st->letOff = true;
-      st->letLevel = -1;
-      res->letFallback = 1;
-      cb200_lists_free(&st->lists, s);
-      build_moments_impl(tr.d_pos, tr.d_mass, tr.d_soft, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last, tr.d_geolo,
-                         tr.d_geohi, tr.d_boxlo, tr.d_boxhi, tr.levelStart, tr.numLevels, nn, nullptr, st->d_mom64, st->d_pkMom, s);
-      cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
-                               tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
-                               cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
-    }
+  /* Two things can make a walk worth repeating, and with several ranks both are decided TOGETHER (the walk of a
+   * locally essential step contains a collective, and the next step's exchange needs every rank): the pools,
+   * sized from the last step, were too small on some rank -> once more with worst-case sizes; the walk met a node
+   * outside the part a rank built (let_kernels.cuh: not expected) -> moments and walk once more on the full build,
+   * and the locally essential build stays off for this step object. */
+  auto agree2 = [&](bool a, bool b, bool &ra, bool &rb) { /* one blocking all-reduce (max) of two flags */
+    double v[2] = {a ? 1.0 : 0.0, b ? 1.0 : 0.0};
+    if (world > 1) cb200_comm_allreduce_f64(st->comm, v, 2, 1, s);
+    ra = v[0] > 0.0; rb = v[1] > 0.0;
+  };
+  auto walk = [&]() {
+    cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
+                             tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
+                             cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
+  };
+  const bool hinted = st->poolHint[0] != 0;
+  bool small = hinted && st->lists.error == 2, outside = st->letLevel >= 0 && st->lists.error == kWalkNotBuilt;
+  if (world > 1 && (hinted || st->letLevel >= 0)) agree2(small, outside, small, outside);
+  if (small) {
+    cb200_lists_free(&st->lists, s);
+    for (int k = 0; k < 3; ++k) extras.poolHint[k] = 0;
+    walk();
+    res->walkRepeated = 1;
+    outside = st->letLevel >= 0 && st->lists.error == kWalkNotBuilt;
+    if (world > 1 && st->letLevel >= 0) { bool dummy = false; agree2(outside, false, outside, dummy); }
   }
+  for (int k = 0; k < 3; ++k) st->poolHint[k] = extras.poolHint[k];
+  if (outside) {
+    fprintf(stderr, "changa_b200: rank %d: the walk left the locally essential tree (block level %d); full moment build from here on\n",
+            rank, st->letLevel);
+    st->letOff = true;
+    st->letLevel = -1;
+    res->letFallback = 1;
+    cb200_lists_free(&st->lists, s);
+    build_moments_impl(tr.d_pos, tr.d_mass, tr.d_soft, tr.d_child0, tr.d_child1, tr.d_first, tr.d_last, tr.d_geolo,
+                       tr.d_geohi, tr.d_boxlo, tr.d_boxhi, tr.levelStart, tr.numLevels, nn, nullptr, st->d_mom64, st->d_pkMom, s);
+    extras.built = nullptr; extras.reduceSoftMax = nullptr;
+    for (int k = 0; k < 3; ++k) extras.poolHint[k] = 0; /* the full build visits no more nodes, but be generous */
+    walk();
+    for (int k = 0; k < 3; ++k) st->poolHint[k] = extras.poolHint[k];
+  }
+  tl_walkExtras = nullptr;
   res->letBlockLevel = st->letLevel;
   st->haveLists = true;
   cb200_lists &li = st->lists;
@@ -826,6 +870,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   }
   cudaChk(cudaEventElapsedTime(&res->ms[PH_TOTAL], st->ev[0], st->ev[PH_FINISH + 1]));
 
+  st->stepsRun += 1;
   /* cost feedback for the next step's cuts: every rank learns every rank's cost and range */
   if (world > 1 && cfg.costCuts && !multistep) {
     std::vector<double> v(2 * (size_t)world, 0.0);

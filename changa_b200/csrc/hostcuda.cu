@@ -1125,7 +1125,7 @@ static int merge_sorted_runs(unsigned long long *keys[2], int *idx[2], std::vect
  * step sorts every rank's slice on its own GPU and merges the runs); both pool blocks of stream s, owned from here */
 static void build_tree_impl(const TreeInput &in, int n, int maxBucket, const double *rootlo, const double *roothi,
                             cb200_tree *out, const int *h_targets, int nCuts, int *h_cuts, cudaStream_t s,
-                            unsigned long long *preKeys = nullptr, int *preOrder = nullptr) {
+                            unsigned long long *preKeys = nullptr, int *preOrder = nullptr, double capFactor = 1.5) {
   memset(out, 0, sizeof *out);
   out->numParticles = n;
   if (n <= 0) return;
@@ -1151,7 +1151,7 @@ static void build_tree_impl(const TreeInput &in, int n, int maxBucket, const dou
 
   /* nodes, level by level inside one cooperative kernel; capacity: a node holds at least one
    * particle, chains of single children are the only way past ~n/3 nodes */
-  const int cap = n + n / 2 + 4096;
+  const int cap = (int)((double)n * capFactor) + 4096; /* the kernel reports an overflow (error 1): the caller may retry with more */
   TreeArrays t;
   t.child0 = out->d_child0 = (int *)pool_alloc((size_t)cap * 4, s);
   t.child1 = out->d_child1 = (int *)pool_alloc((size_t)cap * 4, s);
@@ -1270,6 +1270,9 @@ struct WalkExtras {
   int builtAlways = 0;
   int markEnd = 0; /* end of the level below the block level: unbuilt nodes in [builtAlways, markEnd) carry the mark */
   std::function<void(unsigned long long *d_softMaxBits, cudaStream_t)> reduceSoftMax;
+  /* in: entries of the three pools (cells, buckets, undecided) the caller expects, 0 = size from the tree;
+   * out: entries the walk reserved.  A step sizes the pools of the next one from these */
+  mutable unsigned long long poolHint[3] = {0, 0, 0};
 };
 static thread_local const WalkExtras *tl_walkExtras = nullptr;
 void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const int *h_levelStart,
@@ -1328,6 +1331,14 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   pools.capC = visited * 256 + (1u << 16) + chunkSlack;
   pools.capU = visited * 128 + (1u << 16) + chunkSlack / 4;
   pools.capL = visited * 64 + (1u << 16) + chunkSlack / 2;
+  if (tl_walkExtras && tl_walkExtras->poolHint[0]) { /* last step's use + 30 %: a third of the worst-case sizes */
+    const unsigned long long *hint = tl_walkExtras->poolHint;
+    const unsigned long long c = hint[0] + hint[0] * 3 / 10 + (1u << 16), l = hint[1] + hint[1] * 3 / 10 + (1u << 16),
+                             u = hint[2] + hint[2] * 3 / 10 + (1u << 16);
+    if (c < pools.capC) pools.capC = c;
+    if (l < pools.capL) pools.capL = l;
+    if (u < pools.capU) pools.capU = u;
+  }
   pools.clist = (WalkEntry *)pool_alloc(pools.capC * sizeof(WalkEntry), s);
   pools.lplist = (WalkEntry *)pool_alloc(pools.capL * sizeof(WalkEntry), s);
   pools.undlist = (WalkEntry *)pool_alloc(pools.capU * sizeof(WalkEntry), s);
@@ -1426,9 +1437,11 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   cudaChk(cudaMemcpyAsync(&totals[1], out->d_softMarkers + numBuckets, sizeof(int), cudaMemcpyDeviceToHost, s));
   cudaChk(cudaMemcpyAsync(&totals[2], out->d_partMarkers + numBuckets, sizeof(int), cudaMemcpyDeviceToHost, s));
   cudaChk(cudaMemcpyAsync(&totals[3], pools.error, sizeof(int), cudaMemcpyDeviceToHost, s));
-  unsigned long long wide[3] = {0, 0, 0};
+  unsigned long long wide[3] = {0, 0, 0}, usedPool[3] = {0, 0, 0};
   cudaChk(cudaMemcpyAsync(wide, ctl + 160, sizeof wide, cudaMemcpyDeviceToHost, s));
+  cudaChk(cudaMemcpyAsync(usedPool, ctl, sizeof usedPool, cudaMemcpyDeviceToHost, s));
   cudaChk(cudaStreamSynchronize(s)); /* the list sizes decide the allocations below */
+  if (tl_walkExtras) for (int k = 0; k < 3; ++k) tl_walkExtras->poolHint[k] = usedPool[k];
 #ifdef CB200_WALK_STATS
   { int st[4]; cudaChk(cudaMemcpy(st, ctl + 192, sizeof st, cudaMemcpyDeviceToHost));
     fprintf(stderr, "walk stats: fast routine gave up on clist %d, buckets %d, undecided %d, ring %d of %d nodes\n", st[0], st[1], st[2], st[3], numNodes); }

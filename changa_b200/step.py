@@ -29,7 +29,8 @@ class StepResult(C.Structure):
                 ("nCell", C.c_longlong), ("nSoft", C.c_longlong), ("nPart", C.c_longlong),
                 ("pcPairs", C.c_longlong), ("ppPairs", C.c_longlong),
                 ("h2dBytes", C.c_longlong), ("d2hBytes", C.c_longlong), ("cost", C.c_double),
-                ("ms", C.c_float * len(PHASES)), ("letBlockLevel", C.c_int), ("letFallback", C.c_int)]
+                ("ms", C.c_float * len(PHASES)), ("letBlockLevel", C.c_int), ("letFallback", C.c_int),
+                ("treeRebuilt", C.c_int), ("walkRepeated", C.c_int)]
 
 
 def _bind(L):

@@ -337,6 +337,8 @@ typedef struct cb200_step_result {
   int letBlockLevel;                      /* multi-GPU: tree level below which this rank built only the subtrees near its
                                              own buckets (locally essential moment build); -1: everything built */
   int letFallback;                        /* 1: this step's walk left that part and was repeated on the full build */
+  int treeRebuilt, walkRepeated;          /* 1: the node arrays / the walk's pools, sized from the last step, were too small
+                                             and the phase was repeated with worst-case sizes */
 } cb200_step_result;
 
 /* the costCuts rule on the host: last step's boundaries prevCut[0..world] (particle indices) and the cost

@@ -635,6 +635,42 @@ def test_native_step_sfc_order_output_in_slabs(hc):
     assert np.array_equal(dev.view(np.uint32), rows.view(np.uint32))
 
 
+def test_native_step_resizes_after_an_overflow(hc):
+    """cb200_step_run sizes the node arrays and the walk's pools from the last step instead of their worst cases.  A
+    first step forced to start with node arrays far too small (CB200_TREE_CAP_FACTOR, read once per process: this test
+    sets it through a subprocess) reports treeRebuilt and still gives the right answer; pools scaled to a third of the
+    last step's use (CB200_POOL_HINT_SCALE) make the second step repeat its walk"""
+    import subprocess, sys, os, json
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, %r)
+from changa_b200.hostcuda import HostCUDA
+from changa_b200.step import NativeStep
+from changa_b200.workloads import clustered_box
+hc = HostCUDA(double=False, device=0)
+pos, mass, soft = clustered_box(50000, seed=11)
+st = NativeStep(hc, len(pos), theta=0.7, n_replicas=1, period=1.0, ewald={})
+st.set_particles(pos, mass, soft)
+r1 = st.run(); a = st.out.array[:len(pos)].copy(); f1 = (int(r1.treeRebuilt), int(r1.walkRepeated))
+r2 = st.run(); b = st.out.array[:len(pos)].copy(); f2 = (int(r2.treeRebuilt), int(r2.walkRepeated))
+st.free()
+print(json.dumps({"f1": f1, "f2": f2, "same": bool(np.array_equal(a.view(np.uint32), b.view(np.uint32))),
+                  "sum": float(np.abs(a[:, :3]).sum()), "pairs": [int(r2.pcPairs), int(r2.ppPairs)]}))
+""" % ROOT
+    def run(env):
+        e = dict(os.environ); e.update(env)
+        out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    plain = run({})
+    forced = run({"CB200_TREE_CAP_FACTOR": "0.05", "CB200_POOL_HINT_SCALE": "0.3"})
+    assert plain["f1"] == [0, 0] and plain["f2"] == [0, 0] and plain["same"]
+    assert forced["f1"] == [1, 0] and forced["f2"][1] == 1 and forced["same"]
+    assert forced["pairs"] == plain["pairs"] and forced["sum"] == plain["sum"]
+
+
 def test_clustered_box_device_path(hc):
     """SURVEY config C4's recipe at a testable size (Plummer halos on a uniform background: 40-level
     tree, softened cells, long lists): device tree == host tree, device lists == host lists, forces

@@ -871,6 +871,8 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   cudaChk(cudaEventElapsedTime(&res->ms[PH_TOTAL], st->ev[0], st->ev[PH_FINISH + 1]));
 
   st->stepsRun += 1;
+  /* the second step ran with sizes learned from the first: what the first one reserved beyond that goes back */
+  if (st->stepsRun == 2) pool_trim_device();
   /* cost feedback for the next step's cuts: every rank learns every rank's cost and range */
   if (world > 1 && cfg.costCuts && !multistep) {
     std::vector<double> v(2 * (size_t)world, 0.0);

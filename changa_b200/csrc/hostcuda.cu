@@ -162,6 +162,29 @@ static void block_cache_flush_locked(int dev, cudaStream_t only, bool matchStrea
   }
 }
 
+/* sizes learned from a previous step jitter from step to step; rounded up to three significant bits (steps of at
+ * most 12.5 %) they stay the same and the exact-size block cache keeps hitting */
+static unsigned long long round_up_coarse(unsigned long long x) {
+  if (x < 16) return x;
+  int shift = 0;
+  while ((x >> shift) >= 16) ++shift;
+  const unsigned long long top = ((x + ((1ull << shift) - 1)) >> shift);
+  return top << shift;
+}
+/* everything parked in the block cache of the current device goes back to the driver, and the driver's pool gives
+ * unused memory back to the system: called once by a step object after its sizes have settled */
+static void pool_trim_device() {
+  int dev = 0;
+  cudaChk(cudaGetDevice(&dev));
+  cudaChk(cudaDeviceSynchronize());
+  {
+    std::lock_guard<std::mutex> lock(g_blockMutex);
+    block_cache_flush_locked(dev, nullptr, false);
+  }
+  cudaMemPool_t pool;
+  cudaChk(cudaDeviceGetDefaultMemPool(&pool, dev));
+  cudaChk(cudaMemPoolTrimTo(pool, 0));
+}
 static void *pool_alloc(size_t bytes, cudaStream_t stream) {
   void *p = nullptr;
   if (bytes == 0) return nullptr;
@@ -1151,7 +1174,8 @@ static void build_tree_impl(const TreeInput &in, int n, int maxBucket, const dou
 
   /* nodes, level by level inside one cooperative kernel; capacity: a node holds at least one
    * particle, chains of single children are the only way past ~n/3 nodes */
-  const int cap = (int)((double)n * capFactor) + 4096; /* the kernel reports an overflow (error 1): the caller may retry with more */
+  /* the kernel reports an overflow (error 1): the caller may retry with more */
+  const int cap = (int)round_up_coarse((unsigned long long)((double)n * capFactor) + 4096ull);
   TreeArrays t;
   t.child0 = out->d_child0 = (int *)pool_alloc((size_t)cap * 4, s);
   t.child1 = out->d_child1 = (int *)pool_alloc((size_t)cap * 4, s);
@@ -1335,9 +1359,9 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
     const unsigned long long *hint = tl_walkExtras->poolHint;
     const unsigned long long c = hint[0] + hint[0] * 3 / 10 + (1u << 16), l = hint[1] + hint[1] * 3 / 10 + (1u << 16),
                              u = hint[2] + hint[2] * 3 / 10 + (1u << 16);
-    if (c < pools.capC) pools.capC = c;
-    if (l < pools.capL) pools.capL = l;
-    if (u < pools.capU) pools.capU = u;
+    if (round_up_coarse(c) < pools.capC) pools.capC = round_up_coarse(c);
+    if (round_up_coarse(l) < pools.capL) pools.capL = round_up_coarse(l);
+    if (round_up_coarse(u) < pools.capU) pools.capU = round_up_coarse(u);
   }
   pools.clist = (WalkEntry *)pool_alloc(pools.capC * sizeof(WalkEntry), s);
   pools.lplist = (WalkEntry *)pool_alloc(pools.capL * sizeof(WalkEntry), s);

@@ -196,7 +196,7 @@ struct cb200_step {
   bool haveTree = false, haveLists = false;
   /* sizes learned from the last step: node arrays (tree build) and the walk's pools, instead of their worst cases */
   double treeCapFactor = 0.0;              /* 0: not known yet */
-  unsigned long long poolHint[3] = {0, 0, 0};
+  unsigned long long poolHint[3] = {0, 0, 0}; /* capacities of the walk's pools for the next step (0: from the tree) */
   long long stepsRun = 0;
   /* locally essential moment build (let_kernels.cuh) */
   bool letOff = false;
@@ -534,8 +534,9 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
     res->treeRebuilt = 1;
   }
   if (!st->tree.error) {
-    const double f = 1.3 * (double)st->tree.numNodes / (double)n + 0.01;
-    st->treeCapFactor = f < 1.5 ? f : 1.5;
+    double f = 1.3 * (double)st->tree.numNodes / (double)n + 0.01;
+    if (f > 1.5) f = 1.5;
+    st->treeCapFactor = (st->stepsRun >= 2 && st->treeCapFactor > f) ? st->treeCapFactor : f; /* only grows once settled */
   }
   st->haveTree = true;
   cb200_tree &tr = st->tree;
@@ -748,6 +749,15 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
                              tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
                              cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
   };
+  /* next step's capacities: what this walk reserved + 30 %, rounded coarsely; after the second step (when the
+   * first step's worst-case reservation has been returned) they only grow, so that steady-state steps keep asking
+   * for the same block sizes */
+  auto learn_pools = [&]() {
+    for (int k = 0; k < 3; ++k) {
+      const unsigned long long need = round_up_coarse(extras.poolHint[k] + extras.poolHint[k] * 3 / 10 + (1u << 16));
+      st->poolHint[k] = (st->stepsRun >= 2 && st->poolHint[k] > need) ? st->poolHint[k] : need;
+    }
+  };
   const bool hinted = st->poolHint[0] != 0;
   bool small = hinted && st->lists.error == 2, outside = st->letLevel >= 0 && st->lists.error == kWalkNotBuilt;
   if (world > 1 && (hinted || st->letLevel >= 0)) agree2(small, outside, small, outside);
@@ -759,7 +769,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
     outside = st->letLevel >= 0 && st->lists.error == kWalkNotBuilt;
     if (world > 1 && st->letLevel >= 0) { bool dummy = false; agree2(outside, false, outside, dummy); }
   }
-  for (int k = 0; k < 3; ++k) st->poolHint[k] = extras.poolHint[k];
+  learn_pools();
   if (outside) {
     fprintf(stderr, "changa_b200: rank %d: the walk left the locally essential tree (block level %d); full moment build from here on\n",
             rank, st->letLevel);
@@ -772,7 +782,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
     extras.built = nullptr; extras.reduceSoftMax = nullptr;
     for (int k = 0; k < 3; ++k) extras.poolHint[k] = 0; /* the full build visits no more nodes, but be generous */
     walk();
-    for (int k = 0; k < 3; ++k) st->poolHint[k] = extras.poolHint[k];
+    learn_pools();
   }
   tl_walkExtras = nullptr;
   res->letBlockLevel = st->letLevel;

@@ -1294,7 +1294,7 @@ struct WalkExtras {
   int builtAlways = 0;
   int markEnd = 0; /* end of the level below the block level: unbuilt nodes in [builtAlways, markEnd) carry the mark */
   std::function<void(unsigned long long *d_softMaxBits, cudaStream_t)> reduceSoftMax;
-  /* in: entries of the three pools (cells, buckets, undecided) the caller expects, 0 = size from the tree;
+  /* in: capacities (entries) of the three pools (cells, buckets, undecided), 0 = sized from the tree;
    * out: entries the walk reserved.  A step sizes the pools of the next one from these */
   mutable unsigned long long poolHint[3] = {0, 0, 0};
 };
@@ -1355,13 +1355,11 @@ void cb200_walk_device_active(int numNodes, int numBuckets, int numLevels, const
   pools.capC = visited * 256 + (1u << 16) + chunkSlack;
   pools.capU = visited * 128 + (1u << 16) + chunkSlack / 4;
   pools.capL = visited * 64 + (1u << 16) + chunkSlack / 2;
-  if (tl_walkExtras && tl_walkExtras->poolHint[0]) { /* last step's use + 30 %: a third of the worst-case sizes */
+  if (tl_walkExtras && tl_walkExtras->poolHint[0]) { /* capacities the caller learned from earlier steps */
     const unsigned long long *hint = tl_walkExtras->poolHint;
-    const unsigned long long c = hint[0] + hint[0] * 3 / 10 + (1u << 16), l = hint[1] + hint[1] * 3 / 10 + (1u << 16),
-                             u = hint[2] + hint[2] * 3 / 10 + (1u << 16);
-    if (round_up_coarse(c) < pools.capC) pools.capC = round_up_coarse(c);
-    if (round_up_coarse(l) < pools.capL) pools.capL = round_up_coarse(l);
-    if (round_up_coarse(u) < pools.capU) pools.capU = round_up_coarse(u);
+    if (hint[0] < pools.capC) pools.capC = hint[0];
+    if (hint[1] < pools.capL) pools.capL = hint[1];
+    if (hint[2] < pools.capU) pools.capU = hint[2];
   }
   pools.clist = (WalkEntry *)pool_alloc(pools.capC * sizeof(WalkEntry), s);
   pools.lplist = (WalkEntry *)pool_alloc(pools.capL * sizeof(WalkEntry), s);

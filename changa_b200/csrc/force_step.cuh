@@ -524,7 +524,13 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
    * build reports an overflow; it is then repeated with the full size (rare: every rank sees the same tree, so all
    * ranks repeat together; the repeat sorts the whole box itself). */
   static const double capEnv = getenv("CB200_TREE_CAP_FACTOR") ? atof(getenv("CB200_TREE_CAP_FACTOR")) : 0.0;
-  double capFactor = st->treeCapFactor > 0.0 ? st->treeCapFactor : 0.75;
+  /* CB200_LEARN_SIZES=1 switches the learned sizes on.  Off by default: they cut the memory in use (clustered 512^3
+   * on eight ranks 134 -> 97 GB per rank, 256^3 on one GPU 34 -> 27 GB) at the same resident step time, but on the
+   * 512^3 box the end-to-end steps right after the sizes settle showed 280 ms stalls in the walk phase (the pools'
+   * reserved totals jitter with the order the warps draw their chunks, a capacity that grows is a fresh multi-GB
+   * block from the system once the first step's reservation has been returned): not measured enough to be default. */
+  static const bool learnSizes = getenv("CB200_LEARN_SIZES") && atoi(getenv("CB200_LEARN_SIZES")) != 0;
+  double capFactor = !learnSizes ? 1.5 : (st->treeCapFactor > 0.0 ? st->treeCapFactor : 0.75);
   if (capEnv > 0.0 && st->stepsRun == 0) capFactor = capEnv; /* tests: force the overflow path on the first step */
   build_tree_impl(in, n, cfg.maxBucket, cfg.rootlo, cfg.roothi, &st->tree, fine, cutWorld * S + 1, cuts, s, preKeys, preOrder,
                   capFactor);
@@ -719,7 +725,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
   nvtx_push("CUDA_SER_LIST");
   WalkExtras extras;
   static const double hintScale = getenv("CB200_POOL_HINT_SCALE") ? atof(getenv("CB200_POOL_HINT_SCALE")) : 1.0; /* tests */
-  for (int k = 0; k < 3; ++k) extras.poolHint[k] = (unsigned long long)((double)st->poolHint[k] * hintScale);
+  for (int k = 0; k < 3; ++k) extras.poolHint[k] = learnSizes ? (unsigned long long)((double)st->poolHint[k] * hintScale) : 0ull;
   tl_walkExtras = &extras;
   if (st->letLevel >= 0) {
     extras.built = st->d_letFlag;
@@ -758,7 +764,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
       st->poolHint[k] = (st->stepsRun >= 2 && st->poolHint[k] > need) ? st->poolHint[k] : need;
     }
   };
-  const bool hinted = st->poolHint[0] != 0;
+  const bool hinted = learnSizes && st->poolHint[0] != 0;
   bool small = hinted && st->lists.error == 2, outside = st->letLevel >= 0 && st->lists.error == kWalkNotBuilt;
   if (world > 1 && (hinted || st->letLevel >= 0)) agree2(small, outside, small, outside);
   if (small) {
@@ -882,7 +888,7 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
 
   st->stepsRun += 1;
   /* the second step ran with sizes learned from the first: what the first one reserved beyond that goes back */
-  if (st->stepsRun == 2) pool_trim_device();
+  if (learnSizes && st->stepsRun == 2) pool_trim_device();
   /* cost feedback for the next step's cuts: every rank learns every rank's cost and range */
   if (world > 1 && cfg.costCuts && !multistep) {
     std::vector<double> v(2 * (size_t)world, 0.0);

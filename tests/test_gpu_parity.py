@@ -636,7 +636,8 @@ def test_native_step_sfc_order_output_in_slabs(hc):
 
 
 def test_native_step_resizes_after_an_overflow(hc):
-    """cb200_step_run sizes the node arrays and the walk's pools from the last step instead of their worst cases.  A
+    """with CB200_LEARN_SIZES=1, cb200_step_run sizes the node arrays and the walk's pools from the last step instead of
+    their worst cases.  A
     first step forced to start with node arrays far too small (CB200_TREE_CAP_FACTOR, read once per process: this test
     sets it through a subprocess) reports treeRebuilt and still gives the right answer; pools scaled to a third of the
     last step's use (CB200_POOL_HINT_SCALE) make the second step repeat its walk"""
@@ -664,8 +665,8 @@ print(json.dumps({"f1": f1, "f2": f2, "same": bool(np.array_equal(a.view(np.uint
         out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout + out.stderr
         return json.loads(out.stdout.strip().splitlines()[-1])
-    plain = run({})
-    forced = run({"CB200_TREE_CAP_FACTOR": "0.05", "CB200_POOL_HINT_SCALE": "0.3"})
+    plain = run({"CB200_LEARN_SIZES": "1"})
+    forced = run({"CB200_LEARN_SIZES": "1", "CB200_TREE_CAP_FACTOR": "0.05", "CB200_POOL_HINT_SCALE": "0.3"})
     assert plain["f1"] == [0, 0] and plain["f2"] == [0, 0] and plain["same"]
     assert forced["f1"] == [1, 0] and forced["f2"][1] == 1 and forced["same"]
     assert forced["pairs"] == plain["pairs"] and forced["sum"] == plain["sum"]

@@ -855,6 +855,7 @@ void cb200_set_callback_handler(cb200_callback_fn handler) { g_handler.store(han
 void *cb200_stream_create(void) {
   cudaStream_t s;
   cudaChk(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  stream_counter(s); /* the bucket counter of this stream exists before anything can be captured on it */
   return (void *)s;
 }
 void cb200_stream_destroy(void *stream) {

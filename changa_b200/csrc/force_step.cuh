@@ -737,9 +737,12 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
       ncclChk(nccl_api()->AllReduce(d_bits, d_bits, 1, ncclUint64, ncclMax, st->comm->comm, ws));
     };
   }
-  cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
-                           tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
-                           cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
+  auto walk = [&]() {
+    cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
+                             tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
+                             cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
+  };
+  walk();
   /* Two things can make a walk worth repeating, and with several ranks both are decided TOGETHER (the walk of a
    * locally essential step contains a collective, and the next step's exchange needs every rank): the pools,
    * sized from the last step, were too small on some rank -> once more with worst-case sizes; the walk met a node
@@ -749,11 +752,6 @@ void cb200_step_run(cb200_step *st, const double *h_records, const unsigned char
     double v[2] = {a ? 1.0 : 0.0, b ? 1.0 : 0.0};
     if (world > 1) cb200_comm_allreduce_f64(st->comm, v, 2, 1, s);
     ra = v[0] > 0.0; rb = v[1] > 0.0;
-  };
-  auto walk = [&]() {
-    cb200_walk_device_active(nn, nb, tr.numLevels, tr.levelStart, tr.d_child0, tr.d_child1, tr.d_parent, tr.d_first, tr.d_last,
-                             tr.d_bucketFirst, tr.d_bucketCount, tr.d_bucketNode, tr.d_boxlo, tr.d_boxhi, st->d_mom64, cfg.theta,
-                             cfg.nReplicas, cfg.period, b0, b1, bucketActive, &st->lists, s);
   };
   /* next step's capacities: what this walk reserved + 30 %, rounded coarsely; after the second step (when the
    * first step's worst-case reservation has been returned) they only grow, so that steady-state steps keep asking

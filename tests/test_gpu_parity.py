@@ -635,6 +635,47 @@ def test_native_step_sfc_order_output_in_slabs(hc):
     assert np.array_equal(dev.view(np.uint32), rows.view(np.uint32))
 
 
+def test_full_size_box_properties(hc):
+    """BASELINE config 3 at its full size (uniform 256^3 = 16 777 216 particles, ppartt.c recipe, seed 1), where the
+    oracle is out of reach for the whole box: size-independent properties of cb200_step_run instead.
+      - the tree and the lists are the ones every earlier measurement of this box saw (node, bucket, level and
+        pair-interaction counts: the lists are integer work, so the totals are exact);
+      - a second run of the same step returns the same bits;
+      - linearity: every mass doubled (an exact operation in binary floating point, which commutes with every
+        product and sum on the path and leaves the geometry -- keys, tree, opening tests, lists -- alone)
+        doubles every acceleration and potential bit for bit;
+      - the net force on the box vanishes to the accuracy of the expansion (Newton's third law holds pairwise
+        for p-p, to the multipole error for p-c)."""
+    from changa_b200.step import NativeStep
+    from changa_b200.workloads import uniform_box
+    n = 1 << 24
+    pos, mass, soft = uniform_box(n, seed=1)
+    st = NativeStep(hc, n, theta=0.7, n_replicas=1, period=1.0, ewald={"dEwCut": 2.6, "dEwhCut": 2.8})
+    try:
+        st.set_particles(pos, float(mass[0]), float(soft[0]))
+        res = st.run(sfc_order=True)
+        assert res.error == 0 and res.rows == n
+        assert (res.numNodes, res.numBuckets, res.numLevels) == (4058668, 2029302, 25)
+        assert (res.pcPairs, res.ppPairs) == (6542767976, 4301107563)
+        idx, rows = st.idx.array[:n].copy(), st.out.array[:n].copy()
+        res = st.run(sfc_order=True)
+        again = st.out.array[:n].copy()
+        assert np.array_equal(st.idx.array[:n], idx)
+        st.set_particles(pos, 2.0 * float(mass[0]), float(soft[0]))
+        res2 = st.run(sfc_order=True)
+        assert (res2.pcPairs, res2.ppPairs) == (res.pcPairs, res.ppPairs)
+        doubled = st.out.array[:n].copy()
+        assert np.array_equal(st.idx.array[:n], idx)
+    finally:
+        st.free()
+    assert np.isfinite(rows).all()
+    assert np.array_equal(rows.view(np.uint32), again.view(np.uint32))
+    assert np.array_equal((2.0 * rows[:, :4]).view(np.uint32), doubled[:, :4].view(np.uint32))
+    a = rows[:, :3].astype(np.float64)
+    net = np.linalg.norm(a.sum(axis=0))
+    assert net <= 1e-3 * np.linalg.norm(a, axis=1).sum(), net
+
+
 def test_native_step_resizes_after_an_overflow(hc):
     """with CB200_LEARN_SIZES=1, cb200_step_run sizes the node arrays and the walk's pools from the last step instead of
     their worst cases.  A

@@ -635,6 +635,39 @@ def test_native_step_sfc_order_output_in_slabs(hc):
     assert np.array_equal(dev.view(np.uint32), rows.view(np.uint32))
 
 
+def test_emulated_ranks_tile_the_single_gpu_step(hc, monkeypatch):
+    """the sharding of a multi-GPU step on ONE GPU: CB200_EMULATE_RANK=r/N makes cb200_step_run do rank r's share
+    (tree and moments whole, lists / forces / Ewald of its SFC bucket range only).  The shares tile the box, their
+    pair counts add up to the whole step's, and every share's rows are the whole step's rows bit for bit --
+    what the 2-rank NCCL test and the bench line's parity_vs_n1 check on real ranks."""
+    from changa_b200.step import NativeStep
+    from changa_b200.workloads import uniform_box
+    n = 300000 + 123
+    pos, mass, soft = uniform_box(n, seed=5)
+    st = NativeStep(hc, n, theta=0.7, n_replicas=1, period=1.0, ewald={"dEwCut": 2.6, "dEwhCut": 2.8})
+    try:
+        st.set_particles(pos, float(mass[0]), float(soft[0]))
+        res = st.run(sfc_order=True)
+        assert res.rows == n
+        whole_pairs = (res.pcPairs, res.ppPairs)
+        idx, rows = st.idx.array[:n].copy(), st.out.array[:n].copy()
+        at, pc, pp = 0, 0, 0
+        for r in range(3):
+            monkeypatch.setenv("CB200_EMULATE_RANK", f"{r}/3")
+            res = st.run(sfc_order=True)
+            assert res.partLo == at and res.rows == res.partHi - res.partLo and res.rows > 0
+            k = res.rows
+            assert np.array_equal(st.idx.array[:k], idx[at:at + k])
+            assert np.array_equal(st.out.array[:k].view(np.uint32), rows[at:at + k].view(np.uint32))
+            at += k
+            pc += res.pcPairs
+            pp += res.ppPairs
+        assert at == n and (pc, pp) == whole_pairs
+    finally:
+        monkeypatch.delenv("CB200_EMULATE_RANK", raising=False)
+        st.free()
+
+
 def test_full_size_box_properties(hc):
     """BASELINE config 3 at its full size (uniform 256^3 = 16 777 216 particles, ppartt.c recipe, seed 1), where the
     oracle is out of reach for the whole box: size-independent properties of cb200_step_run instead.

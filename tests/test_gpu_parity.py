@@ -635,6 +635,65 @@ def test_native_step_sfc_order_output_in_slabs(hc):
     assert np.array_equal(dev.view(np.uint32), rows.view(np.uint32))
 
 
+def _direct_sum(pos, mass, soft):
+    """double direct sum with the spline of gravity.h:147-182 (the oracle's pair routine; one list of every
+    particle per target), on the inputs as the float kernels see them"""
+    n = len(pos)
+    parts = np.ascontiguousarray(np.column_stack([np.full(n, mass), np.full(n, soft), pos]).astype(np.float32).astype(np.float64))
+    il = np.zeros((n, 2), dtype=np.int32)
+    il[:, 0] = np.arange(n)
+    il[:, 1] = 0xDB << 22
+    v = np.zeros((n, 5))
+    orc.part_list(parts, parts, np.ascontiguousarray(np.tile(il, (n, 1))), (np.arange(n + 1) * n).astype(np.int32),
+                  np.arange(n, dtype=np.int32), np.ones(n, dtype=np.int32), 0.0, v)
+    return v
+
+
+@pytest.mark.parametrize("case", ["1", "2", "12", "13", "100", "1000", "same50", "pair_in_soft"])
+def test_step_on_tiny_and_degenerate_particle_sets(hc, case):
+    """cb200_step_run at the small end (open boundary): one particle (no force), two, exactly one bucket (12), one
+    more than a bucket (13: the first split), a few buckets, 50 particles at ONE point (keys cannot split them: a
+    61-level chain ending in one oversized bucket; every pair is at zero distance and skipped, HostCUDA.cu:1665),
+    and a pair inside each other's softening length (the spline fix-up path).  Against a double direct sum:
+    rounding level where the lists hold particles only, the expansion's error where cells appear."""
+    from changa_b200.step import NativeStep
+    rng = np.random.default_rng(11)
+    soft = 1e-4
+    if case == "same50":
+        n = 50
+        pos = np.tile(np.array([[0.1, -0.2, 0.3]]), (n, 1))
+    elif case == "pair_in_soft":
+        n = 40
+        pos = rng.uniform(-0.45, 0.45, (n, 3))
+        pos[1] = pos[0] + 0.3 * soft
+    else:
+        n = int(case)
+        pos = rng.uniform(-0.45, 0.45, (n, 3))
+    mass = 1.0 / n
+    st = NativeStep(hc, n, theta=0.7, n_replicas=0, period=1.0, ewald=None)
+    try:
+        st.set_particles(pos, mass, soft)
+        res = st.run()
+        got = st.out.array[:n].astype(np.float64).copy()
+        pc, pp, buckets = res.pcPairs, res.ppPairs, res.numBuckets
+    finally:
+        st.free()
+    assert np.isfinite(got).all()
+    want = _direct_sum(pos, mass, soft)
+    if case in ("1", "same50"):
+        assert buckets == 1 and pp == n * n and pc == 0
+        assert np.array_equal(got[:, :4], np.zeros((n, 4)))
+        return
+    rms = np.sqrt((want[:, :3] ** 2).sum(1).mean())
+    err = np.sqrt(((got[:, :3] - want[:, :3]) ** 2).sum(1)).max() / rms
+    perr = (np.abs(got[:, 3] - want[:, 3]) / np.abs(want[:, 3])).max()
+    if pc == 0:  # particle lists only: every pair is evaluated
+        assert pp == n * n
+        assert err <= 5e-6 and perr <= 2e-6, (err, perr)
+    else:
+        assert err <= 2e-2 and perr <= 1e-3, (err, perr)
+
+
 def test_emulated_ranks_tile_the_single_gpu_step(hc, monkeypatch):
     """the sharding of a multi-GPU step on ONE GPU: CB200_EMULATE_RANK=r/N makes cb200_step_run do rank r's share
     (tree and moments whole, lists / forces / Ewald of its SFC bucket range only).  The shares tile the box, their

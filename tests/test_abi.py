@@ -110,3 +110,15 @@ def test_reference_headers_translation_unit_runs_requests_on_the_gpu():
     r = subprocess.run([LINK_TEST], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "-> ok" in r.stdout, r.stdout
+
+
+def test_every_environment_switch_is_documented():
+    """INTEGRATION.md's table names every CB200_* variable the library reads"""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    read = set()
+    for f in glob.glob(os.path.join(root, "changa_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(root, "changa_b200", "csrc", "*.cpp")):
+        read |= set(re.findall(r'getenv\("(CB200_[A-Z0-9_]+)"\)', open(f).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert read and not [v for v in sorted(read) if v not in doc]

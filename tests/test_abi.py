@@ -4,6 +4,7 @@ reference's own HostCUDA.cu produces (HostCUDA.h:99-126, EwaldCUDA.h:59-62, Cuda
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -122,3 +123,21 @@ def test_every_environment_switch_is_documented():
         read |= set(re.findall(r'getenv\("(CB200_[A-Z0-9_]+)"\)', open(f).read()))
     doc = open(os.path.join(root, "INTEGRATION.md")).read()
     assert read and not [v for v in sorted(read) if v not in doc]
+
+
+def test_the_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under changa_b200/ imports, links or loads it, importing the package
+    does not pull it in, and bench.py reaches it only from its checker / CPU-baseline legs"""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "changa_b200")
+    for f in glob.glob(os.path.join(pkg, "**", "*"), recursive=True):
+        if os.path.isfile(f) and f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+            text = open(f, errors="replace").read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+            assert "liboracle" not in text and "oracle/_ref" not in text and "gravity_oracle" not in text, f
+    code = ("import sys; import changa_b200, changa_b200.hostcuda, changa_b200.step, changa_b200.device_step; "
+            "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; assert not bad, bad")
+    subprocess.check_call([sys.executable, "-c", code], cwd=root)
+    bench = open(os.path.join(root, "bench.py")).read()
+    assert not re.search(r"^(from|import)\s+oracle\b", bench, re.M)  # only inside the functions of its CPU legs

@@ -141,3 +141,26 @@ def test_the_product_never_touches_the_oracle():
     subprocess.check_call([sys.executable, "-c", code], cwd=root)
     bench = open(os.path.join(root, "bench.py")).read()
     assert not re.search(r"^(from|import)\s+oracle\b", bench, re.M)  # only inside the functions of its CPU legs
+
+
+def test_a_missing_library_or_device_fails_loudly():
+    """no CPU fallback anywhere: without the built library the loader raises, and without a CUDA device the first
+    entry point that needs one ends the process with a message (this container has no GPU; on a GPU box the second
+    half is skipped)"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CB200_LIB="/nonexistent/libchanga_b200.so")
+    code = ("from changa_b200 import lib\n"
+            "try:\n    lib.load()\nexcept lib.LibraryMissing as e:\n    print('missing:', e)\nelse:\n    raise SystemExit(3)\n")
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True)
+    assert p.returncode == 0 and "no CPU fallback" in p.stdout, (p.returncode, p.stdout, p.stderr)
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    code = "from changa_b200.hostcuda import HostCUDA\nHostCUDA(double=False, device=0)\nprint('survived')\n"
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
+    assert p.returncode != 0 and "survived" not in p.stdout, (p.returncode, p.stdout)
+    assert "CUDA" in p.stderr or "cuda" in p.stderr, p.stderr[-400:]

@@ -21,7 +21,10 @@ softened cells -> Ewald [-> rows back in the caller's order].
             accelerations inside the timed region, wall clock, max over ranks
   roofline  the p-c kernel (and the p-p kernel) against the measured FP32 FMA peak, 198 / 30 flop per pair
   parity    buckets re-evaluated by the CPU oracle from the step's own lists and moments: median / max |da|/|a|
-  cpu_baseline / --impl reference   the oracle port on the host cores, on a bounded bucket range
+  cpu_baseline                      the oracle port on the host cores, on a bounded bucket range of the step's own lists
+  --impl reference                  the reference's OWN CPU gravity (gravity.h / Ewald.cpp compiled unmodified into
+                                    oracle/_ref/libgravity_ref.so; kind "reference") on all host cores, on a bounded
+                                    bucket range of the same box; the oracle port where that library is absent
   ref_cuda  the reference's own HostCUDA.cu kernels (compiled unmodified) on the same requests, next to
             this library's reference-facing entry points on them
 
@@ -250,12 +253,13 @@ def parity_block(st, prod, orc, period, n_reps, rng_buckets, n_runs=16, run_len=
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the CPU port on the host cores, CPU only
+# reference arm: the reference's own CPU gravity (or the port of it) on the host cores, CPU only
 # ------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """oracle port (kind "port": gravity.h / Ewald.cpp need Charm++ and do not compile here) with all host
-    threads on a bounded bucket range of the same box; tree and lists from the host walk
-    (changa_b200/csrc/treewalk.cpp) -- no GPU is touched.  Rank 0 only."""
+    """the reference's own CPU gravity (kind "reference": gravity.h / Ewald.cpp compiled unmodified into
+    oracle/_ref/libgravity_ref.so; the oracle port, kind "port", where that library is absent) with all host threads
+    on a bounded bucket range of the same box; tree and lists from the host walk (changa_b200/csrc/treewalk.cpp) --
+    no GPU is touched.  Rank 0 only."""
     if rank != 0:
         return
     from oracle import oracle as orc
@@ -288,13 +292,26 @@ def run_reference(args, rank, world):
 
     v = np.zeros((n, 5))
 
-    def step():
+    def port_step():
         v[act] = 0.0
         orc.cell_list(parts, mom, *cell, 1.0, v)
         orc.part_list(parts, parts, *part, 1.0, v)
         if soft_l:
             orc.part_list(parts, node_parts, *soft_l, 1.0, v)
         orc.ewald(parts, act, t.moments[0], momc, 1.0, EWALD["dEwCut"], 1, int(np.ceil(EWALD["dEwCut"])), 1.2e-3, ewt, v)
+
+    # kind "reference": the reference's OWN nodeBucketForce / partBucketForce / BucketEwald (gravity.h and Ewald.cpp
+    # compiled unmodified into oracle/_ref/libgravity_ref.so, which travels with the repo) on the same lists, OpenMP
+    # over buckets; the oracle port is the fallback where that library was never built
+    kind_ran, step, check = "port", port_step, None
+    if not args.ref_port and orc.ref_gravity() is not None:
+        rs = orc.ReferenceStep(t, 1.0, ewald=EWALD, n_replicas=1)
+        kind_ran, step = "reference", (lambda: rs.run(w, b0, b1, threads=threads))
+        step()
+        port_step()
+        got, want = rs.vars(int(act[0]), int(act[-1]) + 1), v[int(act[0]):int(act[-1]) + 1]
+        amag = np.maximum(np.linalg.norm(want[:, :3], axis=1), 1e-300)
+        check = float((np.linalg.norm(got[:, :3] - want[:, :3], axis=1) / amag).max())  # port vs reference: rounding level
 
     for _ in range(max(1, min(args.warmup, 2))):
         step()
@@ -310,9 +327,13 @@ def run_reference(args, rank, world):
         "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(kind, n), "theta": THETA, "expansion": "hexadecapole", "bucket_size": BUCKET,
-                   "note": "CPU restatement of nodeBucketForce / partBucketForce / BucketEwald (OpenMP over buckets) on lists "
-                           "from the host walk; the same box as the GPU arm, a bounded bucket range per step"},
-        "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": threads, "kind": "port", "sample": sample},
+                   "note": ("the reference's own nodeBucketForce / partBucketForce / BucketEwald (gravity.h, Ewald.cpp compiled "
+                            "unmodified, scalar double path; oracle/_ref/libgravity_ref.so)" if kind_ran == "reference" else
+                            "CPU restatement of nodeBucketForce / partBucketForce / BucketEwald") +
+                           ", OpenMP over buckets, on lists from the host walk; the same box as the GPU arm, a bounded bucket "
+                           "range per step",
+                   "port_vs_reference_max_da_over_a": check},
+        "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": threads, "kind": kind_ran, "sample": sample},
         "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -518,6 +539,7 @@ def main():
     ap.add_argument("--target-n", type=int, default=1 << 27)
     ap.add_argument("--cpu-pairs", type=float, default=2.5e9, help="pair interactions of the cpu_baseline sample")
     ap.add_argument("--ref-pairs", type=float, default=6e8, help="pair interactions per step of --impl reference")
+    ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port even where oracle/_ref/libgravity_ref.so exists")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

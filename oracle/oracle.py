@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 _REF_MOM = None
+_REF_GRAV = None
 
 FM_N, MC_N, CM_N = 22, 32, 27
 dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -88,6 +89,79 @@ def ref_moments():
         L.momEvalFmomrcm.argtypes = [dp, d, d, d, d, d, dp, dp, dp, dp, dp]
         _REF_MOM = L
     return _REF_MOM
+
+
+def ref_gravity():
+    """oracle/_ref/libgravity_ref.so: the reference's own gravity.h (SPLINE, partBucketForce, nodeBucketForce,
+    openSoftening, openCriterionBucket / Node) and Ewald.cpp (EwaldInit, BucketEwald) compiled unmodified through
+    oracle/gravity_ref.cpp / ewald_ref.cpp, with the reference's moments.c linked in.  Returns None where it has not been built (no /root/reference)."""
+    global _REF_GRAV
+    if _REF_GRAV is None:
+        so = os.path.join(HERE, "_ref", "libgravity_ref.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        d, i, vp = C.c_double, C.c_int, C.c_void_p
+        L.gref_set_theta.argtypes = [d, d]
+        L.gref_spline.argtypes = [d, d, dp, dp]
+        L.gref_splineq.argtypes = [d, d, d, dp]
+        L.gref_part_bucket_force.argtypes = [dp, dp, dp, i, i, vp, i, dp]
+        L.gref_part_bucket_force.restype = i
+        L.gref_node_bucket_force.argtypes = [dp, dp, dp, dp, dp, dp, i, i, vp, i, dp]
+        L.gref_node_bucket_force.restype = i
+        L.gref_open_softening.argtypes = [dp, dp, dp, dp, dp]
+        L.gref_open_softening.restype = i
+        L.gref_open_criterion_node.argtypes = [dp, i, dp, dp, dp, dp, i]
+        L.gref_open_criterion_node.restype = i
+        L.gref_open_criterion_bucket.argtypes = [dp, i, dp, dp, dp, dp]
+        L.gref_open_criterion_bucket.restype = i
+        L.gref_build_moments.argtypes = [dp, dp, dp, ip, ip, ip, ip, dp, dp, dp, dp, i, dp]
+        lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+        L.gref_step_create.argtypes = [dp, i, dp, i, ip, i, dp, dp, ip, ip, d, i, d, d, i]
+        L.gref_step_create.restype = vp
+        L.gref_step_run.argtypes = [vp, i, i, ip, lp, ip, lp, ip, lp, i]
+        L.gref_step_vars.argtypes = [vp, i, i, dp]
+        L.gref_step_destroy.argtypes = [vp]
+        L.eref_init.argtypes = [dp, d, d, dp, dp, i]
+        L.eref_init.restype = i
+        L.eref_bucket_ewald.argtypes = [dp, d, d, d, i, dp, i, i, vp, i, dp]
+        _REF_GRAV = L
+    return _REF_GRAV
+
+
+class ReferenceStep:
+    """one force evaluation by the reference's own CPU routines (nodeBucketForce, partBucketForce, BucketEwald of
+    gravity.h / Ewald.cpp compiled unmodified: oracle/ewald_ref.cpp::gref_step_*), on a tree given as flat arrays
+    (changa_b200.tree.Tree) and the per-bucket lists of its walk.  OpenMP over buckets."""
+
+    def __init__(self, tree, period, ewald=None, n_replicas=0):
+        G = ref_gravity()
+        assert G is not None, "oracle/_ref/libgravity_ref.so needs /root/reference at build time"
+        self.G, self.t = G, tree
+        ew = ewald or {}
+        self._keep = [as_f64(tree.parts), as_f64(tree.moments), as_i32(tree.bucket_node), as_f64(tree.boxlo).reshape(-1),
+                      as_f64(tree.boxhi).reshape(-1), as_i32(tree.first), as_i32(tree.last)]
+        k = self._keep
+        self.h = G.gref_step_create(k[0].reshape(-1), len(tree.parts), k[1].reshape(-1), len(tree.child0), k[2], len(tree.bucket_node),
+                                    k[3], k[4], k[5], k[6], float(period), 1 if ewald is not None else 0,
+                                    float(ew.get("dEwhCut", 2.8)), float(ew.get("dEwCut", 2.6)), int(n_replicas))
+
+    def run(self, walk, b0, b1, threads=1):
+        """walk: the dict Tree.walk returns (cell / part / soft with markers over all buckets)"""
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
+        self.G.gref_step_run(self.h, int(b0), int(b1), i32(walk["cell"]), i64(walk["cell_mark"]), i32(walk["part"]),
+                             i64(walk["part_mark"]), i32(walk["soft"]), i64(walk["soft_mark"]), int(threads))
+
+    def vars(self, p0, p1):
+        out = np.zeros((p1 - p0, 5))
+        self.G.gref_step_vars(self.h, int(p0), int(p1), out.reshape(-1))
+        return out
+
+    def free(self):
+        if self.h:
+            self.G.gref_step_destroy(self.h)
+            self.h = None
 
 
 # ---- array helpers ---------------------------------------------------------

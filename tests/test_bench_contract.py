@@ -51,3 +51,25 @@ def test_bench_command_line_is_the_contract():
     h = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, check=True).stdout
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in h, flag
+
+
+def test_reference_arm_runs_the_reference_own_cpu_gravity():
+    """`bench.py --impl reference` on a small box: one JSON line with the arm's keys; kind "reference" (the
+    reference's own gravity.h / Ewald.cpp compiled unmodified) where oracle/_ref/libgravity_ref.so exists, and the
+    oracle port with --ref-port -- which agree to rounding"""
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgravity_ref.so"))
+    lines = {}
+    for flag in ([], ["--ref-port"]):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "262144", "--steps", "1",
+                            "--warmup", "1", "--ref-pairs", "2e7"] + flag, capture_output=True, text=True, check=True, cwd=ROOT)
+        out = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        assert len(out) == 1
+        j = json.loads(out[0])
+        assert j["impl"] == "reference" and j["metric"] == "gravity_interactions_per_s" and j["value"] > 0
+        assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert j["cpu_baseline"]["value"] == j["value"] and j["cpu_baseline"]["cores"] >= 1
+        lines[bool(flag)] = j
+    assert lines[True]["cpu_baseline"]["kind"] == "port"
+    assert lines[False]["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    if have_ref:
+        assert lines[False]["config"]["port_vs_reference_max_da_over_a"] < 1e-9

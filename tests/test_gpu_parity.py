@@ -635,6 +635,59 @@ def test_native_step_sfc_order_output_in_slabs(hc):
     assert np.array_equal(dev.view(np.uint32), rows.view(np.uint32))
 
 
+def reference_cpu_golden_workload():
+    """the known answers of the reference's own CPU gravity (gravity.h compiled unmodified: nodeBucketForce,
+    partBucketForce; tests/golden/gravity_kat.npz, inputs float-representable) as ONE list workload: every golden
+    case is a 12-particle bucket with a one-entry list -- a hexadecapole cell (cases whose cell acts as a softened
+    particle are left to the p-p cases; cells closer than two of their radii, where no walk would accept them, are
+    left out) or a source particle (appended behind the targets).  Returns (workload, expected rows)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gravity_kat.npz"))
+    code = lambda sh: ((int(sh[0]) + 3) | ((int(sh[1]) + 3) << 3) | ((int(sh[2]) + 3) << 6)) << 22
+    parts, want, cells, cl, pl, pb_src = [], [], [], [], [], []
+    nbk = 0
+    for cell, shift, part, out, soft in zip(g["nb_cell"], g["nb_shift"], g["nb_part"], g["nb_out"], g["nb_soft"]):
+        d = np.sqrt(((part[:, 2:] - (cell[3:6] + shift)) ** 2).sum(1)).min()
+        if soft or d < 2.0 * cell[0]:
+            continue
+        cl.append((len(cells), code(shift)))
+        cells.append(cell); parts.append(part); want.append(out)
+        nbk += 1
+    n_pc = nbk
+    for part, src, shift, vin, out in zip(g["pb_part"], g["pb_src"], g["pb_shift"], g["pb_in"], g["pb_out"]):
+        if np.any(vin != 0):
+            continue      # a request starts from zeroed accumulators (ZeroVars)
+        pl.append((len(pb_src), code(shift)))
+        pb_src.append(src); parts.append(part); want.append(out)
+        nbk += 1
+    n_targets = 12 * nbk
+    parts = np.concatenate(parts + [np.array(pb_src)])
+    want = np.concatenate(want + [np.zeros((len(pb_src), 5))])
+    as_list = lambda rows, base: np.array([(base + i, c) for i, c in rows], dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, 2)
+    starts = (12 * np.arange(nbk)).astype(np.int32)
+    sizes = np.full(nbk, 12, dtype=np.int32)
+    wl = {"parts": parts, "moments": np.array(cells), "fperiod": 1.0, "ewald": None, "name": "reference CPU golden",
+          "cell": (as_list(cl, 0), np.arange(n_pc + 1, dtype=np.int32), starts[:n_pc].copy(), sizes[:n_pc].copy()),
+          "part": (as_list(pl, n_targets), np.arange(nbk - n_pc + 1, dtype=np.int32), starts[n_pc:].copy(), sizes[n_pc:].copy())}
+    return wl, want, n_pc, nbk - n_pc
+
+
+def test_cuda_path_against_the_reference_cpu_golden(hc):
+    """the CUDA list kernels, through the C ABI, against outputs of the REFERENCE's own CPU code (not the oracle):
+    nodeBucketForce / partBucketForce of gravity.h compiled unmodified (oracle/gravity_ref.cpp), carried here as
+    golden vectors; replica shifts, pairs inside the softening length and coincident pairs included"""
+    from changa_b200.hostcuda import ForceStep
+    wl, want, n_pc, n_pp = reference_cpu_golden_workload()
+    assert n_pc > 200 and n_pp > 60
+    assert np.array_equal(oracle_forces(wl, np_real=np.float64), want)   # the oracle on the same workload: bit for bit
+    step = ForceStep(hc, wl)
+    try:
+        got = step.run().copy()
+    finally:
+        step.free()
+    compare(got, want)
+
+
 def _direct_sum(pos, mass, soft):
     """double direct sum with the spline of gravity.h:147-182 (the oracle's pair routine; one list of every
     particle per target), on the inputs as the float kernels see them"""

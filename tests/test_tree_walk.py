@@ -203,3 +203,45 @@ def test_config_workload_shards_buckets():
     assert n0 + n1 == 16 ** 3 and abs(int(n0) - int(n1)) <= 24
     assert np.array_equal(wl0["parts"], wl1["parts"])
     assert len(wl0["ewald"]["active"]) == n0
+
+
+def test_walk_decisions_by_the_reference_gravity_h():
+    """the sequential walk with every opening decision taken by the REFERENCE's own openCriterionNode /
+    openSoftening (gravity.h compiled unmodified, oracle/_ref/libgravity_ref.so) builds the same lists as with the
+    oracle's restatements, and so does the product's host walk -- on a clustered periodic tree with softened cells
+    (live: needs /root/reference; the golden vectors of tests/golden/gravity_kat.npz carry the pin elsewhere)"""
+    G = orc.ref_gravity()
+    if G is None:
+        pytest.skip("oracle/_ref/libgravity_ref.so needs /root/reference")
+
+    class ReferenceDecisions(SequentialWalk):
+        calls = 0
+
+        def open_criterion(self, node, my, shift):
+            ReferenceDecisions.calls += 1
+            return G.gref_open_criterion_node(self.mom[node], int(self.last[node] - self.first[node] + 1),
+                                              np.ascontiguousarray(shift), self.mom[my], self.boxlo[my], self.boxhi[my],
+                                              int(self.is_bucket(my)))
+
+        def open_softening(self, node, my, shift):
+            return G.gref_open_softening(self.mom[node], np.ascontiguousarray(shift), self.mom[my], self.boxlo[my],
+                                         self.boxhi[my])
+
+    pos, mass, s = particles(1500, 21, soft=0.02)
+    t = Tree(pos, mass, s, max_bucket=8)
+    theta = 0.7
+    G.gref_set_theta(theta, theta ** 4)
+    args = (t.child0, t.child1, t.first, t.last, t.boxlo, t.boxhi, t.moments, t.bucket_node, theta, 1, 1.0)
+    ref = ReferenceDecisions(*args).run()
+    ours = SequentialWalk(*args).run()
+    assert ReferenceDecisions.calls > 50000
+    assert ref == ours
+    w = t.walk(theta=theta, n_replicas=1, period=1.0)
+    nsoft = 0
+    for b in range(t.num_buckets):
+        rc, rp, rs = ref[b]
+        assert np.array_equal(w["cell"][w["cell_mark"][b]:w["cell_mark"][b + 1]], _as_i32(rc, 2)), b
+        assert np.array_equal(w["part"][w["part_mark"][b]:w["part_mark"][b + 1]], _as_i32(rp, 3)), b
+        assert np.array_equal(w["soft"][w["soft_mark"][b]:w["soft_mark"][b + 1]], _as_i32(rs, 2)), b
+        nsoft += len(rs)
+    assert nsoft > 0

@@ -21,7 +21,10 @@ softened cells -> Ewald [-> rows back in the caller's order].
             accelerations inside the timed region, wall clock, max over ranks
   roofline  the p-c kernel (and the p-p kernel) against the measured FP32 FMA peak, 198 / 30 flop per pair
   parity    buckets re-evaluated by the CPU oracle from the step's own lists and moments: median / max |da|/|a|
-  cpu_baseline                      the oracle port on the host cores, on a bounded bucket range of the step's own lists
+  cpu_baseline                      the reference's own CPU gravity (kind "reference": the --impl reference arm as a
+                                    CPU-only subprocess on a bounded bucket range of the same box, all host cores), with
+                                    the oracle port on a bucket range of the step's own lists next to it ("port": also the
+                                    fallback, and the parity_range check)
   --impl reference                  the reference's OWN CPU gravity (gravity.h / Ewald.cpp compiled unmodified into
                                     oracle/_ref/libgravity_ref.so; kind "reference") on all host cores, on a bounded
                                     bucket range of the same box; the oracle port where that library is absent
@@ -338,6 +341,32 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
+def reference_cpu_baseline(pairs, kind, n, timeout=600):
+    """cpu_baseline of kind "reference" for the GPU arm's line: the reference arm (this file, `--impl reference`:
+    the reference's own gravity.h / Ewald.cpp compiled unmodified, all host cores) run as a CPU-only subprocess on a
+    bounded bucket range of the same box.  None when it is not available (no oracle/_ref/libgravity_ref.so) or fails:
+    the caller then keeps the oracle port's numbers."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgravity_ref.so")):
+        return None
+    wl = [k for k, v in WORKLOADS.items() if v[0] == kind]
+    if not wl:
+        return None
+    try:
+        env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", wl[0], "--n", str(n),
+                            "--steps", "1", "--warmup", "1", "--ref-pairs", str(pairs)], capture_output=True, text=True,
+                           timeout=timeout, env=env, cwd=ROOT)
+        line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        j = json.loads(line[-1])
+        c = j["cpu_baseline"]
+        if c.get("kind") != "reference" or not c.get("value"):
+            return None
+        return {"value": c["value"], "unit": c["unit"], "cores": c["cores"], "kind": "reference", "seconds": j["ms_per_step"] * 1e-3,
+                "sample": c["sample"] + "; " + j["config"]["note"]}
+    except Exception:
+        return None
+
+
 def workload_name(kind, n):
     side = round(n ** (1.0 / 3.0))
     cube = f"{side}^3 = " if side ** 3 == n else ""
@@ -450,6 +479,9 @@ def bench_box(hc, comm, kind, n, steps, warmup, local, want_parity=True, want_cp
                                    "kind": "port", "seconds": dt,
                                    "sample": f"buckets [{b0}, {b0 + span}) of {res.numBuckets}: {len(idx)} particles, {pairs} pair "
                                              f"interactions + their Ewald sums, one pass of the oracle port (OpenMP over buckets)"}
+            ref = reference_cpu_baseline(min(cpu_pairs, 1e9), kind, n)
+            if ref is not None:  # the reference's own CPU code did the same kind of sample: that is the baseline
+                out["cpu_baseline"] = dict(ref, port=out["cpu_baseline"])
             out["parity_range"] = parity_stats(prod.vars[idx], rows)
             out["parity_range"]["buckets"] = span
             if want_refcuda:

@@ -14,11 +14,12 @@
  *
  * gravity.h includes four headers.  Three exist in the reference and pull in Charm++ (TreeNode.h,
  * GenericTreeNode.h, SSEdefs.h): their include guards are defined below, so the preprocessor skips them, and the
- * handful of declarations gravity.h needs from them are given here with the reference's names and meanings -- field
- * names as in GravityParticle.h / MultipoleMoments.h / GenericTreeNode.h, node types as GenericTreeNode.h:39-51,
- * opening_geometry_factor as TreeNode.h:35.  The fourth, Space.h, belongs to the absent utility/structures
- * submodule: oracle/shim/gravity/Space.h.  The scalar (non-SSE) code path is the one compiled: CMK_SSE = 0, as in a
- * build without --enable-sse2; cosmoType is double (cosmoType.h without COSMO_FLOAT). */
+ * handful of declarations gravity.h needs from them are given in oracle/shim/gravity/reference_types.h with the
+ * reference's names and meanings -- field names as in GravityParticle.h / GenericTreeNode.h, node types as
+ * GenericTreeNode.h:39-51, opening_geometry_factor as TreeNode.h:35; MultipoleMoments is the reference's own class
+ * (MultipoleMoments.h, unmodified).  The fourth, Space.h, belongs to the absent utility/structures submodule:
+ * oracle/shim/gravity/Space.h.  The scalar (non-SSE) code path is the one compiled: CMK_SSE = 0, as in a build
+ * without --enable-sse2; cosmoType is double (cosmoType.h without COSMO_FLOAT). */
 #define TREENODE_H
 #define GENERICTREENODE_H
 #define __SSEDEFS_H__

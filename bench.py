@@ -562,7 +562,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uniform256", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="particles of the box (default: the workload's own size)")
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=0,
+                    help="particles of the box (default: the workload's own size); under torchrun use --particles "
+                         "(its parser takes --n for an abbreviation of its own options)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
